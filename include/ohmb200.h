@@ -1,0 +1,226 @@
+/*
+ * ohmb200.h — C ABI of libohmb200.so: B200-native (sm_100a) batched ray integration for ohm maps.
+ *
+ * This is the drop-in boundary for ohm's GPU ray-integration path.  Each entry point cites the
+ * reference interface it replaces (paths relative to csiro-robotics/ohm @ 4e2e769).  The C++ facade in
+ * include/ohmb200/GpuMap.hpp (ohm::RayMapper / GpuMap / GpuNdtMap / GpuTsdfMap signatures) is a thin
+ * wrapper over these calls; INTEGRATION.md shows the binding a maintainer adds behind OhmAppGpu.
+ *
+ * Conventions: plain pointers and sizes only; `int` returns 0 on success and a negative OHMB200_E_* code on
+ * failure (message via ohmb200_last_error()); size_t returns follow the reference call they replace.
+ * Not thread-safe per map (same as ohmgpu/GpuMap.h:116-125): one caller thread per map.
+ */
+#ifndef OHMB200_H
+#define OHMB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define OHMB200_API
+#else
+#define OHMB200_API __attribute__((visibility("default")))
+#endif
+
+/* Voxel layers — ohm/DefaultLayer.cpp:76-337.  Bit (1u << id) in ohmb200_params.layers enables a layer. */
+enum ohmb200_layer
+{
+  OHMB200_LAYER_OCCUPANCY = 0,  /* f32, clear value +inf             (DefaultLayer.cpp:85-91)   */
+  OHMB200_LAYER_MEAN = 1,       /* {u32 coord, u32 count}            (VoxelMeanCompute.h:29-33) */
+  OHMB200_LAYER_TRAVERSAL = 2,  /* f32                               (DefaultLayer.cpp:132)     */
+  OHMB200_LAYER_TOUCH_TIME = 3, /* u32 ms since first ray            (VoxelTouchTimeCompute.h)  */
+  OHMB200_LAYER_INCIDENT = 4,   /* u32 packed normal                 (VoxelIncidentCompute.h)   */
+  OHMB200_LAYER_COVARIANCE = 5, /* 6 x f32 packed sqrt covariance    (CovarianceVoxelCompute.h:56-64) */
+  OHMB200_LAYER_INTENSITY = 6,  /* {f32 mean, f32 cov}               (CovarianceVoxelCompute.h:67-73) */
+  OHMB200_LAYER_HIT_MISS = 7,   /* {u32 hit, u32 miss}               (CovarianceVoxelCompute.h:76-82) */
+  OHMB200_LAYER_TSDF = 8,       /* {f32 weight, f32 distance}        (VoxelTsdfCompute.h:20-24) */
+  OHMB200_LAYER_COUNT = 9
+};
+
+/* Which mapper the map runs — the classes OhmAppGpu::prepareForRun picks between (ohmapp/OhmAppGpu.cpp:164-259). */
+enum ohmb200_mode
+{
+  OHMB200_MODE_OCCUPANCY = 0, /* ohm::GpuMap      (ohmgpu/GpuMap.h:143)                         */
+  OHMB200_MODE_NDT = 1,       /* ohm::GpuNdtMap, NdtMode::kOccupancy (ohmgpu/GpuNdtMap.h:63)    */
+  OHMB200_MODE_NDT_TM = 2,    /* ohm::GpuNdtMap, NdtMode::kTraversability                       */
+  OHMB200_MODE_TSDF = 3       /* ohm::GpuTsdfMap  (ohmgpu/GpuTsdfMap.h:37)                      */
+};
+
+/* Ray filters — ohm/RayFilter.cpp:15-55 (the std::function the map holds, OccupancyMap.cpp:215-218). */
+enum ohmb200_filter
+{
+  OHMB200_FILTER_NONE = 0,
+  OHMB200_FILTER_GOOD_RAY = 1,  /* goodRayFilter(max_range); the OccupancyMap default, range 1e10 */
+  OHMB200_FILTER_CLIP_RANGE = 2 /* clipRayFilter(max_length): clip + kRffClippedEnd               */
+};
+
+/* RayFlag — ohm/RayFlag.h:16-60 (same bit values). */
+enum ohmb200_ray_flag
+{
+  OHMB200_RF_DEFAULT = 0,
+  OHMB200_RF_END_POINT_AS_FREE = 1u << 0,
+  OHMB200_RF_STOP_ON_FIRST_OCCUPIED = 1u << 1,
+  OHMB200_RF_EXCLUDE_ORIGIN = 1u << 2,
+  OHMB200_RF_EXCLUDE_SAMPLE = 1u << 3,
+  OHMB200_RF_EXCLUDE_RAY = 1u << 4,
+  OHMB200_RF_EXCLUDE_UNOBSERVED = 1u << 5,
+  OHMB200_RF_EXCLUDE_FREE = 1u << 6,
+  OHMB200_RF_EXCLUDE_OCCUPIED = 1u << 7,
+  OHMB200_RF_REVERSE_WALK = 1u << 8 /* accepted and ignored, as the CPU mappers do */
+};
+
+enum ohmb200_error
+{
+  OHMB200_OK = 0,
+  OHMB200_E_INVALID = -1,     /* bad argument */
+  OHMB200_E_CUDA = -2,        /* CUDA runtime failure (gputil::ApiException in the reference) */
+  OHMB200_E_NO_DEVICE = -3,   /* no sm_100 device: gpuOk() == false, calls are no-ops (GpuMap.cpp:548-551) */
+  OHMB200_E_CACHE_FULL = -4,  /* region table full (GpuLayerCache kCacheFull, GpuMap.cpp:935-975) */
+  OHMB200_E_NOT_FOUND = -5,   /* region/layer absent */
+  OHMB200_E_OVERFLOW = -6     /* an internal per-batch list overflowed; batch was split and retried */
+};
+
+/* Map + mapper parameters.  Mirrors OccupancyMapDetail (ohm/private/OccupancyMapDetail.h:47-84),
+ * NdtMapDetail (ohm/private/NdtMapDetail.h:24-40) and TsdfOptions (ohm/VoxelTsdf.h:27-37). */
+typedef struct ohmb200_params
+{
+  double resolution;        /* voxel edge, metres */
+  int32_t region_dim[3];    /* voxels per region edge; 32 by default (OccupancyMap.h:24-26) */
+  double origin[3];         /* map origin */
+  float hit_value;          /* log-odds added on a hit  (logit 0.9)  */
+  float miss_value;         /* log-odds added on a miss (logit 0.45) */
+  float min_value;          /* -2.0   */
+  float max_value;          /* 3.511  */
+  float threshold_value;    /* occupancy threshold (logit 0.5 = 0) */
+  int32_t saturate_min;     /* saturateAtMinValue */
+  int32_t saturate_max;     /* saturateAtMaxValue */
+  uint32_t layers;          /* bitset of (1u << OHMB200_LAYER_*) */
+  int32_t filter_kind;      /* ohmb200_filter */
+  double filter_range;      /* max_range / max_length for the filter */
+  float sensor_noise;       /* NDT */
+  float adaptation_rate;
+  float reinit_threshold;
+  uint32_t reinit_count;
+  uint32_t sample_threshold;
+  float initial_intensity_cov;
+  int32_t ndt_tm;
+  float tsdf_max_weight;    /* TSDF */
+  float tsdf_trunc;
+  float tsdf_dropoff;
+  float tsdf_sparsity;
+} ohmb200_params;
+
+/* Counters of the last integrate call and totals (the units of the roofline byte model). */
+typedef struct ohmb200_stats
+{
+  uint64_t rays_in;          /* rays offered over the map's life */
+  uint64_t rays_accepted;    /* rays that passed the filter */
+  uint64_t voxel_visits;     /* V: DDA voxel visits (miss side; TSDF: all) */
+  uint64_t sample_updates;   /* S: sample voxel updates */
+  uint64_t ordered_records;  /* visits replayed in exact ray order because the voxel was also hit in the batch */
+  uint64_t regions;          /* regions resident on the device */
+  uint64_t region_capacity;  /* region slots allocated */
+  uint64_t batches;          /* integrate calls */
+  uint64_t kernel_launches;  /* kernels launched by this library */
+} ohmb200_stats;
+
+typedef struct ohmb200_map ohmb200_map;
+
+/* Number of usable (compute capability 10.x) devices.  Replaces ohm::configureGpuFromArgs / gpuDevice()
+ * (ohmgpu/OhmGpu.h:40). */
+OHMB200_API int ohmb200_device_count(void);
+
+/* Defaults of ohm::OccupancyMap's constructor (ohm/OccupancyMap.cpp:195-222), NdtMap and TsdfOptions. */
+OHMB200_API void ohmb200_default_params(ohmb200_params *params, double resolution);
+
+/* Construct map + mapper on `device`.  Replaces `new ohm::OccupancyMap(res, region_dim, flags)` followed by
+ * `ohm::GpuMap(map, borrowed, expected_element_count, gpu_mem_size)` / GpuNdtMap / GpuTsdfMap
+ * (ohmgpu/GpuMap.h:167-169, GpuNdtMap.h:72-74, GpuTsdfMap.h:46-48).  `device_bytes` is the GPU cache budget
+ * (gpu_mem_size; 0 = default), which fixes the number of resident region slots.  NULL on failure. */
+OHMB200_API ohmb200_map *ohmb200_create(const ohmb200_params *params, int mode, size_t device_bytes, int device);
+
+/* ~GpuMap + ~OccupancyMap. */
+OHMB200_API void ohmb200_destroy(ohmb200_map *map);
+
+/* Update the mutable parameters (hit/miss/min/max/threshold/saturation, filter, NDT, TSDF).  Replaces
+ * OccupancyMap::setHitValue/setMissValue/... , GpuMap::setRayFilter (GpuMap.h:214), GpuNdtMap::setSensorNoise
+ * (GpuNdtMap.h:91), GpuTsdfMap::setTsdfOptions (GpuTsdfMap.h:64).  Geometry and layers must not change. */
+OHMB200_API int ohmb200_set_params(ohmb200_map *map, const ohmb200_params *params);
+OHMB200_API int ohmb200_get_params(const ohmb200_map *map, ohmb200_params *params);
+
+/* ohm::RayMapper::integrateRays (ohm/RayMapper.h:57-58) as implemented by GpuMap::integrateRays
+ * (ohmgpu/GpuMap.cpp:540-875).  `rays` = interleaved (origin, sample) f64 xyz triples in HOST memory,
+ * `element_count` = 2 x ray count; `intensities` / `timestamps` are per ray and nullable.  Asynchronous with
+ * respect to the device: inputs are copied to pinned staging before return.  Returns the number of points
+ * integrated (2 x accepted rays, GpuMap.cpp:874) or 0 on failure. */
+OHMB200_API size_t ohmb200_integrate(ohmb200_map *map, const double *rays, size_t element_count,
+                                     const float *intensities, const double *timestamps, unsigned ray_flags);
+
+/* Same call with the arrays already resident in device memory (HBM) on the map's device. */
+OHMB200_API size_t ohmb200_integrate_device(ohmb200_map *map, const double *d_rays, size_t element_count,
+                                            const float *d_intensities, const double *d_timestamps,
+                                            unsigned ray_flags);
+
+/* GpuMap::syncVoxels (ohmgpu/GpuMap.h:199): block until all queued device work is complete.  Voxel data stays
+ * resident; read it back with ohmb200_read_region(s). */
+OHMB200_API int ohmb200_sync(ohmb200_map *map);
+
+/* OccupancyMap::regionCount / region enumeration.  Keys are written sorted by (z, y, x). */
+OHMB200_API size_t ohmb200_region_count(ohmb200_map *map);
+OHMB200_API size_t ohmb200_enumerate_regions(ohmb200_map *map, int16_t *keys_xyz, size_t capacity);
+
+/* Bytes of one region chunk of `layer` (MapLayer::layerByteSize). */
+OHMB200_API size_t ohmb200_region_layer_bytes(const ohmb200_map *map, int layer);
+
+/* GpuLayerCache::syncToExternal(dst, dst_size, region_key) (ohmgpu/GpuLayerCache.h:291): copy one region chunk
+ * of one layer to host memory (x + y*dx + z*dx*dy voxel order, ohm/MapChunk.h:47-50). */
+OHMB200_API int ohmb200_read_region(ohmb200_map *map, const int16_t key_xyz[3], int layer, void *dst, size_t bytes);
+
+/* GpuLayerCache::syncToMainMemory() (ohmgpu/GpuLayerCache.h:268) for `count` regions in one gather + one D2H:
+ * dst receives count x region_layer_bytes, in the order of `keys_xyz`. */
+OHMB200_API int ohmb200_read_regions(ohmb200_map *map, int layer, const int16_t *keys_xyz, size_t count, void *dst,
+                                     size_t bytes);
+
+/* GpuLayerCache::upload (ohmgpu/GpuLayerCache.cpp:172-182): make the region resident (creating it if absent)
+ * and overwrite one layer chunk from host memory. */
+OHMB200_API int ohmb200_write_region(ohmb200_map *map, const int16_t key_xyz[3], int layer, const void *src,
+                                     size_t bytes);
+
+/* GpuCache::clear (ohmgpu/GpuCache.h:109) + OccupancyMap::clear: drop every region. */
+OHMB200_API int ohmb200_clear(ohmb200_map *map);
+
+/* OccupancyMap::firstRayTime / setFirstRayTime (ohm/OccupancyMap.cpp:333-347). < 0 = unset. */
+OHMB200_API double ohmb200_first_ray_time(const ohmb200_map *map);
+OHMB200_API int ohmb200_set_first_ray_time(ohmb200_map *map, double t);
+
+OHMB200_API int ohmb200_get_stats(ohmb200_map *map, ohmb200_stats *stats);
+
+/* Use an external CUDA stream (a cudaStream_t passed as void*) instead of the map's own.  NULL restores it. */
+OHMB200_API int ohmb200_set_stream(ohmb200_map *map, void *cuda_stream);
+
+/* Per-kernel CUDA-event timing on the map's stream (bench.py's roofline numbers).  When enabled every launch is
+ * bracketed by events; ohmb200_kernel_times drains {name -> accumulated ms, launches}. */
+#define OHMB200_KERNEL_SLOTS 16
+typedef struct ohmb200_kernel_time
+{
+  char name[32];
+  double ms;
+  uint64_t launches;
+} ohmb200_kernel_time;
+OHMB200_API int ohmb200_set_profiling(ohmb200_map *map, int enabled);
+OHMB200_API int ohmb200_kernel_times(ohmb200_map *map, ohmb200_kernel_time *out, int capacity, int reset);
+
+/* Message of the last failure on this thread. */
+OHMB200_API const char *ohmb200_last_error(void);
+
+/* "ohmb200 <version> sm_100a" */
+OHMB200_API const char *ohmb200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OHMB200_H */

@@ -1,0 +1,1488 @@
+// ohmb200.cu — kernels, device-resident map runtime and the C ABI of libohmb200.so.
+//
+// Pipeline of one integrateRays batch (all on the map's compute stream, no host synchronisation):
+//
+//   prepSamples   1 thread/ray   filter, sample-voxel key (fp64), region find-or-insert -> (voxel id, ray) pair
+//   radix sort                   pairs by voxel id (stable: ray order is preserved inside a voxel)
+//   markRuns      1 thread/pair  run heads -> pending[voxel] = kHitFlag | run, compact run list
+//   walkRays      1 thread/ray   exact fp64 voxel walk; per visit: unflagged voxel -> RED.ADD pending (miss count),
+//                                flagged voxel -> (run, ray) record chained on the run (replayed in ray order)
+//   applySamples  1 thread/run   replays hits (+mean, incident normal, touch time) interleaved, in ray order, with
+//                                the recorded misses of that voxel — bit-exact with the sequential CPU mapper
+//   resolveMisses 1 CTA/region   pending miss counts -> occupancy (k identical clamped adds commute), clear pending
+//
+// Reference semantics: ohm/RayMapperOccupancy.cpp:68-339 (the CPU mapper is the parity target);
+// replaces ohmgpu/GpuMap.cpp:540-1191 + ohmgpu/gpu/RegionUpdate.cl:158-494 + ohmgpu/GpuLayerCache.cpp.
+#include "ohmb200.h"
+#include "ohmb200_device.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace ohmb200;
+
+// ---------------------------------------------------------------------------------------------------------
+// Errors
+// ---------------------------------------------------------------------------------------------------------
+static thread_local char g_last_error[512] = "";
+
+static int setError(int code, const char *fmt, ...)
+{
+  va_list args;
+  va_start(args, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, args);
+  va_end(args);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                                   \
+  do                                                                                                     \
+  {                                                                                                      \
+    cudaError_t err__ = (expr);                                                                          \
+    if (err__ != cudaSuccess)                                                                            \
+    {                                                                                                    \
+      return setError(OHMB200_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, \
+                      __LINE__);                                                                         \
+    }                                                                                                    \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
+// Device-side batch state
+// ---------------------------------------------------------------------------------------------------------
+struct Counters
+{
+  unsigned long long rays_accepted;
+  unsigned long long voxel_visits;
+  unsigned long long sample_updates;
+  unsigned long long ordered_records;
+  unsigned long long region_count;
+  // per batch (reset before each batch)
+  uint32_t record_count;
+  uint32_t run_count;
+  uint32_t touched_count;
+  uint32_t record_overflow;
+  int table_full;
+};
+
+struct Batch
+{
+  const double *rays;        // [2n] x 3 doubles: origin, sample
+  const float *intensities;  // [n] or null
+  const double *timestamps;  // [n] or null
+  uint32_t n;
+  unsigned ray_flags;
+  uint32_t stamp;
+  double time_base;
+  // sample pairs
+  uint32_t *keys_in, *keys_out;  // voxel ids
+  uint32_t *vals_in, *vals_out;  // ray indices
+  uint32_t *run_list;            // [n] sorted index of each run head
+  int32_t *run_head;             // [n] head of the record chain of the run starting at sorted index i (-1 = none)
+  uint32_t *interval_count;      // [n] misses that precede sorted hit i inside its run
+  uint32_t *tail_overflow;       // [n] unordered (overflowed) misses of run i
+  // ordered miss records
+  uint32_t *record_ray;
+  int32_t *record_next;
+  uint32_t record_capacity;
+  uint32_t *touched_list;  // [capacity] region slots walked this batch
+  double *last_exit;       // [n] exit range of the last walked voxel (traversal layer only)
+  Counters *counters;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Kernels
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t warpAggregatedInc(uint32_t *counter)
+{
+  // One atomic per converged group instead of one per lane.
+  const unsigned mask = __activemask();
+  const int leader = __ffs(mask) - 1;
+  const int lane = threadIdx.x & 31;
+  uint32_t base = 0;
+  if (lane == leader)
+  {
+    base = atomicAdd(counter, (uint32_t)__popc(mask));
+  }
+  base = __shfl_sync(mask, base, leader);
+  return base + __popc(mask & ((1u << lane) - 1u));
+}
+
+__device__ __forceinline__ void loadRay(const Batch &b, uint32_t i, double start[3], double end[3])
+{
+  const double *r = b.rays + (size_t)i * 6;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+  {
+    start[a] = r[a];
+    end[a] = r[3 + a];
+  }
+}
+
+// Filter + sample voxel of every ray.
+__global__ void prepSamples(DeviceMap dm, Geom g, MapParams mp, Batch b, int mode)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool accepted = false;
+  if (i < b.n)
+  {
+    double start[3], end[3];
+    loadRay(b, i, start, end);
+    unsigned filter_flags = 0;
+    uint32_t vid = kInvalidVoxel;
+    if (applyRayFilter(mp, start, end, filter_flags))
+    {
+      accepted = true;
+      // RayMapperOccupancy.cpp:223,234 / RayMapperNdt.cpp:270,284
+      const bool include_sample_in_ray = (filter_flags & kRffClippedEnd) || (b.ray_flags & OHMB200_RF_END_POINT_AS_FREE);
+      bool hit = !include_sample_in_ray;
+      if (mode == OHMB200_MODE_OCCUPANCY)
+      {
+        hit = hit && !(b.ray_flags & OHMB200_RF_EXCLUDE_SAMPLE);
+      }
+      Key skey, ekey;
+      // walkSegmentKeys drops rays with a null key, but the sample update still resolves its own key.
+      (void)skey;
+      if (hit && voxelKey(g, end, ekey))
+      {
+        const int slot = regionSlot(dm, packRegion(ekey.r[0], ekey.r[1], ekey.r[2]));
+        if (slot >= 0)
+        {
+          vid = (uint32_t)slot * g.vpr + voxelIndex(g, ekey);
+        }
+      }
+    }
+    b.keys_in[i] = vid;
+    b.vals_in[i] = i;
+  }
+  const unsigned n_acc = __reduce_add_sync(0xffffffffu, accepted ? 1u : 0u);
+  if ((threadIdx.x & 31) == 0 && n_acc)
+  {
+    atomicAdd(&b.counters->rays_accepted, (unsigned long long)n_acc);
+  }
+}
+
+// Run heads of the sorted (voxel, ray) pairs.
+__global__ void markRuns(DeviceMap dm, Batch b)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b.n)
+  {
+    return;
+  }
+  const uint32_t vid = b.keys_out[i];
+  if (vid == kInvalidVoxel)
+  {
+    return;
+  }
+  if (i == 0 || b.keys_out[i - 1] != vid)
+  {
+    dm.pending[vid] = kHitFlag | i;
+    const uint32_t r = warpAggregatedInc(&b.counters->run_count);
+    b.run_list[r] = i;
+  }
+}
+
+// Exact voxel walk of every ray: the miss side of RayMapperOccupancy::integrateRays.
+__global__ void __launch_bounds__(128) walkRays(DeviceMap dm, Geom g, MapParams mp, Batch b)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned visits = 0;
+  if (i < b.n)
+  {
+    double start[3], end[3];
+    loadRay(b, i, start, end);
+    unsigned filter_flags = 0;
+    Key skey, ekey;
+    double last_exit = 0;
+    if (applyRayFilter(mp, start, end, filter_flags) && !(b.ray_flags & OHMB200_RF_EXCLUDE_RAY) &&
+        voxelKey(g, start, skey) && voxelKey(g, end, ekey))
+    {
+      const bool include_sample_in_ray = (filter_flags & kRffClippedEnd) || (b.ray_flags & OHMB200_RF_END_POINT_AS_FREE);
+      unsigned walk_flags = (!include_sample_in_ray) ? kExcludeEndVoxel : 0u;
+      walk_flags |= (b.ray_flags & OHMB200_RF_EXCLUDE_ORIGIN) ? kExcludeStartVoxel : 0u;
+
+      unsigned long long last_region = kEmptyKey;
+      int slot = -1;
+      walkLine(g, start, end, skey, ekey, walk_flags, [&](const Key &k, double enter, double exit) {
+        const unsigned long long rk = packRegion(k.r[0], k.r[1], k.r[2]);
+        if (rk != last_region)
+        {
+          last_region = rk;
+          slot = regionSlot(dm, rk);
+          if (slot >= 0 && __ldcg(&dm.region_stamp[slot]) != b.stamp)
+          {
+            if (atomicExch(&dm.region_stamp[slot], b.stamp) != b.stamp)
+            {
+              b.touched_list[warpAggregatedInc(&b.counters->touched_count)] = (uint32_t)slot;
+            }
+          }
+        }
+        last_exit = exit;
+        ++visits;
+        if (slot < 0)
+        {
+          return;
+        }
+        const uint32_t vid = (uint32_t)slot * g.vpr + voxelIndex(g, k);
+        const uint32_t p = __ldcg(&dm.pending[vid]);
+        if (p & kHitFlag)
+        {
+          // This voxel also receives samples in this batch: keep the miss ordered against them.
+          const uint32_t run = p & ~kHitFlag;
+          const uint32_t rec = warpAggregatedInc(&b.counters->record_count);
+          if (rec < b.record_capacity)
+          {
+            b.record_ray[rec] = i;
+            b.record_next[rec] = atomicExch(&b.run_head[run], (int32_t)rec);
+          }
+          else
+          {
+            atomicAdd(&b.tail_overflow[run], 1u);
+            b.counters->record_overflow = 1;
+          }
+        }
+        else
+        {
+          atomicAdd(&dm.pending[vid], 1u);
+        }
+        if (dm.traversal)
+        {
+          atomicAdd(&dm.traversal[vid], (float)(exit - enter));
+        }
+      });
+    }
+    if (b.last_exit)
+    {
+      b.last_exit[i] = last_exit;
+    }
+  }
+  __syncwarp();
+  const unsigned total = __reduce_add_sync(0xffffffffu, visits);
+  if ((threadIdx.x & 31) == 0 && total)
+  {
+    atomicAdd(&b.counters->voxel_visits, (unsigned long long)total);
+  }
+}
+
+__device__ __forceinline__ void unpackRegion(unsigned long long k, int r[3])
+{
+  r[0] = (int)(int16_t)(k & 0xffffu);
+  r[1] = (int)(int16_t)((k >> 16) & 0xffffu);
+  r[2] = (int)(int16_t)((k >> 32) & 0xffffu);
+}
+
+// Sample-voxel updates, one thread per voxel, replayed in ray order: RayMapperOccupancy.cpp:234-335.
+__global__ void __launch_bounds__(128) applySamples(DeviceMap dm, Geom g, MapParams mp, Batch b)
+{
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned samples = 0, ordered = 0;
+  if (t < b.counters->run_count)
+  {
+    const uint32_t head = b.run_list[t];
+    const uint32_t vid = b.keys_out[head];
+    uint32_t k = 1;
+    while (head + k < b.n && b.keys_out[head + k] == vid)
+    {
+      ++k;
+    }
+    // Sort this voxel's recorded misses into the intervals between its hits.
+    uint32_t tail = b.tail_overflow[head];
+    for (int32_t rec = b.run_head[head]; rec >= 0; rec = b.record_next[rec])
+    {
+      const uint32_t ray = b.record_ray[rec];
+      uint32_t lo = 0, hi = k;  // first hit whose ray index is greater than `ray`
+      while (lo < hi)
+      {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (b.vals_out[head + mid] < ray)
+        {
+          lo = mid + 1;
+        }
+        else
+        {
+          hi = mid;
+        }
+      }
+      if (lo < k)
+      {
+        ++b.interval_count[head + lo];
+      }
+      else
+      {
+        ++tail;
+      }
+      ++ordered;
+    }
+
+    const uint32_t slot = vid / g.vpr;
+    const uint32_t local = vid - slot * g.vpr;
+    Key key;
+    unpackRegion(dm.keys[slot], key.r);
+    key.l[0] = (int)(local % (uint32_t)g.dim[0]);
+    key.l[1] = (int)((local / (uint32_t)g.dim[0]) % (uint32_t)g.dim[1]);
+    key.l[2] = (int)(local / ((uint32_t)g.dim[0] * (uint32_t)g.dim[1]));
+    double centre[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+    {
+      centre[a] = voxelCentreAxis(g, key.r[a], key.l[a], a);
+    }
+
+    float value = dm.occupancy[vid];
+    uint2 mean = dm.mean ? dm.mean[vid] : make_uint2(0, 0);
+    uint32_t incident = dm.incident ? dm.incident[vid] : 0;
+    uint32_t touch = 0;
+    bool touch_set = false;
+    float traversal_add = 0.0f;
+    for (uint32_t j = 0; j < k; ++j)
+    {
+      value = missRepeat(value, b.interval_count[head + j], mp, b.ray_flags);
+      const uint32_t ray = b.vals_out[head + j];
+      double start[3], end[3];
+      loadRay(b, ray, start, end);
+      value = hitOnce(value, mp, b.ray_flags);
+      uint32_t sample_count = 0;
+      if (dm.mean)
+      {
+        const double local_pt[3] = { end[0] - centre[0], end[1] - centre[1], end[2] - centre[2] };
+        mean.x = subVoxelUpdate(mean.x, mean.y, local_pt, g.res);
+        sample_count = mean.y;
+        ++mean.y;
+      }
+      if (dm.traversal)
+      {
+        const double d[3] = { end[0] - start[0], end[1] - start[1], end[2] - start[2] };
+        const double len = sqrt((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]);
+        traversal_add += (float)(len - b.last_exit[ray]);
+      }
+      if (dm.touch_time && b.timestamps)
+      {
+        touch = encodeTouchTime(b.time_base, b.timestamps[ray]);
+        touch_set = true;
+      }
+      if (dm.incident)
+      {
+        incident = updateIncidentNormal(incident, (float)(start[0] - end[0]), (float)(start[1] - end[1]),
+                                        (float)(start[2] - end[2]), sample_count);
+      }
+      ++samples;
+    }
+    value = missRepeat(value, tail, mp, b.ray_flags);
+
+    dm.occupancy[vid] = value;
+    if (dm.mean)
+    {
+      dm.mean[vid] = mean;
+    }
+    if (dm.incident)
+    {
+      dm.incident[vid] = incident;
+    }
+    if (touch_set)
+    {
+      dm.touch_time[vid] = touch;
+    }
+    if (dm.traversal)
+    {
+      atomicAdd(&dm.traversal[vid], traversal_add);
+    }
+    dm.pending[vid] = 0;
+  }
+  __syncwarp();
+  const unsigned s = __reduce_add_sync(0xffffffffu, samples);
+  const unsigned o = __reduce_add_sync(0xffffffffu, ordered);
+  if ((threadIdx.x & 31) == 0)
+  {
+    if (s)
+    {
+      atomicAdd(&b.counters->sample_updates, (unsigned long long)s);
+    }
+    if (o)
+    {
+      atomicAdd(&b.counters->ordered_records, (unsigned long long)o);
+    }
+  }
+}
+
+// Fold the per-voxel miss counts of every region walked this batch into the occupancy layer.
+__global__ void __launch_bounds__(256) resolveMisses(DeviceMap dm, Geom g, MapParams mp, Batch b)
+{
+  const uint32_t n_regions = b.counters->touched_count;
+  for (uint32_t r = blockIdx.x; r < n_regions; r += gridDim.x)
+  {
+    const size_t base = (size_t)b.touched_list[r] * g.vpr;
+    for (uint32_t v = threadIdx.x; v < g.vpr; v += blockDim.x)
+    {
+      const uint32_t c = dm.pending[base + v];
+      if (c != 0 && !(c & kHitFlag))
+      {
+        dm.occupancy[base + v] = missRepeat(dm.occupancy[base + v], c, mp, b.ray_flags);
+        dm.pending[base + v] = 0;
+      }
+    }
+  }
+}
+
+__global__ void fillFloat(float *dst, size_t n, float value)
+{
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+  {
+    dst[i] = value;
+  }
+}
+
+// Gather region chunks of one layer into a contiguous staging buffer (16-byte vectors).
+__global__ void gatherRegions(const uint4 *slab, const uint32_t *slots, uint4 *dst, size_t vec_per_region)
+{
+  const uint4 *src = slab + (size_t)slots[blockIdx.x] * vec_per_region;
+  uint4 *out = dst + (size_t)blockIdx.x * vec_per_region;
+  for (size_t i = threadIdx.x; i < vec_per_region; i += blockDim.x)
+  {
+    out[i] = src[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Host-side map
+// ---------------------------------------------------------------------------------------------------------
+static const size_t kLayerBytes[OHMB200_LAYER_COUNT] = { 4, 8, 4, 4, 4, 24, 8, 8, 8 };
+
+enum KernelId
+{
+  kKPrep = 0,
+  kKSort,
+  kKMark,
+  kKWalk,
+  kKSamples,
+  kKResolve,
+  kKGather,
+  kKFill,
+  kKernelCount
+};
+static const char *kKernelNames[kKernelCount] = { "prepSamples", "radixSort",     "markRuns",      "walkRays",
+                                                  "applySamples", "resolveMisses", "gatherRegions", "fillFloat" };
+
+struct ohmb200_map
+{
+  int device = 0;
+  int mode = 0;
+  int sm_count = 148;
+  ohmb200_params params{};
+  Geom geom{};
+  MapParams mp{};
+  DeviceMap dm{};
+  void *layer_slab[OHMB200_LAYER_COUNT] = {};
+  size_t region_layer_bytes[OHMB200_LAYER_COUNT] = {};
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  Counters *d_counters = nullptr;
+  Counters *h_counters = nullptr;  // pinned
+  double first_ray_time = -1.0;
+  uint32_t stamp = 0;
+  uint64_t rays_in = 0;
+  uint64_t batches = 0;
+  uint64_t launches = 0;
+  // batch scratch
+  Batch batch{};
+  size_t scratch_rays = 0;
+  void *cub_temp = nullptr;
+  size_t cub_temp_bytes = 0;
+  int sort_bits = 32;
+  // host -> device input staging (double buffered)
+  double *d_rays[2] = {};
+  float *d_intensities[2] = {};
+  double *d_timestamps[2] = {};
+  size_t in_capacity[2] = {};
+  cudaEvent_t in_ready[2] = {};
+  cudaEvent_t in_free[2] = {};
+  int next_input = 0;
+  // gather staging
+  void *d_gather = nullptr;
+  size_t gather_bytes = 0;
+  uint32_t *d_gather_slots = nullptr;
+  size_t gather_slots_cap = 0;
+  // profiling
+  bool profiling = false;
+  std::vector<cudaEvent_t> event_pool;
+  struct Span
+  {
+    int kernel;
+    cudaEvent_t a, b;
+  };
+  std::vector<Span> spans;
+  size_t events_used = 0;
+  double kernel_ms[kKernelCount] = {};
+  uint64_t kernel_launches[kKernelCount] = {};
+};
+
+namespace
+{
+struct KernelScope
+{
+  ohmb200_map *m;
+  int id;
+  cudaEvent_t a = nullptr, b = nullptr;
+  KernelScope(ohmb200_map *map, int kernel)
+    : m(map)
+    , id(kernel)
+  {
+    ++m->launches;
+    if (m->profiling)
+    {
+      a = take();
+      b = take();
+      cudaEventRecord(a, m->stream);
+    }
+  }
+  ~KernelScope()
+  {
+    if (m->profiling)
+    {
+      cudaEventRecord(b, m->stream);
+      m->spans.push_back({ id, a, b });
+    }
+  }
+  cudaEvent_t take()
+  {
+    if (m->events_used == m->event_pool.size())
+    {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      m->event_pool.push_back(e);
+    }
+    return m->event_pool[m->events_used++];
+  }
+};
+
+void drainSpans(ohmb200_map *m)
+{
+  if (m->spans.empty())
+  {
+    return;
+  }
+  cudaStreamSynchronize(m->stream);
+  for (const auto &s : m->spans)
+  {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess)
+    {
+      m->kernel_ms[s.kernel] += ms;
+      ++m->kernel_launches[s.kernel];
+    }
+  }
+  m->spans.clear();
+  m->events_used = 0;
+}
+
+void refreshParams(ohmb200_map *m)
+{
+  const ohmb200_params &p = m->params;
+  Geom &g = m->geom;
+  g.res = p.resolution;
+  g.vpr = 1;
+  for (int a = 0; a < 3; ++a)
+  {
+    g.dim[a] = p.region_dim[a];
+    g.region_size[a] = p.region_dim[a] * p.resolution;  // OccupancyMap.cpp:204-206
+    g.origin[a] = p.origin[a];
+    g.vpr *= (uint32_t)p.region_dim[a];
+  }
+  MapParams &mp = m->mp;
+  mp.hit_value = p.hit_value;
+  mp.miss_value = p.miss_value;
+  mp.min_value = p.min_value;
+  mp.max_value = p.max_value;
+  mp.threshold_value = p.threshold_value;
+  mp.sat_min = p.saturate_min ? p.min_value : -3.402823466e+38f;
+  mp.sat_max = p.saturate_max ? p.max_value : 3.402823466e+38f;
+  mp.filter_kind = p.filter_kind;
+  mp.filter_range = p.filter_range;
+  mp.sensor_noise = p.sensor_noise;
+  mp.adaptation_rate = p.adaptation_rate;
+  mp.reinit_threshold = p.reinit_threshold;
+  mp.initial_intensity_cov = p.initial_intensity_cov;
+  mp.reinit_count = p.reinit_count;
+  mp.sample_threshold = p.sample_threshold;
+  mp.ndt_tm = p.ndt_tm;
+  mp.tsdf_max_weight = p.tsdf_max_weight;
+  mp.tsdf_trunc = p.tsdf_trunc;
+  mp.tsdf_dropoff = p.tsdf_dropoff;
+  mp.tsdf_sparsity = p.tsdf_sparsity;
+}
+
+int initialiseSlabs(ohmb200_map *m)
+{
+  const size_t voxels = (size_t)m->dm.capacity * m->geom.vpr;
+  CUDA_TRY(cudaMemsetAsync(m->dm.keys, 0xFF, sizeof(unsigned long long) * m->dm.capacity, m->stream));
+  CUDA_TRY(cudaMemsetAsync(m->dm.region_stamp, 0, sizeof(uint32_t) * m->dm.capacity, m->stream));
+  CUDA_TRY(cudaMemsetAsync(m->dm.pending, 0, sizeof(uint32_t) * voxels, m->stream));
+  for (int l = 0; l < OHMB200_LAYER_COUNT; ++l)
+  {
+    if (!m->layer_slab[l])
+    {
+      continue;
+    }
+    if (l == OHMB200_LAYER_OCCUPANCY)
+    {
+      KernelScope scope(m, kKFill);
+      fillFloat<<<m->sm_count * 8, 256, 0, m->stream>>>((float *)m->layer_slab[l], voxels, INFINITY);
+    }
+    else
+    {
+      CUDA_TRY(cudaMemsetAsync(m->layer_slab[l], 0, kLayerBytes[l] * voxels, m->stream));
+    }
+  }
+  CUDA_TRY(cudaMemsetAsync(m->d_counters, 0, sizeof(Counters), m->stream));
+  CUDA_TRY(cudaGetLastError());
+  return OHMB200_OK;
+}
+
+template <typename T>
+int deviceAlloc(T *&ptr, size_t count)
+{
+  void *p = nullptr;
+  CUDA_TRY(cudaMalloc(&p, sizeof(T) * std::max<size_t>(count, 1)));
+  ptr = (T *)p;
+  return OHMB200_OK;
+}
+
+int ensureScratch(ohmb200_map *m, size_t n)
+{
+  if (n <= m->scratch_rays)
+  {
+    return OHMB200_OK;
+  }
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  Batch &b = m->batch;
+  cudaFree(b.keys_in);
+  cudaFree(b.keys_out);
+  cudaFree(b.vals_in);
+  cudaFree(b.vals_out);
+  cudaFree(b.run_list);
+  cudaFree(b.run_head);
+  cudaFree(b.interval_count);
+  cudaFree(b.tail_overflow);
+  cudaFree(b.record_ray);
+  cudaFree(b.record_next);
+  cudaFree(b.last_exit);
+  cudaFree(m->cub_temp);
+  b.last_exit = nullptr;
+  const size_t cap = std::max<size_t>(n, 4096);
+  int rc = 0;
+  rc |= deviceAlloc(b.keys_in, cap);
+  rc |= deviceAlloc(b.keys_out, cap);
+  rc |= deviceAlloc(b.vals_in, cap);
+  rc |= deviceAlloc(b.vals_out, cap);
+  rc |= deviceAlloc(b.run_list, cap);
+  rc |= deviceAlloc(b.run_head, cap);
+  rc |= deviceAlloc(b.interval_count, cap);
+  rc |= deviceAlloc(b.tail_overflow, cap);
+  b.record_capacity = (uint32_t)std::min<size_t>(std::max<size_t>(cap * 32, 1u << 20), 1u << 28);
+  rc |= deviceAlloc(b.record_ray, b.record_capacity);
+  rc |= deviceAlloc(b.record_next, b.record_capacity);
+  if (m->dm.traversal)
+  {
+    rc |= deviceAlloc(b.last_exit, cap);
+  }
+  if (rc)
+  {
+    return OHMB200_E_CUDA;
+  }
+  m->cub_temp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, m->cub_temp_bytes, b.keys_in, b.keys_out, b.vals_in, b.vals_out, (int)cap, 0,
+                                  m->sort_bits, m->stream);
+  CUDA_TRY(cudaMalloc(&m->cub_temp, std::max<size_t>(m->cub_temp_bytes, 16)));
+  m->scratch_rays = cap;
+  return OHMB200_OK;
+}
+
+int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_intensities, const double *d_timestamps,
+                unsigned ray_flags)
+{
+  if (n == 0)
+  {
+    return OHMB200_OK;
+  }
+  int rc = ensureScratch(m, n);
+  if (rc)
+  {
+    return rc;
+  }
+  Batch &b = m->batch;
+  b.rays = d_rays;
+  b.intensities = d_intensities;
+  b.timestamps = (m->dm.touch_time) ? d_timestamps : nullptr;
+  b.n = (uint32_t)n;
+  b.ray_flags = ray_flags;
+  b.stamp = ++m->stamp;
+  b.time_base = m->first_ray_time;
+  b.counters = m->d_counters;
+  cudaStream_t s = m->stream;
+  const unsigned threads = 128;
+  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  const bool has_samples = m->mode != OHMB200_MODE_TSDF;
+
+  // Reset the per-batch counters (record_count .. record_overflow are contiguous).
+  CUDA_TRY(cudaMemsetAsync(&m->d_counters->record_count, 0, sizeof(uint32_t) * 4, s));
+  if (has_samples)
+  {
+    CUDA_TRY(cudaMemsetAsync(b.run_head, 0xFF, sizeof(int32_t) * n, s));
+    CUDA_TRY(cudaMemsetAsync(b.interval_count, 0, sizeof(uint32_t) * n, s));
+    CUDA_TRY(cudaMemsetAsync(b.tail_overflow, 0, sizeof(uint32_t) * n, s));
+    {
+      KernelScope scope(m, kKPrep);
+      prepSamples<<<blocks, threads, 0, s>>>(m->dm, m->geom, m->mp, b, m->mode);
+    }
+    {
+      KernelScope scope(m, kKSort);
+      size_t temp = m->cub_temp_bytes;
+      cub::DeviceRadixSort::SortPairs(m->cub_temp, temp, b.keys_in, b.keys_out, b.vals_in, b.vals_out, (int)n, 0,
+                                      m->sort_bits, s);
+    }
+    {
+      KernelScope scope(m, kKMark);
+      markRuns<<<blocks, threads, 0, s>>>(m->dm, b);
+    }
+  }
+  {
+    KernelScope scope(m, kKWalk);
+    walkRays<<<blocks, threads, 0, s>>>(m->dm, m->geom, m->mp, b);
+  }
+  if (has_samples)
+  {
+    KernelScope scope(m, kKSamples);
+    applySamples<<<blocks, threads, 0, s>>>(m->dm, m->geom, m->mp, b);
+  }
+  {
+    KernelScope scope(m, kKResolve);
+    resolveMisses<<<m->sm_count * 4, 256, 0, s>>>(m->dm, m->geom, m->mp, b);
+  }
+  CUDA_TRY(cudaGetLastError());
+  m->rays_in += n;
+  ++m->batches;
+  return OHMB200_OK;
+}
+
+int pullCounters(ohmb200_map *m)
+{
+  CUDA_TRY(cudaMemcpyAsync(m->h_counters, m->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  return OHMB200_OK;
+}
+
+int findSlots(ohmb200_map *m, const int16_t *keys_xyz, size_t count, std::vector<uint32_t> &slots)
+{
+  std::vector<unsigned long long> table(m->dm.capacity);
+  CUDA_TRY(cudaMemcpyAsync(table.data(), m->dm.keys, sizeof(unsigned long long) * table.size(), cudaMemcpyDeviceToHost,
+                           m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  slots.resize(count);
+  for (size_t i = 0; i < count; ++i)
+  {
+    const unsigned long long key = (unsigned long long)(uint16_t)keys_xyz[3 * i] |
+                                   ((unsigned long long)(uint16_t)keys_xyz[3 * i + 1] << 16) |
+                                   ((unsigned long long)(uint16_t)keys_xyz[3 * i + 2] << 32);
+    uint32_t h = hashRegion(key) % m->dm.capacity;
+    bool found = false;
+    for (uint32_t probe = 0; probe < m->dm.capacity; ++probe)
+    {
+      if (table[h] == key)
+      {
+        found = true;
+        break;
+      }
+      if (table[h] == kEmptyKey)
+      {
+        break;
+      }
+      h = (h + 1 == m->dm.capacity) ? 0 : h + 1;
+    }
+    if (!found)
+    {
+      return setError(OHMB200_E_NOT_FOUND, "region (%d,%d,%d) is not resident", keys_xyz[3 * i], keys_xyz[3 * i + 1],
+                      keys_xyz[3 * i + 2]);
+    }
+    slots[i] = h;
+  }
+  return OHMB200_OK;
+}
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *ohmb200_last_error(void)
+{
+  return g_last_error;
+}
+
+const char *ohmb200_version(void)
+{
+  return "ohmb200 0.1.0 sm_100a";
+}
+
+int ohmb200_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return 0;
+  }
+  int usable = 0;
+  for (int d = 0; d < n; ++d)
+  {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10)
+    {
+      ++usable;
+    }
+  }
+  return usable;
+}
+
+void ohmb200_default_params(ohmb200_params *p, double resolution)
+{
+  // ohm/OccupancyMap.cpp:195-213, ohm/private/NdtMapDetail.h:24-40, ohm/NdtMap.cpp:194-213, ohm/VoxelTsdf.h:27-37
+  memset(p, 0, sizeof(*p));
+  p->resolution = resolution;
+  p->region_dim[0] = p->region_dim[1] = p->region_dim[2] = 32;
+  p->hit_value = logf(0.9f / (1.0f - 0.9f));
+  p->miss_value = logf(0.45f / (1.0f - 0.45f));
+  p->min_value = -2.0f;
+  p->max_value = 3.511f;
+  p->threshold_value = logf(0.5f / (1.0f - 0.5f));
+  p->layers = 1u << OHMB200_LAYER_OCCUPANCY;
+  p->filter_kind = OHMB200_FILTER_GOOD_RAY;
+  p->filter_range = 1e10;
+  p->sensor_noise = 0.05f;
+  p->adaptation_rate = 0.2f;
+  p->reinit_threshold = logf(0.2f / (1.0f - 0.2f));
+  p->reinit_count = 100;
+  p->sample_threshold = 3;
+  p->initial_intensity_cov = 1.0f;
+  p->tsdf_max_weight = 1e4f;
+  p->tsdf_trunc = 0.1f;
+  p->tsdf_dropoff = 0.0f;
+  p->tsdf_sparsity = 1.0f;
+}
+
+ohmb200_map *ohmb200_create(const ohmb200_params *params, int mode, size_t device_bytes, int device)
+{
+  if (!params || params->resolution <= 0 || mode < 0 || mode > OHMB200_MODE_TSDF)
+  {
+    setError(OHMB200_E_INVALID, "ohmb200_create: bad parameters");
+    return nullptr;
+  }
+  for (int a = 0; a < 3; ++a)
+  {
+    if (params->region_dim[a] < 1 || params->region_dim[a] > 255)
+    {
+      setError(OHMB200_E_INVALID, "ohmb200_create: region_dim must be in [1,255]");
+      return nullptr;
+    }
+  }
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)
+  {
+    cudaGetLastError();
+    setError(OHMB200_E_NO_DEVICE, "ohmb200_create: no CUDA device %d (the CUDA path is mandatory; there is no CPU fallback)",
+             device);
+    return nullptr;
+  }
+  cudaDeviceProp prop{};
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10)
+  {
+    setError(OHMB200_E_NO_DEVICE, "ohmb200_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
+             prop.major, prop.minor);
+    return nullptr;
+  }
+  if (cudaSetDevice(device) != cudaSuccess)
+  {
+    setError(OHMB200_E_CUDA, "cudaSetDevice(%d) failed", device);
+    return nullptr;
+  }
+
+  ohmb200_map *m = new ohmb200_map();
+  m->device = device;
+  m->mode = mode;
+  m->sm_count = prop.multiProcessorCount;
+  m->params = *params;
+  // Layers the mapper requires (ohmgpu/GpuNdtMap.cpp:80-94, ohmapp/OhmAppGpu.cpp:192-201).
+  if (mode == OHMB200_MODE_TSDF)
+  {
+    m->params.layers |= 1u << OHMB200_LAYER_TSDF;
+  }
+  else
+  {
+    m->params.layers |= 1u << OHMB200_LAYER_OCCUPANCY;
+  }
+  if (mode == OHMB200_MODE_NDT || mode == OHMB200_MODE_NDT_TM)
+  {
+    m->params.layers |= (1u << OHMB200_LAYER_MEAN) | (1u << OHMB200_LAYER_COVARIANCE);
+  }
+  if (mode == OHMB200_MODE_NDT_TM)
+  {
+    m->params.layers |= (1u << OHMB200_LAYER_INTENSITY) | (1u << OHMB200_LAYER_HIT_MISS);
+    m->params.ndt_tm = 1;
+  }
+  refreshParams(m);
+
+  size_t bytes_per_region = sizeof(uint32_t) * m->geom.vpr;  // pending
+  for (int l = 0; l < OHMB200_LAYER_COUNT; ++l)
+  {
+    if (m->params.layers & (1u << l))
+    {
+      m->region_layer_bytes[l] = kLayerBytes[l] * m->geom.vpr;
+      bytes_per_region += m->region_layer_bytes[l];
+    }
+  }
+  if (device_bytes == 0)
+  {
+    device_bytes = (size_t)8 << 30;
+  }
+  size_t free_bytes = 0, total_bytes = 0;
+  cudaMemGetInfo(&free_bytes, &total_bytes);
+  device_bytes = std::min(device_bytes, (size_t)(free_bytes * 0.9));
+  size_t capacity = std::max<size_t>(device_bytes / bytes_per_region, 8);
+  capacity = std::min<size_t>(capacity, (size_t)0xFFFFFFF0u / m->geom.vpr);  // voxel ids are 32-bit
+  m->dm.capacity = (uint32_t)capacity;
+  m->sort_bits = 32;
+
+  bool ok = true;
+  ok = ok && cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+  m->stream = m->own_stream;
+  for (int i = 0; i < 2 && ok; ++i)
+  {
+    ok = ok && cudaEventCreateWithFlags(&m->in_ready[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&m->in_free[i], cudaEventDisableTiming) == cudaSuccess;
+  }
+  const size_t voxels = capacity * m->geom.vpr;
+  ok = ok && cudaMalloc(&m->dm.keys, sizeof(unsigned long long) * capacity) == cudaSuccess;
+  ok = ok && cudaMalloc(&m->dm.region_stamp, sizeof(uint32_t) * capacity) == cudaSuccess;
+  ok = ok && cudaMalloc(&m->dm.pending, sizeof(uint32_t) * voxels) == cudaSuccess;
+  ok = ok && cudaMalloc(&m->batch.touched_list, sizeof(uint32_t) * capacity) == cudaSuccess;
+  ok = ok && cudaMalloc(&m->d_counters, sizeof(Counters)) == cudaSuccess;
+  ok = ok && cudaMallocHost(&m->h_counters, sizeof(Counters)) == cudaSuccess;
+  for (int l = 0; l < OHMB200_LAYER_COUNT && ok; ++l)
+  {
+    if (m->params.layers & (1u << l))
+    {
+      ok = ok && cudaMalloc(&m->layer_slab[l], kLayerBytes[l] * voxels) == cudaSuccess;
+    }
+  }
+  if (!ok)
+  {
+    setError(OHMB200_E_CUDA, "ohmb200_create: device allocation failed (%zu region slots x %zu bytes): %s", capacity,
+             bytes_per_region, cudaGetErrorString(cudaGetLastError()));
+    ohmb200_destroy(m);
+    return nullptr;
+  }
+  m->dm.occupancy = (float *)m->layer_slab[OHMB200_LAYER_OCCUPANCY];
+  m->dm.mean = (uint2 *)m->layer_slab[OHMB200_LAYER_MEAN];
+  m->dm.traversal = (float *)m->layer_slab[OHMB200_LAYER_TRAVERSAL];
+  m->dm.touch_time = (uint32_t *)m->layer_slab[OHMB200_LAYER_TOUCH_TIME];
+  m->dm.incident = (uint32_t *)m->layer_slab[OHMB200_LAYER_INCIDENT];
+  m->dm.covariance = (float *)m->layer_slab[OHMB200_LAYER_COVARIANCE];
+  m->dm.intensity = (float2 *)m->layer_slab[OHMB200_LAYER_INTENSITY];
+  m->dm.hit_miss = (uint2 *)m->layer_slab[OHMB200_LAYER_HIT_MISS];
+  m->dm.tsdf = (float2 *)m->layer_slab[OHMB200_LAYER_TSDF];
+  m->dm.region_count = &m->d_counters->region_count;
+  m->dm.table_full = &m->d_counters->table_full;
+  if (initialiseSlabs(m) != OHMB200_OK || cudaStreamSynchronize(m->stream) != cudaSuccess)
+  {
+    ohmb200_destroy(m);
+    return nullptr;
+  }
+  return m;
+}
+
+void ohmb200_destroy(ohmb200_map *m)
+{
+  if (!m)
+  {
+    return;
+  }
+  cudaSetDevice(m->device);
+  cudaDeviceSynchronize();
+  Batch &b = m->batch;
+  void *to_free[] = { m->dm.keys,       m->dm.region_stamp, m->dm.pending,      b.touched_list,   m->d_counters,
+                      b.keys_in,        b.keys_out,         b.vals_in,          b.vals_out,       b.run_list,
+                      b.run_head,       b.interval_count,   b.tail_overflow,    b.record_ray,     b.record_next,
+                      b.last_exit,      m->cub_temp,        m->d_rays[0],       m->d_rays[1],     m->d_intensities[0],
+                      m->d_intensities[1], m->d_timestamps[0], m->d_timestamps[1], m->d_gather,    m->d_gather_slots };
+  for (void *p : to_free)
+  {
+    if (p)
+    {
+      cudaFree(p);
+    }
+  }
+  for (void *p : m->layer_slab)
+  {
+    if (p)
+    {
+      cudaFree(p);
+    }
+  }
+  if (m->h_counters)
+  {
+    cudaFreeHost(m->h_counters);
+  }
+  for (cudaEvent_t e : m->event_pool)
+  {
+    cudaEventDestroy(e);
+  }
+  for (int i = 0; i < 2; ++i)
+  {
+    if (m->in_ready[i])
+    {
+      cudaEventDestroy(m->in_ready[i]);
+    }
+    if (m->in_free[i])
+    {
+      cudaEventDestroy(m->in_free[i]);
+    }
+  }
+  if (m->own_stream)
+  {
+    cudaStreamDestroy(m->own_stream);
+  }
+  if (m->copy_stream)
+  {
+    cudaStreamDestroy(m->copy_stream);
+  }
+  cudaGetLastError();
+  delete m;
+}
+
+int ohmb200_set_params(ohmb200_map *m, const ohmb200_params *p)
+{
+  if (!m || !p)
+  {
+    return setError(OHMB200_E_INVALID, "null argument");
+  }
+  if (p->resolution != m->params.resolution || memcmp(p->region_dim, m->params.region_dim, sizeof(p->region_dim)) != 0)
+  {
+    return setError(OHMB200_E_INVALID, "resolution and region dimensions are fixed at creation");
+  }
+  const uint32_t layers = m->params.layers;
+  const int ndt_tm = m->params.ndt_tm;
+  m->params = *p;
+  m->params.layers = layers;
+  m->params.ndt_tm = ndt_tm;
+  refreshParams(m);
+  return OHMB200_OK;
+}
+
+int ohmb200_get_params(const ohmb200_map *m, ohmb200_params *p)
+{
+  if (!m || !p)
+  {
+    return setError(OHMB200_E_INVALID, "null argument");
+  }
+  *p = m->params;
+  return OHMB200_OK;
+}
+
+size_t ohmb200_integrate_device(ohmb200_map *m, const double *d_rays, size_t element_count, const float *d_intensities,
+                                const double *d_timestamps, unsigned ray_flags)
+{
+  if (!m || !d_rays || element_count < 2)
+  {
+    setError(OHMB200_E_INVALID, "ohmb200_integrate_device: bad arguments");
+    return 0;
+  }
+  cudaSetDevice(m->device);
+  if (d_timestamps && m->first_ray_time < 0)
+  {
+    // OccupancyMap::updateFirstRayTime(*timestamps) (RayMapperOccupancy.cpp:99-103)
+    double t0 = 0;
+    if (cudaMemcpyAsync(&t0, d_timestamps, sizeof(double), cudaMemcpyDeviceToHost, m->stream) != cudaSuccess ||
+        cudaStreamSynchronize(m->stream) != cudaSuccess)
+    {
+      setError(OHMB200_E_CUDA, "failed to read the first timestamp");
+      return 0;
+    }
+    m->first_ray_time = t0;
+  }
+  if (launchBatch(m, d_rays, element_count / 2, d_intensities, d_timestamps, ray_flags) != OHMB200_OK)
+  {
+    return 0;
+  }
+  return element_count;
+}
+
+size_t ohmb200_integrate(ohmb200_map *m, const double *rays, size_t element_count, const float *intensities,
+                         const double *timestamps, unsigned ray_flags)
+{
+  if (!m || !rays || element_count < 2)
+  {
+    setError(OHMB200_E_INVALID, "ohmb200_integrate: bad arguments");
+    return 0;
+  }
+  cudaSetDevice(m->device);
+  const size_t n = element_count / 2;
+  const int buf = m->next_input;
+  m->next_input ^= 1;
+  // Drop inputs the map has no layer for (GpuMap.cpp:566-575).
+  if (!(m->params.layers & (1u << OHMB200_LAYER_INTENSITY)))
+  {
+    intensities = nullptr;
+  }
+  if (!(m->params.layers & (1u << OHMB200_LAYER_TOUCH_TIME)))
+  {
+    timestamps = nullptr;
+  }
+  if (timestamps && m->first_ray_time < 0)
+  {
+    m->first_ray_time = timestamps[0];
+  }
+  if (n > m->in_capacity[buf])
+  {
+    cudaEventSynchronize(m->in_free[buf]);
+    cudaFree(m->d_rays[buf]);
+    cudaFree(m->d_intensities[buf]);
+    cudaFree(m->d_timestamps[buf]);
+    const size_t cap = std::max<size_t>(n, 4096);
+    if (cudaMalloc(&m->d_rays[buf], sizeof(double) * 6 * cap) != cudaSuccess ||
+        cudaMalloc(&m->d_intensities[buf], sizeof(float) * cap) != cudaSuccess ||
+        cudaMalloc(&m->d_timestamps[buf], sizeof(double) * cap) != cudaSuccess)
+    {
+      setError(OHMB200_E_CUDA, "input staging allocation failed");
+      m->in_capacity[buf] = 0;
+      return 0;
+    }
+    m->in_capacity[buf] = cap;
+  }
+  // Upload on the copy stream once the kernels that last read this buffer are done; the other buffer's batch may
+  // still be running on the compute stream (upload/compute overlap).
+  cudaStreamWaitEvent(m->copy_stream, m->in_free[buf], 0);
+  bool ok = cudaMemcpyAsync(m->d_rays[buf], rays, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, m->copy_stream) ==
+            cudaSuccess;
+  if (intensities)
+  {
+    ok = ok && cudaMemcpyAsync(m->d_intensities[buf], intensities, sizeof(float) * n, cudaMemcpyHostToDevice,
+                               m->copy_stream) == cudaSuccess;
+  }
+  if (timestamps)
+  {
+    ok = ok && cudaMemcpyAsync(m->d_timestamps[buf], timestamps, sizeof(double) * n, cudaMemcpyHostToDevice,
+                               m->copy_stream) == cudaSuccess;
+  }
+  ok = ok && cudaEventRecord(m->in_ready[buf], m->copy_stream) == cudaSuccess;
+  ok = ok && cudaStreamWaitEvent(m->stream, m->in_ready[buf], 0) == cudaSuccess;
+  if (!ok)
+  {
+    setError(OHMB200_E_CUDA, "ray upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return 0;
+  }
+  const int rc = launchBatch(m, m->d_rays[buf], n, intensities ? m->d_intensities[buf] : nullptr,
+                             timestamps ? m->d_timestamps[buf] : nullptr, ray_flags);
+  cudaEventRecord(m->in_free[buf], m->stream);
+  // The caller's arrays are only guaranteed to be read during the call (GpuMap.cpp:843-862).
+  cudaEventSynchronize(m->in_ready[buf]);
+  return rc == OHMB200_OK ? element_count : 0;
+}
+
+int ohmb200_sync(ohmb200_map *m)
+{
+  if (!m)
+  {
+    return setError(OHMB200_E_INVALID, "null map");
+  }
+  cudaSetDevice(m->device);
+  CUDA_TRY(cudaStreamSynchronize(m->copy_stream));
+  int rc = pullCounters(m);
+  if (rc)
+  {
+    return rc;
+  }
+  if (m->h_counters->table_full)
+  {
+    return setError(OHMB200_E_CACHE_FULL, "region table full (%u slots): raise device_bytes", m->dm.capacity);
+  }
+  return OHMB200_OK;
+}
+
+size_t ohmb200_region_count(ohmb200_map *m)
+{
+  if (!m || pullCounters(m) != OHMB200_OK)
+  {
+    return 0;
+  }
+  return (size_t)m->h_counters->region_count;
+}
+
+size_t ohmb200_enumerate_regions(ohmb200_map *m, int16_t *keys_xyz, size_t capacity)
+{
+  if (!m)
+  {
+    return 0;
+  }
+  cudaSetDevice(m->device);
+  std::vector<unsigned long long> table(m->dm.capacity);
+  if (cudaMemcpyAsync(table.data(), m->dm.keys, sizeof(unsigned long long) * table.size(), cudaMemcpyDeviceToHost,
+                      m->stream) != cudaSuccess ||
+      cudaStreamSynchronize(m->stream) != cudaSuccess)
+  {
+    setError(OHMB200_E_CUDA, "region table download failed");
+    return 0;
+  }
+  struct R
+  {
+    int16_t x, y, z;
+  };
+  std::vector<R> regions;
+  for (unsigned long long k : table)
+  {
+    if (k != kEmptyKey)
+    {
+      regions.push_back({ (int16_t)(k & 0xffff), (int16_t)((k >> 16) & 0xffff), (int16_t)((k >> 32) & 0xffff) });
+    }
+  }
+  std::sort(regions.begin(), regions.end(), [](const R &a, const R &b) {
+    if (a.z != b.z)
+    {
+      return a.z < b.z;
+    }
+    if (a.y != b.y)
+    {
+      return a.y < b.y;
+    }
+    return a.x < b.x;
+  });
+  for (size_t i = 0; i < regions.size() && i < capacity && keys_xyz; ++i)
+  {
+    keys_xyz[3 * i] = regions[i].x;
+    keys_xyz[3 * i + 1] = regions[i].y;
+    keys_xyz[3 * i + 2] = regions[i].z;
+  }
+  return regions.size();
+}
+
+size_t ohmb200_region_layer_bytes(const ohmb200_map *m, int layer)
+{
+  if (!m || layer < 0 || layer >= OHMB200_LAYER_COUNT)
+  {
+    return 0;
+  }
+  return m->region_layer_bytes[layer];
+}
+
+int ohmb200_read_regions(ohmb200_map *m, int layer, const int16_t *keys_xyz, size_t count, void *dst, size_t bytes)
+{
+  if (!m || layer < 0 || layer >= OHMB200_LAYER_COUNT || !m->layer_slab[layer] || (!keys_xyz && count) || !dst)
+  {
+    return setError(OHMB200_E_INVALID, "ohmb200_read_regions: bad arguments or layer %d absent", layer);
+  }
+  const size_t chunk = m->region_layer_bytes[layer];
+  if (bytes < chunk * count)
+  {
+    return setError(OHMB200_E_INVALID, "destination too small: %zu < %zu", bytes, chunk * count);
+  }
+  if (count == 0)
+  {
+    return OHMB200_OK;
+  }
+  cudaSetDevice(m->device);
+  std::vector<uint32_t> slots;
+  int rc = findSlots(m, keys_xyz, count, slots);
+  if (rc)
+  {
+    return rc;
+  }
+  if (chunk * count > m->gather_bytes)
+  {
+    cudaFree(m->d_gather);
+    m->gather_bytes = 0;
+    CUDA_TRY(cudaMalloc(&m->d_gather, chunk * count));
+    m->gather_bytes = chunk * count;
+  }
+  if (count > m->gather_slots_cap)
+  {
+    cudaFree(m->d_gather_slots);
+    m->gather_slots_cap = 0;
+    CUDA_TRY(cudaMalloc(&m->d_gather_slots, sizeof(uint32_t) * count));
+    m->gather_slots_cap = count;
+  }
+  CUDA_TRY(cudaMemcpyAsync(m->d_gather_slots, slots.data(), sizeof(uint32_t) * count, cudaMemcpyHostToDevice, m->stream));
+  if (chunk % 16 == 0)
+  {
+    KernelScope scope(m, kKGather);
+    gatherRegions<<<(unsigned)count, 256, 0, m->stream>>>((const uint4 *)m->layer_slab[layer], m->d_gather_slots,
+                                                          (uint4 *)m->d_gather, chunk / 16);
+  }
+  else
+  {
+    for (size_t i = 0; i < count; ++i)
+    {
+      CUDA_TRY(cudaMemcpyAsync((char *)m->d_gather + i * chunk, (const char *)m->layer_slab[layer] + (size_t)slots[i] * chunk,
+                               chunk, cudaMemcpyDeviceToDevice, m->stream));
+    }
+  }
+  CUDA_TRY(cudaMemcpyAsync(dst, m->d_gather, chunk * count, cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  return OHMB200_OK;
+}
+
+int ohmb200_read_region(ohmb200_map *m, const int16_t key_xyz[3], int layer, void *dst, size_t bytes)
+{
+  return ohmb200_read_regions(m, layer, key_xyz, 1, dst, bytes);
+}
+
+__global__ void insertRegion(DeviceMap dm, unsigned long long key, int *slot_out)
+{
+  *slot_out = regionSlot(dm, key);
+}
+
+int ohmb200_write_region(ohmb200_map *m, const int16_t key_xyz[3], int layer, const void *src, size_t bytes)
+{
+  if (!m || !key_xyz || layer < 0 || layer >= OHMB200_LAYER_COUNT || !m->layer_slab[layer] || !src)
+  {
+    return setError(OHMB200_E_INVALID, "ohmb200_write_region: bad arguments or layer absent");
+  }
+  const size_t chunk = m->region_layer_bytes[layer];
+  if (bytes != chunk)
+  {
+    return setError(OHMB200_E_INVALID, "chunk size mismatch: %zu != %zu", bytes, chunk);
+  }
+  cudaSetDevice(m->device);
+  const unsigned long long key = (unsigned long long)(uint16_t)key_xyz[0] | ((unsigned long long)(uint16_t)key_xyz[1] << 16) |
+                                 ((unsigned long long)(uint16_t)key_xyz[2] << 32);
+  int *d_slot = (int *)&m->d_counters->record_count;  // scratch word, reset before every batch
+  insertRegion<<<1, 1, 0, m->stream>>>(m->dm, key, d_slot);
+  int slot = -1;
+  CUDA_TRY(cudaMemcpyAsync(&slot, d_slot, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  if (slot < 0)
+  {
+    return setError(OHMB200_E_CACHE_FULL, "region table full");
+  }
+  CUDA_TRY(cudaMemcpyAsync((char *)m->layer_slab[layer] + (size_t)slot * chunk, src, chunk, cudaMemcpyHostToDevice,
+                           m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  return OHMB200_OK;
+}
+
+int ohmb200_clear(ohmb200_map *m)
+{
+  if (!m)
+  {
+    return setError(OHMB200_E_INVALID, "null map");
+  }
+  cudaSetDevice(m->device);
+  CUDA_TRY(cudaStreamSynchronize(m->copy_stream));
+  int rc = initialiseSlabs(m);
+  if (rc)
+  {
+    return rc;
+  }
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  return OHMB200_OK;
+}
+
+double ohmb200_first_ray_time(const ohmb200_map *m)
+{
+  return m ? m->first_ray_time : -1.0;
+}
+
+int ohmb200_set_first_ray_time(ohmb200_map *m, double t)
+{
+  if (!m)
+  {
+    return setError(OHMB200_E_INVALID, "null map");
+  }
+  m->first_ray_time = t;
+  return OHMB200_OK;
+}
+
+int ohmb200_get_stats(ohmb200_map *m, ohmb200_stats *stats)
+{
+  if (!m || !stats)
+  {
+    return setError(OHMB200_E_INVALID, "null argument");
+  }
+  cudaSetDevice(m->device);
+  int rc = pullCounters(m);
+  if (rc)
+  {
+    return rc;
+  }
+  stats->rays_in = m->rays_in;
+  stats->rays_accepted = m->h_counters->rays_accepted;
+  stats->voxel_visits = m->h_counters->voxel_visits;
+  stats->sample_updates = m->h_counters->sample_updates;
+  stats->ordered_records = m->h_counters->ordered_records;
+  stats->regions = m->h_counters->region_count;
+  stats->region_capacity = m->dm.capacity;
+  stats->batches = m->batches;
+  stats->kernel_launches = m->launches;
+  return OHMB200_OK;
+}
+
+int ohmb200_set_stream(ohmb200_map *m, void *cuda_stream)
+{
+  if (!m)
+  {
+    return setError(OHMB200_E_INVALID, "null map");
+  }
+  cudaSetDevice(m->device);
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  m->stream = cuda_stream ? (cudaStream_t)cuda_stream : m->own_stream;
+  return OHMB200_OK;
+}
+
+int ohmb200_set_profiling(ohmb200_map *m, int enabled)
+{
+  if (!m)
+  {
+    return setError(OHMB200_E_INVALID, "null map");
+  }
+  drainSpans(m);
+  m->profiling = enabled != 0;
+  return OHMB200_OK;
+}
+
+int ohmb200_kernel_times(ohmb200_map *m, ohmb200_kernel_time *out, int capacity, int reset)
+{
+  if (!m || !out)
+  {
+    return setError(OHMB200_E_INVALID, "null argument");
+  }
+  cudaSetDevice(m->device);
+  drainSpans(m);
+  int n = 0;
+  for (int k = 0; k < kKernelCount && n < capacity; ++k)
+  {
+    if (m->kernel_launches[k] == 0)
+    {
+      continue;
+    }
+    memset(&out[n], 0, sizeof(out[n]));
+    strncpy(out[n].name, kKernelNames[k], sizeof(out[n].name) - 1);
+    out[n].ms = m->kernel_ms[k];
+    out[n].launches = m->kernel_launches[k];
+    ++n;
+  }
+  if (reset)
+  {
+    memset(m->kernel_ms, 0, sizeof(m->kernel_ms));
+    memset(m->kernel_launches, 0, sizeof(m->kernel_launches));
+  }
+  return n;
+}
+
+}  // extern "C"

@@ -1,0 +1,535 @@
+// ohmb200_device.cuh — device-side map model, key maths and the exact fp64 voxel walk.
+//
+// Everything here is compiled with --fmad=false: the parity target is ohm's CPU mapper, whose x86-64 build
+// never contracts a*b+c into an FMA, and the voxel sequence of a ray is decided by comparisons of such
+// expressions.  All fp64 operators used (+ - * / sqrt floor) are IEEE-754 correctly rounded on sm_100a, so a
+// ray produces bit-identical exit times — hence identical voxel keys — on the device and in the CPU mapper.
+//
+// Semantics follow (reference file:line, csiro-robotics/ohm @ 4e2e769):
+//   point -> key        ohm/MapCoord.h:37-93, ohm/MapRegion.cpp:32-69
+//   key -> centre       ohm/OccupancyMap.h:757-778
+//   key stepping/diff   ohm/OccupancyMap.h:827-846,887-901
+//   voxel walk          ohm/LineWalkCompute.h:162-413 (driven as ohm/LineWalk.h:112-129 does on the CPU)
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ohmb200
+{
+constexpr uint64_t kEmptyKey = ~0ull;
+constexpr uint32_t kHitFlag = 0x80000000u;   // pending word: voxel has sample updates in this batch
+constexpr uint32_t kInvalidVoxel = 0xFFFFFFFFu;
+
+// Ray filter result flags (ohm/RayFilter.h:22-29)
+constexpr unsigned kRffInvalid = 1u, kRffClippedStart = 2u, kRffClippedEnd = 4u;
+// Walk flags (ohm/LineWalk.h:51-57)
+constexpr unsigned kExcludeStartVoxel = 1u, kExcludeEndVoxel = 2u;
+
+struct Geom
+{
+  double res;
+  double region_size[3];
+  double origin[3];
+  int dim[3];
+  uint32_t vpr;  // voxels per region
+};
+
+struct MapParams
+{
+  float hit_value, miss_value, min_value, max_value, threshold_value;
+  float sat_min, sat_max;  // lowest()/max() when saturation is disabled (RayMapperOccupancy.cpp:94-95)
+  int filter_kind;
+  double filter_range;
+  float sensor_noise, adaptation_rate, reinit_threshold, initial_intensity_cov;
+  uint32_t reinit_count, sample_threshold;
+  int ndt_tm;
+  float tsdf_max_weight, tsdf_trunc, tsdf_dropoff, tsdf_sparsity;
+};
+
+// Region table + layer slabs.  A region's slab slot IS its hash-table index: slabs are initialised to the layer
+// clear values once, so inserting a region is a single 64-bit CAS and needs no per-region setup.
+struct DeviceMap
+{
+  unsigned long long *keys;  // [capacity] packed region keys, kEmptyKey when free
+  uint32_t capacity;
+  uint32_t *region_stamp;    // [capacity] last batch stamp that walked the region
+  uint32_t *pending;         // [capacity * vpr] per-batch miss counters / kHitFlag|run
+  float *occupancy;          // layer slabs, nullptr when the layer is absent
+  uint2 *mean;
+  float *traversal;
+  uint32_t *touch_time;
+  uint32_t *incident;
+  float *covariance;         // 6 floats per voxel
+  float2 *intensity;
+  uint2 *hit_miss;
+  float2 *tsdf;
+  unsigned long long *region_count;  // device counter of occupied slots
+  int *table_full;                   // set when an insert found no free slot
+};
+
+struct Key
+{
+  int r[3];  // region
+  int l[3];  // local voxel
+};
+
+__device__ __forceinline__ unsigned long long packRegion(int x, int y, int z)
+{
+  return (unsigned long long)(uint16_t)x | ((unsigned long long)(uint16_t)y << 16) |
+         ((unsigned long long)(uint16_t)z << 32);
+}
+
+__host__ __device__ __forceinline__ uint32_t hashRegion(unsigned long long k)
+{
+  k *= 0x9E3779B97F4A7C15ull;
+  return (uint32_t)(k >> 32) ^ (uint32_t)k;
+}
+
+// Find or insert a region; returns its slot, or -1 when the table is full.
+__device__ inline int regionSlot(const DeviceMap &m, unsigned long long key)
+{
+  uint32_t h = hashRegion(key) % m.capacity;
+  for (uint32_t probe = 0; probe < m.capacity; ++probe)
+  {
+    unsigned long long k = m.keys[h];
+    if (k == key)
+    {
+      return (int)h;
+    }
+    if (k == kEmptyKey)
+    {
+      const unsigned long long old = atomicCAS(&m.keys[h], kEmptyKey, key);
+      if (old == kEmptyKey)
+      {
+        atomicAdd(m.region_count, 1ull);
+        return (int)h;
+      }
+      if (old == key)
+      {
+        return (int)h;
+      }
+    }
+    h = (h + 1 == m.capacity) ? 0 : h + 1;
+  }
+  *m.table_full = 1;
+  return -1;
+}
+
+// Lookup only.
+__device__ inline int regionFind(const DeviceMap &m, unsigned long long key)
+{
+  uint32_t h = hashRegion(key) % m.capacity;
+  for (uint32_t probe = 0; probe < m.capacity; ++probe)
+  {
+    const unsigned long long k = m.keys[h];
+    if (k == key)
+    {
+      return (int)h;
+    }
+    if (k == kEmptyKey)
+    {
+      return -1;
+    }
+    h = (h + 1 == m.capacity) ? 0 : h + 1;
+  }
+  return -1;
+}
+
+// ohm/MapCoord.h:85-93
+__device__ __forceinline__ int pointToRegionCoord(double coord, double resolution)
+{
+  return (int)floor(coord / resolution + 0.5);
+}
+
+// ohm/MapCoord.h:41-80
+__device__ __forceinline__ int pointToRegionVoxel(double coord, double voxel_resolution, double region_resolution)
+{
+  const double epsilon = (double)1e-6f;
+  if (-epsilon <= coord && coord < 0)
+  {
+    coord = 0;
+  }
+  else if (coord >= region_resolution && coord - epsilon < region_resolution)
+  {
+    coord -= epsilon;
+  }
+  return (int)floor(coord / voxel_resolution);
+}
+
+// ohm/OccupancyMap.cpp:859-886 -> ohm/MapRegion.cpp:32-69.  false => null key.
+__device__ inline bool voxelKey(const Geom &g, const double p[3], Key &key)
+{
+  bool ok = true;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+  {
+    const int rc = (int)(int16_t)pointToRegionCoord(p[a] - g.origin[a], g.region_size[a]);
+    const double centre = rc * g.region_size[a];
+    const double region_min = centre - 0.5 * g.region_size[a];
+    const double local = p[a] - g.origin[a] - region_min;
+    const int q = pointToRegionVoxel(local, g.res, g.region_size[a]);
+    key.r[a] = rc;
+    key.l[a] = q;
+    ok = ok && (0 <= q && q < g.dim[a]);
+  }
+  return ok;
+}
+
+// ohm/OccupancyMap.h:757-778
+__device__ __forceinline__ double voxelCentreAxis(const Geom &g, int region, int local, int a)
+{
+  double c = (double)(float)region;
+  c *= g.region_size[a];
+  c -= 0.5 * g.region_size[a];
+  c += g.origin[a];
+  c += (double)local * g.res;
+  c += 0.5 * g.res;
+  return c;
+}
+
+__device__ __forceinline__ uint32_t voxelIndex(const Geom &g, const Key &k)
+{
+  // ohm/MapChunk.h:47-50
+  return (uint32_t)k.l[0] + (uint32_t)k.l[1] * g.dim[0] + (uint32_t)k.l[2] * g.dim[0] * g.dim[1];
+}
+
+// ohm/RayFilter.cpp:15-55.  Returns false for a rejected ray; may move `end` and set kRffClippedEnd.
+__device__ inline bool applyRayFilter(const MapParams &p, double start[3], double end[3], unsigned &filter_flags)
+{
+  if (p.filter_kind == 0)
+  {
+    return true;
+  }
+  bool good = true;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+  {
+    good = good && !isnan(start[a]) && !isinf(start[a]) && !isnan(end[a]) && !isinf(end[a]);
+  }
+  double ray[3] = { end[0] - start[0], end[1] - start[1], end[2] - start[2] };
+  const double len2 = (ray[0] * ray[0] + ray[1] * ray[1]) + ray[2] * ray[2];
+  const double range = p.filter_range;
+  if (p.filter_kind == 1)
+  {
+    good = good && (range <= 0 || len2 <= range * range);
+    if (!good)
+    {
+      filter_flags |= kRffInvalid;
+    }
+    return good;
+  }
+  // clipRayFilter
+  if (good && range > 0 && len2 > range * range)
+  {
+    const double len = sqrt(len2);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+    {
+      ray[a] /= len;
+      end[a] = start[a] + ray[a] * range;
+    }
+    filter_flags |= kRffClippedEnd;
+  }
+  if (!good)
+  {
+    filter_flags |= kRffInvalid;
+  }
+  return good;
+}
+
+// State of one ray's voxel walk.  time_next[a] is always recomputed as initial + delta * |stepped| (never
+// accumulated, LineWalkCompute.h:298-300), so the walk can be resumed anywhere from `stepped` alone.
+struct Walk
+{
+  double initial[3];
+  double delta[3];
+  double time_next[3];
+  double length;
+  int remaining[3];
+  int stepped[3];
+  int dir[3];  // +1 / -1
+  Key cur;
+  Key end;
+  int axis;
+  unsigned limit;
+};
+
+__device__ __forceinline__ int selectNextAxis(const double t[3])
+{
+  int axis = 0;
+  axis = (t[axis] < t[1]) ? axis : 1;
+  axis = (t[axis] < t[2]) ? axis : 2;
+  return axis;
+}
+
+// LineWalkCompute.h:188-280 + the set-up half of walkLineVoxels (:351-379).
+__device__ inline void walkInit(Walk &w, const Geom &g, const double start[3], const double end[3], const Key &skey,
+                                const Key &ekey)
+{
+  double dir[3], inv[3];
+  int sign[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+  {
+    dir[a] = end[a] - start[a];
+  }
+  double length = dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2];
+  length = (length > 1e-6) ? sqrt(length) : 0;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+  {
+    sign[a] = dir[a] < 0;
+    dir[a] /= length;
+    inv[a] = (length > 0) ? 1 / dir[a] : 0;
+  }
+  w.length = length;
+  w.limit = 0;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+  {
+    const double centre = voxelCentreAxis(g, skey.r[a], skey.l[a], a);
+    double vmin = centre - 0.5 * g.res;
+    double vmax = centre + 0.5 * g.res;
+    const double initial = ((sign[a] ? vmin : vmax) - start[a]) * inv[a];
+    const int sd = -2 * sign[a] + 1;
+    const double shift = sd * g.res;
+    vmin += shift;
+    vmax += shift;
+    double delta = ((sign[a] ? vmin : vmax) - start[a]) * inv[a];
+    if (delta != (double)INFINITY)
+    {
+      delta -= initial;
+    }
+    w.initial[a] = initial;
+    w.delta[a] = delta;
+    w.dir[a] = sd;
+    w.stepped[a] = 0;
+    w.remaining[a] = ekey.l[a] - skey.l[a] + (int)(int16_t)(ekey.r[a] - skey.r[a]) * g.dim[a];
+    w.limit |= (w.remaining[a] == 0) ? (1u << a) : 0u;
+    w.time_next[a] = w.remaining[a] ? initial : (double)INFINITY;
+  }
+  w.cur = skey;
+  w.end = ekey;
+  w.axis = selectNextAxis(w.time_next);
+}
+
+// LineWalkCompute.h:291-307 (+ key stepping OccupancyMap.h:827-846)
+__device__ __forceinline__ void walkStep(Walk &w, const Geom &g)
+{
+  // Select by predication rather than dynamic indexing to keep the state in registers.
+  const int a = w.axis;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+  {
+    if (i == a)
+    {
+      const int d = w.dir[i];
+      int local = w.cur.l[i] + d;
+      int region = w.cur.r[i];
+      if (local < 0)
+      {
+        --region;
+        local = g.dim[i] - 1;
+      }
+      else if (local >= g.dim[i])
+      {
+        ++region;
+        local = 0;
+      }
+      w.cur.l[i] = local;
+      w.cur.r[i] = (int)(int16_t)region;
+      w.remaining[i] -= d;
+      w.stepped[i] += d;
+      w.time_next[i] = w.remaining[i] ? w.initial[i] + w.delta[i] * abs(w.stepped[i]) : (double)INFINITY;
+      w.limit |= (w.remaining[i] == 0) ? (1u << i) : 0u;
+    }
+  }
+  w.axis = selectNextAxis(w.time_next);
+}
+
+__device__ __forceinline__ bool walkAtEnd(const Walk &w)
+{
+  return w.cur.r[0] == w.end.r[0] && w.cur.r[1] == w.end.r[1] && w.cur.r[2] == w.end.r[2] &&
+         w.cur.l[0] == w.end.l[0] && w.cur.l[1] == w.end.l[1] && w.cur.l[2] == w.end.l[2];
+}
+
+__device__ __forceinline__ double walkNextTime(const Walk &w)
+{
+  return (w.axis == 0) ? w.time_next[0] : ((w.axis == 1) ? w.time_next[1] : w.time_next[2]);
+}
+
+// Drives `visit(key, enter, exit)` exactly as walkLineVoxels (LineWalkCompute.h:345-413) would.
+template <typename Visit>
+__device__ inline unsigned walkLine(const Geom &g, const double start[3], const double end[3], const Key &skey,
+                                    const Key &ekey, unsigned flags, Visit &&visit)
+{
+  Walk w;
+  walkInit(w, g, start, end, skey, ekey);
+  double last_time = 0;
+  unsigned count = 0;
+  if (flags & kExcludeStartVoxel)
+  {
+    last_time = walkNextTime(w);
+    ++count;
+    walkStep(w, g);
+  }
+  while (w.limit < 7u && !walkAtEnd(w))
+  {
+    const double t = walkNextTime(w);
+    visit(w.cur, last_time, t);
+    last_time = t;
+    ++count;
+    walkStep(w, g);
+  }
+  if ((flags & kExcludeEndVoxel) == 0u)
+  {
+    visit(ekey, last_time, w.length);
+    ++count;
+  }
+  return count;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Per-voxel arithmetic
+// ---------------------------------------------------------------------------------------------------------
+
+// One miss applied to `v` with the CPU mapper's flag logic (RayMapperOccupancy.cpp:150-166 +
+// VoxelOccupancyCompute.h:110-120).  A pure function of v, so k identical misses commute with each other.
+__device__ __forceinline__ float missOnce(float v, const MapParams &p, unsigned ray_flags)
+{
+  const float uninit = INFINITY;
+  const bool unobserved = v == uninit;
+  const bool is_free = !unobserved && v < p.threshold_value;
+  const bool occupied = !unobserved && v >= p.threshold_value;
+  float adj = p.miss_value;
+  adj = (unobserved && (ray_flags & (1u << 5))) ? uninit : adj;
+  adj = (is_free && (ray_flags & (1u << 6))) ? 0.0f : adj;
+  adj = (occupied && (ray_flags & (1u << 7))) ? 0.0f : adj;
+  const float base = (!unobserved) ? v : 0.0f;
+  adj = (unobserved || (p.sat_min < v && v < p.sat_max)) ? adj : 0.0f;
+  return (base != uninit) ? fmaxf(p.min_value, base + adj) : base;
+}
+
+// `count` consecutive misses.  Stops early at a fixed point (min clamp, saturation, exclusion).
+__device__ __forceinline__ float missRepeat(float v, uint32_t count, const MapParams &p, unsigned ray_flags)
+{
+  while (count)
+  {
+    const float n = missOnce(v, p, ray_flags);
+    if (n == v)
+    {
+      break;
+    }
+    v = n;
+    --count;
+  }
+  return v;
+}
+
+// RayMapperOccupancy.cpp:262-279 + VoxelOccupancyCompute.h:44-54
+__device__ __forceinline__ float hitOnce(float v, const MapParams &p, unsigned ray_flags)
+{
+  const float uninit = INFINITY;
+  const bool unobserved = v == uninit;
+  const bool is_free = !unobserved && v < p.threshold_value;
+  const bool occupied = !unobserved && v >= p.threshold_value;
+  float adj = p.hit_value;
+  adj = (unobserved && (ray_flags & (1u << 5))) ? uninit : adj;
+  adj = (is_free && (ray_flags & (1u << 6))) ? 0.0f : adj;
+  adj = (occupied && (ray_flags & (1u << 7))) ? 0.0f : adj;
+  const float base = (!unobserved) ? v : 0.0f;
+  adj = (unobserved || (p.sat_min < v && v < p.sat_max)) ? adj : 0.0f;
+  return (base != uninit) ? fminf(base + adj, p.max_value) : base;
+}
+
+// ohm/VoxelMeanCompute.h:69-152 instantiated as the CPU mappers do: <glm::dvec3, double>.
+__device__ __forceinline__ void subVoxelToLocal(uint32_t coord, double resolution, double out[3])
+{
+  const double mean_resolution = resolution / (double)1023;
+  const double offset = (double)0.5f * resolution;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+  {
+    out[a] = (int)((coord >> (10 * a)) & 1023u) * mean_resolution - offset;
+  }
+}
+
+__device__ __forceinline__ uint32_t subVoxelCoord(const double local[3], double resolution)
+{
+  const double mean_resolution = resolution / (double)1023;
+  const double offset = (double)0.5f * resolution;
+  uint32_t pattern = 0;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+  {
+    int pos = pointToRegionCoord(local[a] + offset, mean_resolution);
+    pos = (pos >= 0 ? (pos < 1024 ? pos : 1023) : 0);
+    pattern |= ((uint32_t)pos) << (10 * a);
+  }
+  return pattern | (1u << 31);
+}
+
+__device__ __forceinline__ uint32_t subVoxelUpdate(uint32_t coord, uint32_t count, const double local[3],
+                                                   double resolution)
+{
+  double mean[3];
+  subVoxelToLocal(coord, resolution, mean);
+  const double w = (double)1 / (double)(count + 1u);
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+  {
+    mean[a] += (local[a] - mean[a]) * w;
+  }
+  return subVoxelCoord(mean, resolution);
+}
+
+// ohm/VoxelIncidentCompute.h:35-112 (float arithmetic; sqrtf and '/' are IEEE under -prec-sqrt/-prec-div)
+__device__ inline uint32_t updateIncidentNormal(uint32_t packed, float ix, float iy, float iz, uint32_t count)
+{
+  float nx = (2.0f * ((float)((packed >> 0) & 0x3FFFu) / 16383.0f)) - 1.0f;
+  float ny = (2.0f * ((float)((packed >> 15) & 0x3FFFu) / 16383.0f)) - 1.0f;
+  nx = fmaxf(-1.0f, fminf(nx, 1.0f));
+  ny = fmaxf(-1.0f, fminf(ny, 1.0f));
+  float nz = fmaxf(-1.0f, fminf(1.0f - (nx * nx + ny * ny), 1.0f));
+  const bool set = (packed & (1u << 30)) != 0;
+  nx = set ? nx : 0.0f;
+  ny = set ? ny : 0.0f;
+  nz = set ? sqrtf(nz) : 0.0f;
+  nz *= (packed & (1u << 31)) ? -1.0f : 1.0f;
+
+  count = ((nx != 0 || ny != 0 || nz != 0) && count) ? count : 0;
+  const float w = 1.0f / (float)(count + 1u);
+  float len2 = ix * ix + iy * iy + iz * iz;
+  float s = (len2 > 1e-6f) ? 1.0f / sqrtf(len2) : 0.0f;
+  ix *= s;
+  iy *= s;
+  iz *= s;
+  nx += (ix - nx) * w;
+  ny += (iy - ny) * w;
+  nz += (iz - nz) * w;
+  len2 = nx * nx + ny * ny + nz * nz;
+  s = (len2 > 1e-6f) ? 1.0f / sqrtf(len2) : 0.0f;
+  nx *= s;
+  ny *= s;
+  nz *= s;
+
+  const float ex = 0.5f * (fmaxf(-1.0f, fminf(nx, 1.0f)) + 1.0f);
+  const float ey = 0.5f * (fmaxf(-1.0f, fminf(ny, 1.0f)) + 1.0f);
+  uint32_t n = 0;
+  n |= ((uint32_t)(ex * 16383.0f) & 0x3FFFu) << 0;
+  n |= ((uint32_t)(ey * 16383.0f) & 0x3FFFu) << 15;
+  n &= ~((1u << 30) | (1u << 31));
+  n |= (nz < 0) ? (1u << 31) : 0u;
+  n |= (ex != 0.0f || ey != 0.0f || nz != 0.0f) ? (1u << 30) : 0u;
+  return n;
+}
+
+// ohm/VoxelTouchTimeCompute.h:18-27
+__device__ __forceinline__ uint32_t encodeTouchTime(double timebase, double timestamp)
+{
+  // x86-64 converts double -> unsigned through a 64-bit truncation; mirror that rather than saturating.
+  return (uint32_t)(long long)((timestamp - timebase) / 0.001);
+}
+
+}  // namespace ohmb200

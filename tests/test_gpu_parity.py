@@ -1,0 +1,215 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on identical seeded inputs.
+
+Mirrors tests/ohmtestgpu/GpuMapTest.cpp of the reference (gpuMapTest / compareMaps), but with a bit-exact bar
+for keys, counts and occupancy instead of the reference's "99% of voxels within half a hit".
+"""
+import numpy as np
+import pytest
+
+import ohm_b200
+from ohm_b200 import gpumap as gm
+from ohm_b200.lidar import LidarBox, cube_rays
+from parity import check_counts, compare_maps, integrate_both, make_pair
+
+pytestmark = pytest.mark.gpu
+
+
+def random_rays(count, extent, seed=5489, origin=(0.05, 0.05, 0.05)):
+    # GpuMapTest.cpp:341-351: sensor at (0.05,0.05,0.05), samples uniform in +-extent (mt19937 default seed)
+    rng = np.random.RandomState(seed)
+    rays = np.empty((2 * count, 3))
+    rays[0::2] = np.asarray(origin)
+    rays[1::2] = rng.uniform(-extent, extent, size=(count, 3))
+    return rays
+
+
+def test_config1_single_region(gpu):
+    """BASELINE config 1: 10k rays into a 0.2 m map, one region."""
+    g, c = make_pair(0.2)
+    integrate_both(g, c, cube_rays(10000))
+    s = compare_maps(g, c)
+    assert s["regions"] == 1
+    st = check_counts(g, c)
+    assert st["rays_accepted"] == 10000
+
+
+def test_populate_tiny(gpu):
+    # GpuMapTest.cpp PopulateTiny: two rays
+    g, c = make_pair(0.25)
+    rays = np.array([[0.3, 0, 0], [1.1, 0, 0], [-5.0, 0, 0], [0.3, 0, 0]])
+    integrate_both(g, c, rays)
+    compare_maps(g, c)
+    check_counts(g, c)
+
+
+def test_populate_small(gpu):
+    # GpuMapTest.cpp:332-350 PopulateSmall: 64 rays +-50 m, batches of 32
+    g, c = make_pair(0.25)
+    integrate_both(g, c, random_rays(64, 50.0), batch=32)
+    compare_maps(g, c)
+    check_counts(g, c)
+
+
+def test_populate_large_batched(gpu):
+    # GpuMapTest.cpp:352-371 PopulateLarge (131072 rays +-25 m, batch 2048), at a quarter of the ray count
+    g, c = make_pair(0.25, device_bytes=4 << 30)
+    integrate_both(g, c, random_rays(32768, 25.0), batch=2048)
+    compare_maps(g, c)
+    st = check_counts(g, c)
+    assert st["batches"] == 16
+
+
+def test_compare_in_voxel_rays_then_clear(gpu):
+    # GpuMapTest.cpp:525-630 GpuMap.Compare: degenerate rays inside every voxel of a 16^3 region => every voxel
+    # == hit value exactly; then 16 clearing rays with a stronger miss value.
+    g, c = make_pair(0.25, region_dim=(16, 16, 16))
+    centres = []
+    for z in range(16):
+        for y in range(16):
+            for x in range(16):
+                centres.append(c.voxel_centre([0, 0, 0, x, y, z]))
+    centres = np.asarray(centres)
+    rays = np.repeat(centres, 2, axis=0)
+    integrate_both(g, c, rays)
+    compare_maps(g, c)
+    occ = g.region_layer((0, 0, 0), gm.LAYER_OCCUPANCY)
+    assert np.all(occ == np.float32(g.hit_value()))
+    # miss value := -hit + miss (GpuMapTest.cpp:592-593), then clear the bottom slice along y
+    new_miss = float(np.float32(-g.hit_value()) + np.float32(g.miss_value()))
+    g.set_miss_value(new_miss)
+    c.set_params(miss_value=new_miss)
+    clear = []
+    for x in range(16):
+        clear.append(c.voxel_centre([0, 0, 0, x, 0, 0]))
+        clear.append(c.voxel_centre([0, 0, 0, x, 15, 0]))
+    integrate_both(g, c, np.asarray(clear))
+    compare_maps(g, c)
+    occ = g.region_layer((0, 0, 0), gm.LAYER_OCCUPANCY).reshape(16, 16, 16)  # [z, y, x]
+    assert np.all(occ[0, :15, :] < 0) and np.all(occ[0, 15, :] > 0) and np.all(occ[1:] == np.float32(g.hit_value()))
+
+
+@pytest.mark.parametrize("flags", [
+    gm.RF_END_POINT_AS_FREE, gm.RF_EXCLUDE_ORIGIN, gm.RF_EXCLUDE_SAMPLE, gm.RF_EXCLUDE_RAY,
+    gm.RF_EXCLUDE_UNOBSERVED, gm.RF_EXCLUDE_FREE, gm.RF_EXCLUDE_OCCUPIED, gm.RF_REVERSE_WALK,
+    gm.RF_EXCLUDE_ORIGIN | gm.RF_END_POINT_AS_FREE,
+])
+def test_ray_flags(gpu, flags):
+    g, c = make_pair(0.25)
+    rays = random_rays(4096, 12.0, seed=7)
+    # a first default pass so that the exclusion flags see free, occupied and unobserved voxels
+    integrate_both(g, c, rays[:4096])
+    integrate_both(g, c, rays[4096:], ray_flags=flags)
+    integrate_both(g, c, rays[2048:6144], ray_flags=flags)
+    compare_maps(g, c)
+    check_counts(g, c)
+
+
+def test_clip_range_filter(gpu):
+    # clipRayFilter: long rays are clipped, flagged kRffClippedEnd and their end voxel takes a miss, not a hit
+    g, c = make_pair(0.25, filter_kind=gm.FILTER_CLIP_RANGE, filter_range=10.0)
+    integrate_both(g, c, random_rays(4096, 25.0, seed=11))
+    compare_maps(g, c)
+    st = check_counts(g, c)
+    assert st["sample_updates"] < 4096
+
+
+def test_bad_rays_are_dropped(gpu):
+    # GpuMapTest.cpp:817-835 CheckBadRays + goodRayFilter: NaN/inf/too-long rays are skipped, tiny rays terminate
+    g, c = make_pair(0.1, filter_range=100.0)
+    rays = random_rays(256, 5.0, seed=3)
+    rays[3] = [np.nan, 0, 0]
+    rays[9] = [np.inf, 1, 1]
+    rays[20] = [0, -np.inf, 1]
+    rays[41] = [500.0, 0, 0]               # beyond filter_range
+    rays[50] = rays[51] = [0.30001, 0.2, 0.1]  # zero length
+    rays[61] = rays[60] + 1e-9             # sub-epsilon
+    integrate_both(g, c, rays)
+    compare_maps(g, c)
+    st = check_counts(g, c)
+    assert st["rays_accepted"] == 256 - 4
+
+
+def test_all_sample_layers(gpu):
+    """Voxel mean, incident normal, touch time (exact) and traversal (fp tolerance: summation order)."""
+    layers = [gm.LAYER_OCCUPANCY, gm.LAYER_MEAN, gm.LAYER_TRAVERSAL, gm.LAYER_TOUCH_TIME, gm.LAYER_INCIDENT]
+    g, c = make_pair(0.2, layers=layers)
+    n = 8192
+    rays = random_rays(n, 6.0, seed=21)
+    ts = 100.0 + np.arange(n) * 1e-3
+    integrate_both(g, c, rays, timestamps=ts, batch=3000)
+    compare_maps(g, c, tol_layers={gm.LAYER_TRAVERSAL: 2e-4})
+    assert g.first_ray_time() == c.first_ray_time() == 100.0
+    check_counts(g, c)
+
+
+def test_many_samples_one_voxel(gpu):
+    # GpuVoxelMeanTests / Ndt.Hit shape: thousands of samples into a single 2 m voxel — mean count must be exact
+    layers = [gm.LAYER_OCCUPANCY, gm.LAYER_MEAN, gm.LAYER_INCIDENT]
+    g, c = make_pair(2.0, layers=layers)
+    rng = np.random.RandomState(1153297050 % 2 ** 32)
+    n = 5000
+    rays = np.zeros((2 * n, 3))
+    rays[0::2] = [1.0, 1.0, 5.0]
+    rays[1::2] = rng.uniform(0.01, 1.99, size=(n, 3))
+    integrate_both(g, c, rays, batch=1024)
+    compare_maps(g, c)
+    key = c.voxel_key([1.0, 1.0, 1.0])
+    mean = g.region_layer(tuple(key[:3]), gm.LAYER_MEAN)
+    idx = key[3] + 32 * key[4] + 32 * 32 * key[5]
+    assert mean[idx, 1] == n
+
+
+def test_lidar_sweep_config2(gpu):
+    """BASELINE config 2: one 64x2048 sweep at 0.1 m, occupancy only — bit-exact map, exact V/S/N."""
+    g, c = make_pair(0.1, device_bytes=4 << 30)
+    rays, _, _ = LidarBox(1).sweep()
+    integrate_both(g, c, rays)
+    s = compare_maps(g, c)
+    st = check_counts(g, c)
+    assert st["rays_accepted"] == rays.shape[0] // 2
+    assert s["regions"] > 1000
+
+
+def test_lidar_two_sweeps_with_mean(gpu):
+    layers = [gm.LAYER_OCCUPANCY, gm.LAYER_MEAN]
+    g, c = make_pair(0.1, device_bytes=6 << 30, layers=layers)
+    box = LidarBox(2)
+    for k in range(2):
+        rays, _, _ = box.sweep()
+        # app-sized batches for the second sweep (ohmapp/OhmAppCpu.h:52)
+        integrate_both(g, c, rays, batch=None if k == 0 else 4096 * 8)
+    compare_maps(g, c)
+    check_counts(g, c)
+
+
+def test_empty_and_ragged(gpu):
+    g, c = make_pair(0.25)
+    assert g.L.ohmb200_integrate(g.h, None, 0, None, None, 0) == 0
+    rays = random_rays(3, 4.0)
+    # element_count odd: the trailing origin without a sample is ignored (element_count / 2 rays)
+    g.integrate_rays(rays[:5])
+    c.integrate_rays(rays[:4])
+    g.sync_voxels()
+    compare_maps(g, c)
+    assert g.region_count() == len(c.region_keys())
+
+
+def test_clear_and_reuse(gpu):
+    g, c = make_pair(0.25)
+    g.integrate_rays(random_rays(512, 10.0, seed=5))
+    g.sync_voxels()
+    assert g.region_count() > 0
+    g.clear()
+    assert g.region_count() == 0
+    integrate_both(g, c, random_rays(512, 10.0, seed=6))
+    compare_maps(g, c)
+
+
+def test_write_region_roundtrip(gpu):
+    # GpuLayerCache::upload equivalent: host chunk -> device -> host
+    g, c = make_pair(0.25)
+    chunk = np.random.RandomState(0).uniform(-2, 3, size=32 ** 3).astype(np.float32)
+    g.write_region((3, -2, 1), gm.LAYER_OCCUPANCY, chunk)
+    back = g.region_layer((3, -2, 1), gm.LAYER_OCCUPANCY)
+    assert np.array_equal(back, chunk)
+    assert g.region_count() == 1
