@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s of the ray-integration hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # the CUDA path (libohmb200.so through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference CPU mapper (oracle port) on host cores
+
+Workload (N=1): BASELINE.json configs[1] — "GpuMap occupancy-only: 1 synthetic 64x2048 lidar sweep, 0.1 m voxels".
+One step = one integrateRays pass of the whole sweep (131072 rays) into an EMPTY map (the map is cleared and L2 is
+flushed between steps, outside the timed spans), so every step includes region creation and streams the full
+map working set (> L2) from HBM.
+
+  value   rays/s with the rays already resident in HBM (ohmb200_integrate_device), CUDA-event timed on the stream
+          the kernels are launched on, max over ranks.
+  e2e     the same step through the reference-facing call ohmb200_integrate with HOST (pinned) ray buffers:
+          host->device copy of the rays, all kernels, device->host read of the step's counters, and the
+          syncVoxels-equivalent download of every occupancy region chunk, all inside the timed span.
+  N>1     regions are sharded over the GPUs (ohmb200_set_partition); rank r holds 1/N of the sweep's rays, one
+          NCCL all-gather per step hands every GPU the whole sweep, and each GPU applies the visits/samples that
+          fall in the regions it owns.  Strong scaling: the sweep is fixed as N grows.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mrays/sec (64-beam lidar, 0.1 m voxels)"
+UNIT = "Mrays/s"
+RESOLUTION = 0.1
+WORKLOAD = "GpuMap occupancy-only: 1 synthetic 64x2048 lidar sweep, 0.1 m voxels"
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, or None."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.device_index = device_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.device_index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        clocks, reasons = [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    clocks.append(float(f[1]))
+                    out["sm_max_mhz"] = float(f[2])
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                     f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if clocks:
+            # "under load": the upper half of the samples (idle samples before/after the spans read low)
+            clocks.sort()
+            out["sm_mhz"] = float(np.median(clocks[len(clocks) // 2:]))
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(clocks)
+        return out
+
+
+def sweep_rays():
+    from ohm_b200.lidar import LidarBox
+    rays, _, _ = LidarBox(1).sweep()
+    return np.ascontiguousarray(rays)
+
+
+def cpu_baseline(rays, reps):
+    """The oracle port of RayMapperOccupancy, single thread (the reference mapper is single-threaded by design,
+    ohm/RayMapperOccupancy.h:25-27), on `reps` fresh-map passes of the same sweep."""
+    from oracle import pyoracle as po
+    po.lib()
+    n = rays.shape[0] // 2
+    times = []
+    stats = None
+    for _ in range(reps):
+        m = po.OracleMap(RESOLUTION)
+        t0 = time.perf_counter()
+        m.integrate_rays(rays)
+        times.append(time.perf_counter() - t0)
+        stats = m.stats()
+        m.close()
+    t = float(np.median(times))
+    return {"value": n / t / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{reps} x full config-2 sweep ({n} rays, {stats['voxel_visits']} voxel visits) into a fresh map, "
+                      f"median {t:.3f} s/sweep", "seconds_per_sweep": t}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rays = sweep_rays()
+    n = rays.shape[0] // 2
+    from oracle import pyoracle as po
+    po.lib()
+    for _ in range(min(args.warmup, 1)):
+        m = po.OracleMap(RESOLUTION)
+        m.integrate_rays(rays)
+        m.close()
+    t_total = 0.0
+    visits = 0
+    for _ in range(args.steps):
+        m = po.OracleMap(RESOLUTION)
+        t0 = time.perf_counter()
+        m.integrate_rays(rays)
+        t_total += time.perf_counter() - t0
+        visits = m.stats()["voxel_visits"]
+        m.close()
+    ms = 1e3 * t_total / args.steps
+    value = n / (ms * 1e-3) / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64 walk / f32 log-odds", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rays_per_step": n, "voxel_visits_per_step": visits,
+                   "note": "CPU RayMapperOccupancy restated in C (oracle/ohm_oracle.c), 1 thread — the reference mapper is "
+                           "single-threaded by design; each step is the full sweep into a fresh map"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"{args.steps} x full sweep of {n} rays"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    import ohm_b200
+    from ohm_b200 import gpumap as gm
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    rays = sweep_rays()
+    n = rays.shape[0] // 2
+    gpu = ohm_b200.GpuMap(RESOLUTION, device_bytes=int(args.device_gib * (1 << 30)), device=local_rank)
+    if world > 1:
+        gpu.set_partition(rank, world)
+    stream = torch.cuda.Stream()
+    gpu.set_stream(stream.cuda_stream)
+
+    # Device-resident rays: every rank holds its 1/world slice; the gathered sweep is the kernels' input.
+    per = (n + world - 1) // world
+    pad = per * world
+    rays_padded = np.full((pad * 2, 3), np.nan)  # NaN rays are rejected by the filter (padding only)
+    rays_padded[:2 * n] = rays
+    d_slice = torch.from_numpy(rays_padded[2 * per * rank:2 * per * (rank + 1)].copy()).cuda()
+    d_full = torch.empty((pad * 2, 3), dtype=torch.float64, device="cuda")
+    if world == 1:
+        d_full.copy_(d_slice)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    # Pinned host buffers for the end-to-end arm.
+    h_rays = torch.from_numpy(rays).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reset_map():
+        gpu.clear()
+        flush.fill_(1)
+        torch.cuda.synchronize()
+
+    def device_step():
+        with torch.cuda.stream(stream):
+            if world > 1:
+                dist.all_gather_into_tensor(d_full, d_slice)
+            gpu.integrate_rays_device(d_full.data_ptr(), 2 * pad)
+
+    def timed(fn, count, profile=False):
+        total_ms = 0.0
+        for _ in range(count):
+            reset_map()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if profile:
+                gpu.set_profiling(True)
+            a.record(stream)
+            fn()
+            b.record(stream)
+            b.synchronize()
+            if profile:
+                gpu.set_profiling(False)
+            barrier()
+            ms = torch.tensor([a.elapsed_time(b)], device="cuda")
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            total_ms += float(ms.item())
+        return total_ms
+
+    # ---- device-resident arm -----------------------------------------------------------------------------
+    timed(device_step, args.warmup)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = gpu.stats()["kernel_launches"]
+    gpu.kernel_times(reset=True)
+    t_ms = timed(device_step, args.steps)
+    launches = gpu.stats()["kernel_launches"] - launches0
+    # A second, separately profiled pass gives per-kernel durations (events around every launch perturb the
+    # whole-step time slightly, so it is not the pass `value` comes from).
+    timed(device_step, max(3, min(args.steps, 10)), profile=True)
+    ktimes = gpu.kernel_times(reset=True)
+    reset_map()
+    device_step()
+    torch.cuda.synchronize()
+    st = gpu.stats()
+    visits_rank, samples_rank = st["voxel_visits"], st["sample_updates"]
+    regions_rank = st["regions"]
+    tot = torch.tensor([visits_rank, samples_rank, regions_rank], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tot)
+    visits, samples, regions = (int(x) for x in tot.tolist())
+    ms_per_step = t_ms / args.steps
+    value = n / (ms_per_step * 1e-3) / 1e6
+
+    # ---- end-to-end arm (host buffers through ohmb200_integrate + map download) ---------------------------
+    occ_bytes = gpu.L.ohmb200_region_layer_bytes(gpu.h, gm.LAYER_OCCUPANCY)
+    keys = gpu.region_keys()
+    h_map = torch.empty(max(len(keys), 1) * occ_bytes, dtype=torch.uint8).pin_memory()
+    keys_c = np.ascontiguousarray(keys, dtype=np.int16)
+    stats_struct = gm.Stats()
+
+    def e2e_step():
+        # every rank uploads the whole sweep from its own pinned buffer (PCIe per GPU), integrates its regions,
+        # reads the counters back and downloads its occupancy chunks (syncVoxels).
+        gpu.integrate_rays_ptr(h_rays.data_ptr(), 2 * n)
+        gpu.L.ohmb200_get_stats(gpu.h, ctypes.byref(stats_struct))
+        k = gpu.region_keys()
+        kc = np.ascontiguousarray(k, dtype=np.int16)
+        rc = gpu.L.ohmb200_read_regions(gpu.h, gm.LAYER_OCCUPANCY, kc.ctypes.data_as(ctypes.POINTER(ctypes.c_int16)),
+                                        len(k), h_map.data_ptr(), h_map.numel())
+        assert rc == 0, ohm_b200._lib.last_error()
+
+    def timed_host(count):
+        total = 0.0
+        for _ in range(count):
+            reset_map()
+            barrier()
+            t0 = time.perf_counter()
+            e2e_step()
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            total += float(dt.item())
+            barrier()
+        return total
+
+    timed_host(max(1, min(args.warmup, 3)))
+    e2e_s = timed_host(args.steps) / args.steps
+    e2e_value = n / e2e_s / 1e6
+    clocks = sampler.stop() if rank == 0 else None
+    d2h = len(keys) * occ_bytes + ctypes.sizeof(gm.Stats) + keys_c.nbytes
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        # Algorithmic bytes (occupancy-only): 8 B per voxel visit (4 R + 4 W) + 44 B per ray.
+        alg_bytes = 8 * visits + 44 * n
+        dom = max(ktimes.items(), key=lambda kv: kv[1]["ms"]) if ktimes else ("walkRays", {"ms": 0, "launches": 1})
+        dom_name, dom_t = dom
+        dom_ms = dom_t["ms"] / max(dom_t["launches"], 1)
+        achieved = alg_bytes / (dom_ms * 1e-3) / 1e9 / max(world, 1) if dom_ms > 0 else 0.0
+        traffic = ncu_traffic()
+        cpu = cpu_baseline(rays, reps=args.cpu_reps) if args.cpu_reps > 0 else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64 walk / f32 log-odds", "data": "synthetic",
+            "config": {
+                "workload": WORKLOAD, "rays_per_step": n, "voxel_visits_per_step": visits,
+                "sample_updates_per_step": samples, "regions": regions, "resolution_m": RESOLUTION,
+                "parallelism": "single GPU" if world == 1 else f"regions sharded over {world} GPUs, 1 NCCL all-gather of the rays per step",
+                "l2": "map cleared + 512 MiB L2 flush between timed steps (outside the timed spans); the per-step map "
+                      "working set (pending + occupancy tiles of every touched region) exceeds the 126 MB L2",
+                "timing": "CUDA events on the launch stream per step, max over ranks, summed over steps",
+            },
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_rays.numel() * 8),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
+                    "what": "ohmb200_integrate(pinned host rays) + counters read + download of every occupancy chunk"},
+            "gpu_launches": int(launches),
+            "kernels_ms_per_step": {k: v["ms"] / max(v["launches"], 1) for k, v in ktimes.items()},
+            "roofline": {
+                "bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak if peak else None,
+                "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                "algorithmic_bytes_per_launch": alg_bytes // max(world, 1),
+                "kernel_ms": dom_ms, "peak_source": peak_src,
+                "model": "8 B x voxel visits + 44 B x rays (SURVEY §8d), per GPU",
+            },
+            "clocks": clocks,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    gpu.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ohmb200", choices=["ohmb200", "reference"])
+    ap.add_argument("--device-gib", type=float, default=6.0, help="device bytes for the region slabs")
+    ap.add_argument("--cpu-reps", type=int, default=8, help="oracle passes for cpu_baseline (0 = skip)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

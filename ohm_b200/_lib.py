@@ -77,6 +77,8 @@ SYMBOLS = [
     ("ohmb200_set_first_ray_time", C.c_int, [_vp, C.c_double]),
     ("ohmb200_get_stats", C.c_int, [_vp, C.POINTER(Stats)]),
     ("ohmb200_set_stream", C.c_int, [_vp, _vp]),
+    ("ohmb200_set_partition", C.c_int, [_vp, C.c_int, C.c_int]),
+    ("ohmb200_region_owner", C.c_int, [_kp, C.c_int]),
     ("ohmb200_set_profiling", C.c_int, [_vp, C.c_int]),
     ("ohmb200_kernel_times", C.c_int, [_vp, C.POINTER(KernelTime), C.c_int, C.c_int]),
     ("ohmb200_last_error", C.c_char_p, []),

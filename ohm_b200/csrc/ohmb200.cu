@@ -149,7 +149,7 @@ __global__ void prepSamples(DeviceMap dm, Geom g, MapParams mp, Batch b, int mod
       Key skey, ekey;
       // walkSegmentKeys drops rays with a null key, but the sample update still resolves its own key.
       (void)skey;
-      if (hit && voxelKey(g, end, ekey))
+      if (hit && voxelKey(g, end, ekey) && ownsRegion(dm, ekey.r))
       {
         const int slot = regionSlot(dm, packRegion(ekey.r[0], ekey.r[1], ekey.r[2]));
         if (slot >= 0)
@@ -215,7 +215,9 @@ __global__ void __launch_bounds__(128) walkRays(DeviceMap dm, Geom g, MapParams 
         if (rk != last_region)
         {
           last_region = rk;
-          slot = regionSlot(dm, rk);
+          // Regions owned by another GPU are walked (the voxel sequence is a property of the whole ray) but not
+          // updated here: their owner applies the same visits.
+          slot = ownsRegion(dm, k.r) ? regionSlot(dm, rk) : -2;
           if (slot >= 0 && __ldcg(&dm.region_stamp[slot]) != b.stamp)
           {
             if (atomicExch(&dm.region_stamp[slot], b.stamp) != b.stamp)
@@ -225,11 +227,12 @@ __global__ void __launch_bounds__(128) walkRays(DeviceMap dm, Geom g, MapParams 
           }
         }
         last_exit = exit;
-        ++visits;
         if (slot < 0)
         {
+          visits += (slot == -1) ? 1u : 0u;
           return;
         }
+        ++visits;
         const uint32_t vid = (uint32_t)slot * g.vpr + voxelIndex(g, k);
         const uint32_t p = __ldcg(&dm.pending[vid]);
         if (p & kHitFlag)
@@ -1001,6 +1004,8 @@ ohmb200_map *ohmb200_create(const ohmb200_params *params, int mode, size_t devic
   m->dm.tsdf = (float2 *)m->layer_slab[OHMB200_LAYER_TSDF];
   m->dm.region_count = &m->d_counters->region_count;
   m->dm.table_full = &m->d_counters->table_full;
+  m->dm.part_rank = 0;
+  m->dm.part_world = 1;
   if (initialiseSlabs(m) != OHMB200_OK || cudaStreamSynchronize(m->stream) != cudaSuccess)
   {
     ohmb200_destroy(m);
@@ -1443,6 +1448,24 @@ int ohmb200_set_stream(ohmb200_map *m, void *cuda_stream)
   CUDA_TRY(cudaStreamSynchronize(m->stream));
   m->stream = cuda_stream ? (cudaStream_t)cuda_stream : m->own_stream;
   return OHMB200_OK;
+}
+
+int ohmb200_set_partition(ohmb200_map *m, int rank, int world)
+{
+  if (!m || world < 1 || rank < 0 || rank >= world)
+  {
+    return setError(OHMB200_E_INVALID, "ohmb200_set_partition: need 0 <= rank < world");
+  }
+  cudaSetDevice(m->device);
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  m->dm.part_rank = rank;
+  m->dm.part_world = world;
+  return OHMB200_OK;
+}
+
+int ohmb200_region_owner(const int16_t key_xyz[3], int world)
+{
+  return (key_xyz && world >= 1) ? regionOwner(key_xyz[0], key_xyz[1], key_xyz[2], world) : -1;
 }
 
 int ohmb200_set_profiling(ohmb200_map *m, int enabled)

@@ -66,6 +66,8 @@ struct DeviceMap
   float2 *tsdf;
   unsigned long long *region_count;  // device counter of occupied slots
   int *table_full;                   // set when an insert found no free slot
+  int part_rank;                     // this GPU's index among `part_world` region owners (multi-GPU sharding)
+  int part_world;                    // 1 = the map owns every region
 };
 
 struct Key
@@ -84,6 +86,20 @@ __host__ __device__ __forceinline__ uint32_t hashRegion(unsigned long long k)
 {
   k *= 0x9E3779B97F4A7C15ull;
   return (uint32_t)(k >> 32) ^ (uint32_t)k;
+}
+
+// Region -> owning GPU: block-cyclic over 2x2x2-region blocks so the dense regions near a moving sensor spread
+// over all owners while most short hops stay local.
+__host__ __device__ __forceinline__ int regionOwner(int rx, int ry, int rz, int world)
+{
+  const int v = (rx >> 1) + 3 * (ry >> 1) + 5 * (rz >> 1);
+  const int r = v % world;
+  return r < 0 ? r + world : r;
+}
+
+__device__ __forceinline__ bool ownsRegion(const DeviceMap &m, const int r[3])
+{
+  return m.part_world <= 1 || regionOwner(r[0], r[1], r[2], m.part_world) == m.part_rank;
 }
 
 // Find or insert a region; returns its slot, or -1 when the table is full.

@@ -237,6 +237,15 @@ class GpuMap:
         self._check(self.L.ohmb200_get_stats(self.h, C.byref(s)))
         return {k: int(getattr(s, k)) for k, _ in Stats._fields_}
 
+    # -- multi-GPU sharding ----------------------------------------------------------------------------------
+    def set_partition(self, rank, world):
+        """Keep only the regions owned by `rank` of `world` GPUs (include/ohmb200.h: ohmb200_set_partition)."""
+        self._check(self.L.ohmb200_set_partition(self.h, int(rank), int(world)))
+
+    def region_owner(self, key, world):
+        key = np.ascontiguousarray(key, dtype=np.int16)
+        return self.L.ohmb200_region_owner(key.ctypes.data_as(C.POINTER(C.c_int16)), int(world))
+
     # -- measurement ---------------------------------------------------------------------------------------
     def set_stream(self, cuda_stream):
         self._check(self.L.ohmb200_set_stream(self.h, cuda_stream))
