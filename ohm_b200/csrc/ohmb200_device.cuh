@@ -384,13 +384,17 @@ __device__ inline unsigned walkLine(const Geom &g, const double start[3], const 
   walkInit(w, g, start, end, skey, ekey);
   double last_time = 0;
   unsigned count = 0;
+  // A well-formed walk takes exactly |dx|+|dy|+|dz| steps.  The bound only matters for non-finite input that slipped
+  // past a disabled filter (the reference documents a hang there, ohmgpu/GpuMap.h:209-210); it never alters a
+  // valid walk.
+  const unsigned max_steps = (unsigned)(abs(w.remaining[0]) + abs(w.remaining[1]) + abs(w.remaining[2]));
   if (flags & kExcludeStartVoxel)
   {
     last_time = walkNextTime(w);
     ++count;
     walkStep(w, g);
   }
-  while (w.limit < 7u && !walkAtEnd(w))
+  while (w.limit < 7u && !walkAtEnd(w) && count <= max_steps)
   {
     const double t = walkNextTime(w);
     visit(w.cur, last_time, t);

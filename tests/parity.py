@@ -56,8 +56,12 @@ def compare_maps(gpu, cpu, exact_layers=None, tol_layers=None):
             elif tol_layers and layer in tol_layers:
                 gf = np.nan_to_num(ga.astype(np.float64), posinf=1e30, neginf=-1e30)
                 cf = np.nan_to_num(ca.astype(np.float64), posinf=1e30, neginf=-1e30)
-                err = np.abs(gf - cf).max()
-                assert err <= tol_layers[layer], f"layer {gm.LAYER_NAMES[layer]} region {key}: max err {err}"
+                # tolerance = (rtol, atol): |gpu - cpu| <= atol + rtol * |cpu|
+                rtol, atol = tol_layers[layer]
+                err = np.abs(gf - cf) - (atol + rtol * np.abs(cf))
+                worst = int(np.argmax(err))
+                assert err.max() <= 0, (f"layer {gm.LAYER_NAMES[layer]} region {key}: gpu {gf.flat[worst]} vs cpu "
+                                        f"{cf.flat[worst]} exceeds rtol {rtol} atol {atol}")
         if gm.LAYER_OCCUPANCY in g[key]:
             summary["voxels_observed"] += int(np.isfinite(g[key][gm.LAYER_OCCUPANCY]).sum())
     return summary

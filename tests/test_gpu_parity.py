@@ -137,7 +137,9 @@ def test_all_sample_layers(gpu):
     rays = random_rays(n, 6.0, seed=21)
     ts = 100.0 + np.arange(n) * 1e-3
     integrate_both(g, c, rays, timestamps=ts, batch=3000)
-    compare_maps(g, c, tol_layers={gm.LAYER_TRAVERSAL: 2e-4})
+    # traversal is a running fp32 sum of per-visit path lengths: the GPU adds in a different order than the
+    # sequential mapper, so the bar is fp32 summation noise (relative 2e-5, a few ulp of a sum of thousands of terms)
+    compare_maps(g, c, tol_layers={gm.LAYER_TRAVERSAL: (2e-5, 1e-6)})
     assert g.first_ray_time() == c.first_ray_time() == 100.0
     check_counts(g, c)
 
@@ -213,3 +215,36 @@ def test_write_region_roundtrip(gpu):
     back = g.region_layer((3, -2, 1), gm.LAYER_OCCUPANCY)
     assert np.array_equal(back, chunk)
     assert g.region_count() == 1
+
+
+def test_region_partition_union_matches_single_map(gpu):
+    """Multi-GPU sharding on one device: two maps owning complementary region sets, fed the same rays, hold
+    between them exactly the single-map (= oracle) result — no region on both, every visit applied once."""
+    layers = [gm.LAYER_OCCUPANCY, gm.LAYER_MEAN]
+    rays = random_rays(8192, 20.0, seed=13)
+    g, c = make_pair(0.25, layers=layers)
+    c.integrate_rays(rays)
+    world = 2
+    parts = []
+    for r in range(world):
+        p = ohm_b200.GpuMap(0.25, device_bytes=1 << 30, layers=layers)
+        p.set_partition(r, world)
+        p.integrate_rays(rays)
+        p.sync_voxels()
+        parts.append(p)
+    dumps = [p.dump() for p in parts]
+    assert not (set(dumps[0]) & set(dumps[1]))
+    union = dict(dumps[0])
+    union.update(dumps[1])
+    ref = c.dump()
+    assert sorted(union) == sorted(ref)
+    for key in ref:
+        assert g.region_owner(key, world) == (0 if key in dumps[0] else 1)
+        for layer in layers:
+            a, b = np.ascontiguousarray(union[key][layer]), np.ascontiguousarray(ref[key][layer])
+            if a.dtype == np.float32:
+                a, b = a.view(np.uint32), b.view(np.uint32)
+            assert np.array_equal(a, b), (key, layer)
+    cs = c.stats()
+    assert sum(p.stats()["voxel_visits"] for p in parts) == cs["voxel_visits"]
+    assert sum(p.stats()["sample_updates"] for p in parts) == cs["sample_updates"]
