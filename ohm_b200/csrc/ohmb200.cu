@@ -15,7 +15,9 @@
 // replaces ohmgpu/GpuMap.cpp:540-1191 + ohmgpu/gpu/RegionUpdate.cl:158-494 + ohmgpu/GpuLayerCache.cpp.
 #include "ohmb200.h"
 #include "ohmb200_device.cuh"
+#include "ohmb200_regions.cuh"
 
+#include <cub/block/block_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
@@ -68,8 +70,15 @@ struct Counters
   uint32_t run_count;
   uint32_t touched_count;
   uint32_t record_overflow;
+  uint32_t segment_total;  // region-binned path
+  uint32_t item_count;
+  uint32_t work_next;
+  uint32_t segment_overflow;
+  // sticky
   int table_full;
+  int overflow_seen;
 };
+constexpr int kPerBatchCounterWords = 8;  // record_count .. segment_overflow
 
 struct Batch
 {
@@ -93,6 +102,17 @@ struct Batch
   uint32_t record_capacity;
   uint32_t *touched_list;  // [capacity] region slots walked this batch
   double *last_exit;       // [n] exit range of the last walked voxel (traversal layer only)
+  // region-binned path
+  RayRec *recs;            // [n] walk constants
+  double *ray_length;      // [n] (traversal layer only)
+  uint32_t *record_vid;    // [record_capacity] voxel id of an ordered-miss record (linked to its run afterwards)
+  uint32_t *seg_count;     // [capacity] segments per region slot
+  uint32_t *seg_offset;    // [capacity] exclusive scan of seg_count
+  uint32_t *seg_cursor;    // [capacity] fill cursors
+  Segment *segments;       // [seg_capacity] binned by region slot
+  uint32_t seg_capacity;
+  WorkItem *items;         // (region, segment range) work list
+  uint32_t item_capacity;
   Counters *counters;
 };
 
@@ -183,7 +203,10 @@ __global__ void markRuns(DeviceMap dm, Batch b)
   }
   if (i == 0 || b.keys_out[i - 1] != vid)
   {
-    dm.pending[vid] = kHitFlag | i;
+    if (dm.pending)
+    {
+      dm.pending[vid] = kHitFlag | i;
+    }
     const uint32_t r = warpAggregatedInc(&b.counters->run_count);
     b.run_list[r] = i;
   }
@@ -396,7 +419,10 @@ __global__ void __launch_bounds__(128) applySamples(DeviceMap dm, Geom g, MapPar
     {
       atomicAdd(&dm.traversal[vid], traversal_add);
     }
-    dm.pending[vid] = 0;
+    if (dm.pending)
+    {
+      dm.pending[vid] = 0;
+    }
   }
   __syncwarp();
   const unsigned s = __reduce_add_sync(0xffffffffu, samples);
@@ -433,6 +459,8 @@ __global__ void __launch_bounds__(256) resolveMisses(DeviceMap dm, Geom g, MapPa
   }
 }
 
+#include "ohmb200_region_kernels.cuh"
+
 __global__ void fillFloat(float *dst, size_t n, float value)
 {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -467,16 +495,27 @@ enum KernelId
   kKResolve,
   kKGather,
   kKFill,
+  kKPrepRays,
+  kKPlan,
+  kKEmit,
+  kKWalkRegions,
+  kKLink,
   kKernelCount
 };
-static const char *kKernelNames[kKernelCount] = { "prepSamples", "radixSort",     "markRuns",      "walkRays",
-                                                  "applySamples", "resolveMisses", "gatherRegions", "fillFloat" };
+static const char *kKernelNames[kKernelCount] = { "prepSamples",  "radixSort",     "markRuns",      "walkRays",
+                                                  "applySamples", "resolveMisses", "gatherRegions", "fillFloat",
+                                                  "prepRays",     "planRegions",   "emitSegments",  "walkRegions",
+                                                  "linkRecords" };
+static_assert(kKernelCount <= OHMB200_KERNEL_SLOTS, "raise OHMB200_KERNEL_SLOTS");
 
 struct ohmb200_map
 {
   int device = 0;
   int mode = 0;
   int sm_count = 148;
+  int algo = 1;           // 1 = region-binned walk (shared-memory tiles), 0 = one thread per ray (global counters)
+  size_t tile_bytes = 0;  // dynamic shared memory of walkRegions
+  int walk_ctas_per_sm = 1;
   ohmb200_params params{};
   Geom geom{};
   MapParams mp{};
@@ -626,7 +665,10 @@ int initialiseSlabs(ohmb200_map *m)
   const size_t voxels = (size_t)m->dm.capacity * m->geom.vpr;
   CUDA_TRY(cudaMemsetAsync(m->dm.keys, 0xFF, sizeof(unsigned long long) * m->dm.capacity, m->stream));
   CUDA_TRY(cudaMemsetAsync(m->dm.region_stamp, 0, sizeof(uint32_t) * m->dm.capacity, m->stream));
-  CUDA_TRY(cudaMemsetAsync(m->dm.pending, 0, sizeof(uint32_t) * voxels, m->stream));
+  if (m->dm.pending)
+  {
+    CUDA_TRY(cudaMemsetAsync(m->dm.pending, 0, sizeof(uint32_t) * voxels, m->stream));
+  }
   for (int l = 0; l < OHMB200_LAYER_COUNT; ++l)
   {
     if (!m->layer_slab[l])
@@ -695,6 +737,25 @@ int ensureScratch(ohmb200_map *m, size_t n)
   {
     rc |= deviceAlloc(b.last_exit, cap);
   }
+  if (m->algo == 1)
+  {
+    cudaFree(b.recs);
+    cudaFree(b.ray_length);
+    cudaFree(b.record_vid);
+    cudaFree(b.segments);
+    cudaFree(b.items);
+    b.ray_length = nullptr;
+    rc |= deviceAlloc(b.recs, cap);
+    if (m->dm.traversal)
+    {
+      rc |= deviceAlloc(b.ray_length, cap);
+    }
+    rc |= deviceAlloc(b.record_vid, b.record_capacity);
+    b.seg_capacity = (uint32_t)std::min<size_t>(cap * 96, 0xFFFFFFF0u);
+    rc |= deviceAlloc(b.segments, b.seg_capacity);
+    b.item_capacity = m->dm.capacity + b.seg_capacity / kMaxSegmentsPerItem + 16;
+    rc |= deviceAlloc(b.items, b.item_capacity);
+  }
   if (rc)
   {
     return OHMB200_E_CUDA;
@@ -733,8 +794,61 @@ int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_i
   const unsigned blocks = (unsigned)((n + threads - 1) / threads);
   const bool has_samples = m->mode != OHMB200_MODE_TSDF;
 
-  // Reset the per-batch counters (record_count .. record_overflow are contiguous).
-  CUDA_TRY(cudaMemsetAsync(&m->d_counters->record_count, 0, sizeof(uint32_t) * 4, s));
+  // Reset the per-batch counters (record_count .. segment_overflow are contiguous).
+  CUDA_TRY(cudaMemsetAsync(&m->d_counters->record_count, 0, sizeof(uint32_t) * kPerBatchCounterWords, s));
+  if (m->algo == 1)
+  {
+    CUDA_TRY(cudaMemsetAsync(b.seg_count, 0, sizeof(uint32_t) * m->dm.capacity, s));
+    CUDA_TRY(cudaMemsetAsync(b.seg_cursor, 0, sizeof(uint32_t) * m->dm.capacity, s));
+    CUDA_TRY(cudaMemsetAsync(b.run_head, 0xFF, sizeof(int32_t) * n, s));
+    CUDA_TRY(cudaMemsetAsync(b.interval_count, 0, sizeof(uint32_t) * n, s));
+    CUDA_TRY(cudaMemsetAsync(b.tail_overflow, 0, sizeof(uint32_t) * n, s));
+    {
+      KernelScope scope(m, kKPrepRays);
+      prepRays<<<blocks, threads, 0, s>>>(m->dm, m->geom, m->mp, b, m->mode);
+    }
+    if (has_samples)
+    {
+      {
+        KernelScope scope(m, kKSort);
+        size_t temp = m->cub_temp_bytes;
+        cub::DeviceRadixSort::SortPairs(m->cub_temp, temp, b.keys_in, b.keys_out, b.vals_in, b.vals_out, (int)n, 0,
+                                        m->sort_bits, s);
+      }
+      {
+        KernelScope scope(m, kKMark);
+        markRuns<<<blocks, threads, 0, s>>>(m->dm, b);
+      }
+    }
+    {
+      KernelScope scope(m, kKPlan);
+      planRegions<<<1, 1024, 0, s>>>(m->dm, b);
+    }
+    {
+      KernelScope scope(m, kKEmit);
+      emitSegments<<<blocks, threads, 0, s>>>(m->dm, m->geom, b);
+    }
+    {
+      KernelScope scope(m, kKWalkRegions);
+      walkRegions<<<m->sm_count * m->walk_ctas_per_sm, 256, m->tile_bytes, s>>>(m->dm, m->geom, m->mp, b,
+                                                                             has_samples ? 1 : 0);
+    }
+    if (has_samples)
+    {
+      {
+        KernelScope scope(m, kKLink);
+        linkRecords<<<m->sm_count * 4, 256, 0, s>>>(b);
+      }
+      {
+        KernelScope scope(m, kKSamples);
+        applySamples<<<blocks, threads, 0, s>>>(m->dm, m->geom, m->mp, b);
+      }
+    }
+    CUDA_TRY(cudaGetLastError());
+    m->rays_in += n;
+    ++m->batches;
+    return OHMB200_OK;
+  }
   if (has_samples)
   {
     CUDA_TRY(cudaMemsetAsync(b.run_head, 0xFF, sizeof(int32_t) * n, s));
@@ -942,7 +1056,27 @@ ohmb200_map *ohmb200_create(const ohmb200_params *params, int mode, size_t devic
   }
   refreshParams(m);
 
-  size_t bytes_per_region = sizeof(uint32_t) * m->geom.vpr;  // pending
+  // Walk algorithm: the region-binned path needs the u16 counter tile of a region to fit in shared memory.
+  m->tile_bytes = sizeof(uint32_t) * ((m->geom.vpr + 1u) / 2u);
+  m->algo = 1;
+  if (const char *env = getenv("OHMB200_ALGO"))
+  {
+    m->algo = atoi(env) ? 1 : 0;
+  }
+  if (m->tile_bytes > 200u * 1024u || mode != OHMB200_MODE_OCCUPANCY)
+  {
+    m->algo = 0;
+  }
+  if (m->algo == 1)
+  {
+    if (cudaFuncSetAttribute(walkRegions, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->tile_bytes) != cudaSuccess)
+    {
+      cudaGetLastError();
+      m->algo = 0;
+    }
+    m->walk_ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220u * 1024u) / (m->tile_bytes + 1024u)));
+  }
+  size_t bytes_per_region = (m->algo == 0) ? sizeof(uint32_t) * m->geom.vpr : 3 * sizeof(uint32_t);  // pending / counters
   for (int l = 0; l < OHMB200_LAYER_COUNT; ++l)
   {
     if (m->params.layers & (1u << l))
@@ -975,7 +1109,16 @@ ohmb200_map *ohmb200_create(const ohmb200_params *params, int mode, size_t devic
   const size_t voxels = capacity * m->geom.vpr;
   ok = ok && cudaMalloc(&m->dm.keys, sizeof(unsigned long long) * capacity) == cudaSuccess;
   ok = ok && cudaMalloc(&m->dm.region_stamp, sizeof(uint32_t) * capacity) == cudaSuccess;
-  ok = ok && cudaMalloc(&m->dm.pending, sizeof(uint32_t) * voxels) == cudaSuccess;
+  if (m->algo == 0)
+  {
+    ok = ok && cudaMalloc(&m->dm.pending, sizeof(uint32_t) * voxels) == cudaSuccess;
+  }
+  else
+  {
+    ok = ok && cudaMalloc(&m->batch.seg_count, sizeof(uint32_t) * capacity) == cudaSuccess;
+    ok = ok && cudaMalloc(&m->batch.seg_offset, sizeof(uint32_t) * capacity) == cudaSuccess;
+    ok = ok && cudaMalloc(&m->batch.seg_cursor, sizeof(uint32_t) * capacity) == cudaSuccess;
+  }
   ok = ok && cudaMalloc(&m->batch.touched_list, sizeof(uint32_t) * capacity) == cudaSuccess;
   ok = ok && cudaMalloc(&m->d_counters, sizeof(Counters)) == cudaSuccess;
   ok = ok && cudaMallocHost(&m->h_counters, sizeof(Counters)) == cudaSuccess;
@@ -1027,7 +1170,9 @@ void ohmb200_destroy(ohmb200_map *m)
                       b.keys_in,        b.keys_out,         b.vals_in,          b.vals_out,       b.run_list,
                       b.run_head,       b.interval_count,   b.tail_overflow,    b.record_ray,     b.record_next,
                       b.last_exit,      m->cub_temp,        m->d_rays[0],       m->d_rays[1],     m->d_intensities[0],
-                      m->d_intensities[1], m->d_timestamps[0], m->d_timestamps[1], m->d_gather,    m->d_gather_slots };
+                      m->d_intensities[1], m->d_timestamps[0], m->d_timestamps[1], m->d_gather,    m->d_gather_slots,
+                      b.recs,           b.ray_length,       b.record_vid,       b.seg_count,      b.seg_offset,
+                      b.seg_cursor,     b.segments,         b.items };
   for (void *p : to_free)
   {
     if (p)
@@ -1218,6 +1363,10 @@ int ohmb200_sync(ohmb200_map *m)
   if (m->h_counters->table_full)
   {
     return setError(OHMB200_E_CACHE_FULL, "region table full (%u slots): raise device_bytes", m->dm.capacity);
+  }
+  if (m->h_counters->overflow_seen)
+  {
+    return setError(OHMB200_E_OVERFLOW, "a per-batch segment/record list overflowed: results are incomplete; use smaller batches");
   }
   return OHMB200_OK;
 }

@@ -15,6 +15,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Key maths and the walk are also compiled for the host by tests/cpp/segments_host_test.cu (no GPU needed there).
+#define OHMB200_HD __host__ __device__
+
 namespace ohmb200
 {
 constexpr uint64_t kEmptyKey = ~0ull;
@@ -76,7 +79,7 @@ struct Key
   int l[3];  // local voxel
 };
 
-__device__ __forceinline__ unsigned long long packRegion(int x, int y, int z)
+OHMB200_HD __forceinline__ unsigned long long packRegion(int x, int y, int z)
 {
   return (unsigned long long)(uint16_t)x | ((unsigned long long)(uint16_t)y << 16) |
          ((unsigned long long)(uint16_t)z << 32);
@@ -153,13 +156,13 @@ __device__ inline int regionFind(const DeviceMap &m, unsigned long long key)
 }
 
 // ohm/MapCoord.h:85-93
-__device__ __forceinline__ int pointToRegionCoord(double coord, double resolution)
+OHMB200_HD __forceinline__ int pointToRegionCoord(double coord, double resolution)
 {
   return (int)floor(coord / resolution + 0.5);
 }
 
 // ohm/MapCoord.h:41-80
-__device__ __forceinline__ int pointToRegionVoxel(double coord, double voxel_resolution, double region_resolution)
+OHMB200_HD __forceinline__ int pointToRegionVoxel(double coord, double voxel_resolution, double region_resolution)
 {
   const double epsilon = (double)1e-6f;
   if (-epsilon <= coord && coord < 0)
@@ -174,7 +177,7 @@ __device__ __forceinline__ int pointToRegionVoxel(double coord, double voxel_res
 }
 
 // ohm/OccupancyMap.cpp:859-886 -> ohm/MapRegion.cpp:32-69.  false => null key.
-__device__ inline bool voxelKey(const Geom &g, const double p[3], Key &key)
+OHMB200_HD inline bool voxelKey(const Geom &g, const double p[3], Key &key)
 {
   bool ok = true;
 #pragma unroll
@@ -193,7 +196,7 @@ __device__ inline bool voxelKey(const Geom &g, const double p[3], Key &key)
 }
 
 // ohm/OccupancyMap.h:757-778
-__device__ __forceinline__ double voxelCentreAxis(const Geom &g, int region, int local, int a)
+OHMB200_HD __forceinline__ double voxelCentreAxis(const Geom &g, int region, int local, int a)
 {
   double c = (double)(float)region;
   c *= g.region_size[a];
@@ -204,14 +207,14 @@ __device__ __forceinline__ double voxelCentreAxis(const Geom &g, int region, int
   return c;
 }
 
-__device__ __forceinline__ uint32_t voxelIndex(const Geom &g, const Key &k)
+OHMB200_HD __forceinline__ uint32_t voxelIndex(const Geom &g, const Key &k)
 {
   // ohm/MapChunk.h:47-50
   return (uint32_t)k.l[0] + (uint32_t)k.l[1] * g.dim[0] + (uint32_t)k.l[2] * g.dim[0] * g.dim[1];
 }
 
 // ohm/RayFilter.cpp:15-55.  Returns false for a rejected ray; may move `end` and set kRffClippedEnd.
-__device__ inline bool applyRayFilter(const MapParams &p, double start[3], double end[3], unsigned &filter_flags)
+OHMB200_HD inline bool applyRayFilter(const MapParams &p, double start[3], double end[3], unsigned &filter_flags)
 {
   if (p.filter_kind == 0)
   {
@@ -271,7 +274,7 @@ struct Walk
   unsigned limit;
 };
 
-__device__ __forceinline__ int selectNextAxis(const double t[3])
+OHMB200_HD __forceinline__ int selectNextAxis(const double t[3])
 {
   int axis = 0;
   axis = (t[axis] < t[1]) ? axis : 1;
@@ -280,7 +283,7 @@ __device__ __forceinline__ int selectNextAxis(const double t[3])
 }
 
 // LineWalkCompute.h:188-280 + the set-up half of walkLineVoxels (:351-379).
-__device__ inline void walkInit(Walk &w, const Geom &g, const double start[3], const double end[3], const Key &skey,
+OHMB200_HD inline void walkInit(Walk &w, const Geom &g, const double start[3], const double end[3], const Key &skey,
                                 const Key &ekey)
 {
   double dir[3], inv[3];
@@ -331,7 +334,7 @@ __device__ inline void walkInit(Walk &w, const Geom &g, const double start[3], c
 }
 
 // LineWalkCompute.h:291-307 (+ key stepping OccupancyMap.h:827-846)
-__device__ __forceinline__ void walkStep(Walk &w, const Geom &g)
+OHMB200_HD __forceinline__ void walkStep(Walk &w, const Geom &g)
 {
   // Select by predication rather than dynamic indexing to keep the state in registers.
   const int a = w.axis;
@@ -364,20 +367,20 @@ __device__ __forceinline__ void walkStep(Walk &w, const Geom &g)
   w.axis = selectNextAxis(w.time_next);
 }
 
-__device__ __forceinline__ bool walkAtEnd(const Walk &w)
+OHMB200_HD __forceinline__ bool walkAtEnd(const Walk &w)
 {
   return w.cur.r[0] == w.end.r[0] && w.cur.r[1] == w.end.r[1] && w.cur.r[2] == w.end.r[2] &&
          w.cur.l[0] == w.end.l[0] && w.cur.l[1] == w.end.l[1] && w.cur.l[2] == w.end.l[2];
 }
 
-__device__ __forceinline__ double walkNextTime(const Walk &w)
+OHMB200_HD __forceinline__ double walkNextTime(const Walk &w)
 {
   return (w.axis == 0) ? w.time_next[0] : ((w.axis == 1) ? w.time_next[1] : w.time_next[2]);
 }
 
 // Drives `visit(key, enter, exit)` exactly as walkLineVoxels (LineWalkCompute.h:345-413) would.
 template <typename Visit>
-__device__ inline unsigned walkLine(const Geom &g, const double start[3], const double end[3], const Key &skey,
+OHMB200_HD inline unsigned walkLine(const Geom &g, const double start[3], const double end[3], const Key &skey,
                                     const Key &ekey, unsigned flags, Visit &&visit)
 {
   Walk w;
