@@ -730,7 +730,7 @@ int ensureScratch(ohmb200_map *m, size_t n)
   rc |= deviceAlloc(b.run_head, cap);
   rc |= deviceAlloc(b.interval_count, cap);
   rc |= deviceAlloc(b.tail_overflow, cap);
-  b.record_capacity = (uint32_t)std::min<size_t>(std::max<size_t>(cap * 32, 1u << 20), 1u << 28);
+  b.record_capacity = (uint32_t)std::min<size_t>(std::max<size_t>(cap * 24, 1u << 20), 1u << 28);
   rc |= deviceAlloc(b.record_ray, b.record_capacity);
   rc |= deviceAlloc(b.record_next, b.record_capacity);
   if (m->dm.traversal)
@@ -800,6 +800,11 @@ int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_i
   {
     CUDA_TRY(cudaMemsetAsync(b.seg_count, 0, sizeof(uint32_t) * m->dm.capacity, s));
     CUDA_TRY(cudaMemsetAsync(b.seg_cursor, 0, sizeof(uint32_t) * m->dm.capacity, s));
+    if (has_samples)
+    {
+      // record slots are reserved per warp in chunks; unwritten slots must read as "no record"
+      CUDA_TRY(cudaMemsetAsync(b.record_vid, 0xFF, sizeof(uint32_t) * b.record_capacity, s));
+    }
     CUDA_TRY(cudaMemsetAsync(b.run_head, 0xFF, sizeof(int32_t) * n, s));
     CUDA_TRY(cudaMemsetAsync(b.interval_count, 0, sizeof(uint32_t) * n, s));
     CUDA_TRY(cudaMemsetAsync(b.tail_overflow, 0, sizeof(uint32_t) * n, s));
@@ -830,8 +835,8 @@ int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_i
     }
     {
       KernelScope scope(m, kKWalkRegions);
-      walkRegions<<<m->sm_count * m->walk_ctas_per_sm, 256, m->tile_bytes, s>>>(m->dm, m->geom, m->mp, b,
-                                                                             has_samples ? 1 : 0);
+      walkRegions<<<m->sm_count * m->walk_ctas_per_sm, kWalkThreads, m->tile_bytes, s>>>(m->dm, m->geom, m->mp, b,
+                                                                                      has_samples ? 1 : 0);
     }
     if (has_samples)
     {
@@ -1074,7 +1079,7 @@ ohmb200_map *ohmb200_create(const ohmb200_params *params, int mode, size_t devic
       cudaGetLastError();
       m->algo = 0;
     }
-    m->walk_ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220u * 1024u) / (m->tile_bytes + 1024u)));
+    m->walk_ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (220u * 1024u) / (m->tile_bytes + 1024u)));
   }
   size_t bytes_per_region = (m->algo == 0) ? sizeof(uint32_t) * m->geom.vpr : 3 * sizeof(uint32_t);  // pending / counters
   for (int l = 0; l < OHMB200_LAYER_COUNT; ++l)

@@ -1,8 +1,9 @@
 // ohmb200_region_kernels.cuh — kernels of the region-binned pipeline (included by ohmb200.cu after Batch/Counters).
 //
 //   prepRays      1 thread/ray   filter, keys, walk constants (RayRec), sample pair; pass A of the exact segment
-//                                enumeration: region find-or-insert + per-region segment histogram
-//   planRegions   1 CTA          exclusive scan of the histogram -> segment offsets; (region, <=8192 segments) work items
+//                                enumeration: region find-or-insert + per-region segment histogram + touched list
+//   planRegions   1 CTA          scan of the touched regions' histogram -> segment offsets; (region, <=2048 segments)
+//                                work items, largest regions first
 //   emitSegments  1 thread/ray   pass B: re-enumerate, scatter 16-byte segments into their region's range
 //   walkRegions   persistent CTAs, one work item at a time: zero a u16 counter tile in shared memory, flag this
 //                                region's sample voxels, resume every segment's walk against the tile (1 shared-memory
@@ -13,7 +14,7 @@
 
 namespace ohmb200
 {
-// Adds 1 to counters[slot] for every calling lane; lanes of the converged group that share a slot issue one atomic.
+// Lanes of the converged group that share a slot issue one atomic for all of them.
 // Returns this lane's position in its slot (previous value + rank).
 __device__ __forceinline__ uint32_t slotAggregatedInc(uint32_t *counters, uint32_t slot)
 {
@@ -46,6 +47,15 @@ __device__ __forceinline__ uint32_t lowerBound(const uint32_t *keys, uint32_t n,
     }
   }
   return lo;
+}
+
+__device__ __forceinline__ void loadRec(RayRec &rec, const RayRec *src)
+{
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+  {
+    reinterpret_cast<uint4 *>(&rec)[k] = reinterpret_cast<const uint4 *>(src)[k];
+  }
 }
 }  // namespace ohmb200
 
@@ -88,10 +98,7 @@ __global__ void __launch_bounds__(128) prepRays(DeviceMap dm, Geom g, MapParams 
       }
       if (mode == OHMB200_MODE_TSDF || !(b.ray_flags & OHMB200_RF_EXCLUDE_RAY))
       {
-        if (!makeRayRec(rec, g, start, end, walk_flags) && (rec.flags & kRecValid) == 0)
-        {
-          rec.flags = 0;
-        }
+        makeRayRec(rec, g, start, end, walk_flags);  // leaves rec.flags == 0 when the ray is not walked
       }
       if (b.ray_length)
       {
@@ -102,10 +109,11 @@ __global__ void __launch_bounds__(128) prepRays(DeviceMap dm, Geom g, MapParams 
     }
     b.keys_in[i] = vid;
     b.vals_in[i] = i;
-    reinterpret_cast<uint4 *>(b.recs + i)[0] = reinterpret_cast<const uint4 *>(&rec)[0];
-    reinterpret_cast<uint4 *>(b.recs + i)[1] = reinterpret_cast<const uint4 *>(&rec)[1];
-    reinterpret_cast<uint4 *>(b.recs + i)[2] = reinterpret_cast<const uint4 *>(&rec)[2];
-    reinterpret_cast<uint4 *>(b.recs + i)[3] = reinterpret_cast<const uint4 *>(&rec)[3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+      reinterpret_cast<uint4 *>(b.recs + i)[k] = reinterpret_cast<const uint4 *>(&rec)[k];
+    }
     if (b.last_exit)
     {
       b.last_exit[i] = 0;
@@ -123,7 +131,16 @@ __global__ void __launch_bounds__(128) prepRays(DeviceMap dm, Geom g, MapParams 
         visits += (unsigned)n;
         if (slot >= 0)
         {
-          slotAggregatedInc(b.seg_count, (uint32_t)slot);
+          // one fire-and-forget reduction per group of lanes that entered the same region
+          const unsigned peers = __match_any_sync(__activemask(), slot);
+          if ((int)(threadIdx.x & 31) == __ffs(peers) - 1)
+          {
+            if (__ldcg(&dm.region_stamp[slot]) != b.stamp && atomicExch(&dm.region_stamp[slot], b.stamp) != b.stamp)
+            {
+              b.touched_list[atomicAdd(&b.counters->touched_count, 1u)] = (uint32_t)slot;
+            }
+            atomicAdd(&b.seg_count[slot], (uint32_t)__popc(peers));
+          }
         }
       });
     }
@@ -144,54 +161,66 @@ __global__ void __launch_bounds__(128) prepRays(DeviceMap dm, Geom g, MapParams 
   }
 }
 
-// Single CTA: segment offsets per region slot and the work-item list.
+// Single CTA over the touched regions only: segment offsets and the work-item list (largest regions first).
 __global__ void __launch_bounds__(1024) planRegions(DeviceMap dm, Batch b)
 {
   typedef cub::BlockScan<uint32_t, 1024> Scan;
   __shared__ typename Scan::TempStorage scan_storage;
-  const uint32_t per = (dm.capacity + 1023u) / 1024u;
-  const uint32_t first = threadIdx.x * per;
-  const uint32_t last = min(first + per, dm.capacity);
-  uint32_t sum = 0;
-  for (uint32_t s = first; s < last; ++s)
+  __shared__ uint32_t carry;
+  const uint32_t touched = b.counters->touched_count;
+  if (threadIdx.x == 0)
   {
-    sum += b.seg_count[s];
+    carry = 0;
   }
-  uint32_t base = 0, total = 0;
-  Scan(scan_storage).ExclusiveSum(sum, base, total);
-  for (uint32_t s = first; s < last; ++s)
+  __syncthreads();
+  for (uint32_t base = 0; base < touched; base += 1024)
   {
-    b.seg_offset[s] = base;
-    base += b.seg_count[s];
+    const uint32_t t = base + threadIdx.x;
+    const uint32_t slot = (t < touched) ? b.touched_list[t] : 0;
+    const uint32_t count = (t < touched) ? b.seg_count[slot] : 0;
+    uint32_t offset = 0, total = 0;
+    Scan(scan_storage).ExclusiveSum(count, offset, total);
+    if (t < touched)
+    {
+      b.seg_offset[slot] = carry + offset;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+      carry += total;
+    }
+    __syncthreads();
   }
   if (threadIdx.x == 0)
   {
-    b.counters->segment_total = total;
-    if (total > b.seg_capacity)
+    b.counters->segment_total = carry;
+    if (carry > b.seg_capacity)
     {
       b.counters->segment_overflow = 1;
       b.counters->overflow_seen = 1;
     }
   }
+  // Work items in decreasing size classes so that the long items start first and the tail is made of small ones.
   __syncthreads();
-  // Work items: large regions first (they bound the tail), split into <= kMaxSegmentsPerItem pieces.
-  for (int pass = 0; pass < 2; ++pass)
+  for (int pass = 0; pass < 5; ++pass)
   {
-    for (uint32_t s = first; s < last; ++s)
+    const uint32_t hi = (pass == 0) ? 0xFFFFFFFFu : (kMaxSegmentsPerItem >> (pass == 1 ? 0 : (pass == 2 ? 1 : (pass == 3 ? 3 : 5))));
+    const uint32_t lo = (pass == 4) ? 1u : (kMaxSegmentsPerItem >> (pass == 0 ? 0 : (pass == 1 ? 1 : (pass == 2 ? 3 : 5))));
+    for (uint32_t t = threadIdx.x; t < touched; t += blockDim.x)
     {
-      const uint32_t count = b.seg_count[s];
-      const bool large = count >= kMaxSegmentsPerItem / 4;
-      if (count == 0 || large != (pass == 0))
+      const uint32_t slot = b.touched_list[t];
+      const uint32_t count = b.seg_count[slot];
+      if (count < lo || count >= hi)
       {
         continue;
       }
       const uint32_t pieces = (count + kMaxSegmentsPerItem - 1) / kMaxSegmentsPerItem;
       const uint32_t at = atomicAdd(&b.counters->item_count, pieces);
-      const uint32_t begin = b.seg_offset[s];
+      const uint32_t begin = b.seg_offset[slot];
       for (uint32_t p = 0; p < pieces && at + p < b.item_capacity; ++p)
       {
         WorkItem w;
-        w.slot = s;
+        w.slot = slot;
         w.begin = begin + p * kMaxSegmentsPerItem;
         w.end = min(begin + count, w.begin + kMaxSegmentsPerItem);
         w.shared = pieces > 1;
@@ -211,10 +240,7 @@ __global__ void __launch_bounds__(128) emitSegments(DeviceMap dm, Geom g, Batch 
     return;
   }
   RayRec rec;
-  reinterpret_cast<uint4 *>(&rec)[0] = reinterpret_cast<const uint4 *>(b.recs + i)[0];
-  reinterpret_cast<uint4 *>(&rec)[1] = reinterpret_cast<const uint4 *>(b.recs + i)[1];
-  reinterpret_cast<uint4 *>(&rec)[2] = reinterpret_cast<const uint4 *>(b.recs + i)[2];
-  reinterpret_cast<uint4 *>(&rec)[3] = reinterpret_cast<const uint4 *>(b.recs + i)[3];
+  loadRec(rec, b.recs + i);
   if (!(rec.flags & kRecValid))
   {
     return;
@@ -242,15 +268,23 @@ __global__ void __launch_bounds__(128) emitSegments(DeviceMap dm, Geom g, Batch 
   });
 }
 
+constexpr int kWalkThreads = 512;
+
 // Persistent CTAs: one (region, segment range) work item at a time against a shared-memory counter tile.
-__global__ void __launch_bounds__(256) walkRegions(DeviceMap dm, Geom g, MapParams mp, Batch b, int has_samples)
+__global__ void __launch_bounds__(kWalkThreads, 2) walkRegions(DeviceMap dm, Geom g, MapParams mp, Batch b, int has_samples)
 {
   extern __shared__ uint32_t tile[];
   __shared__ WorkItem item;
   __shared__ uint32_t sample_range[2];
+  // per-warp reservation of ordered-miss record slots: (base << 32) | used
+  __shared__ unsigned long long record_chunk[kWalkThreads / 32];
   const uint32_t words = (g.vpr + 1u) >> 1;
   const uint32_t tid = threadIdx.x;
-  const int dx = g.dim[0], dxy = g.dim[0] * g.dim[1];
+  const uint32_t warp = tid >> 5;
+  if ((tid & 31u) == 0)
+  {
+    record_chunk[warp] = (unsigned long long)kRecordChunk;  // "full": the first record reserves a chunk
+  }
 
   for (;;)
   {
@@ -274,9 +308,20 @@ __global__ void __launch_bounds__(256) walkRegions(DeviceMap dm, Geom g, MapPara
     }
     const uint32_t slot = item.slot;
     const uint32_t vbase = slot * g.vpr;
-    for (uint32_t w = tid; w < words; w += blockDim.x)
+    if ((words & 3u) == 0)
     {
-      tile[w] = 0;
+      uint4 *tile4 = reinterpret_cast<uint4 *>(tile);
+      for (uint32_t w = tid; w < (words >> 2); w += blockDim.x)
+      {
+        tile4[w] = make_uint4(0, 0, 0, 0);
+      }
+    }
+    else
+    {
+      for (uint32_t w = tid; w < words; w += blockDim.x)
+      {
+        tile[w] = 0;
+      }
     }
     if (has_samples && tid < 2)
     {
@@ -308,17 +353,35 @@ __global__ void __launch_bounds__(256) walkRegions(DeviceMap dm, Geom g, MapPara
       const int local0[3] = { (int)((tail.y >> 16) & 0xffu), (int)(tail.y >> 24), (int)(tail.z & 0xffu) };
       const double init[3] = { rp->initial[0], rp->initial[1], rp->initial[2] };
       const double delta[3] = { rp->delta[0], rp->delta[1], rp->delta[2] };
-      auto visit = [&](const int l[3], double t_enter, double t_exit, bool last_of_ray) {
-        const uint32_t idx = (uint32_t)(l[0] + l[1] * dx + l[2] * dxy);
+      auto count_visit = [&](uint32_t idx) {
         const uint32_t shift = (idx & 1u) * 16u;
         const uint32_t old = atomicAdd(&tile[idx >> 1], 1u << shift);
         if ((old >> shift) & kTileFlag)
         {
-          const uint32_t r = warpAggregatedInc(&b.counters->record_count);
-          if (r < b.record_capacity)
+          // Ordered-miss record.  Slots come from a per-warp chunk: one global atomic per kRecordChunk records.
+          const unsigned group = __activemask();
+          const uint32_t n = (uint32_t)__popc(group);
+          const uint32_t rank = (uint32_t)__popc(group & ((1u << (tid & 31u)) - 1u));
+          uint32_t at = 0;
+          if (rank == 0)
           {
-            b.record_vid[r] = vbase + idx;
-            b.record_ray[r] = ray;
+            const unsigned long long state = atomicAdd(&record_chunk[warp], (unsigned long long)n);
+            const uint32_t used = (uint32_t)state;
+            if (used + n <= kRecordChunk)
+            {
+              at = (uint32_t)(state >> 32) + used;
+            }
+            else
+            {
+              at = atomicAdd(&b.counters->record_count, kRecordChunk);
+              atomicExch(&record_chunk[warp], ((unsigned long long)at << 32) | n);
+            }
+          }
+          at = __shfl_sync(group, at, __ffs(group) - 1) + rank;
+          if (at < b.record_capacity)
+          {
+            b.record_vid[at] = vbase + idx;
+            b.record_ray[at] = ray;
           }
           else
           {
@@ -326,22 +389,24 @@ __global__ void __launch_bounds__(256) walkRegions(DeviceMap dm, Geom g, MapPara
             b.counters->overflow_seen = 1;
           }
         }
-        if (dm.traversal)
-        {
-          atomicAdd(&dm.traversal[vbase + idx], (float)(t_exit - t_enter));
-          if (last_of_ray)
-          {
-            b.last_exit[ray] = t_exit;
-          }
-        }
       };
       if (dm.traversal)
       {
-        resumeSegment<true>(init, delta, local0, total, flags, st, visits, b.ray_length[ray], g, visit);
+        const int dx = g.dim[0], dxy = g.dim[0] * g.dim[1];
+        resumeSegment<true>(init, delta, local0, total, flags, st, visits, b.ray_length[ray], g,
+                            [&](const int l[3], double t_enter, double t_exit, bool last_of_ray) {
+                              const uint32_t idx = (uint32_t)(l[0] + l[1] * dx + l[2] * dxy);
+                              count_visit(idx);
+                              atomicAdd(&dm.traversal[vbase + idx], (float)(t_exit - t_enter));
+                              if (last_of_ray)
+                              {
+                                b.last_exit[ray] = t_exit;
+                              }
+                            });
       }
       else
       {
-        resumeSegment<false>(init, delta, local0, total, flags, st, visits, 0.0, g, visit);
+        resumeSegmentFast(init, delta, local0, total, flags, st, visits, g, count_visit);
       }
     }
     __syncthreads();
@@ -416,13 +481,19 @@ __global__ void __launch_bounds__(256) walkRegions(DeviceMap dm, Geom g, MapPara
   }
 }
 
-// Attach every ordered-miss record to the run (sorted sample pairs) of its voxel.
+// Attach every ordered-miss record to the run (sorted sample pairs) of its voxel.  Slots reserved by a warp but
+// never written keep the kInvalidVoxel fill and are skipped.
 __global__ void linkRecords(Batch b)
 {
   const uint32_t count = min(b.counters->record_count, b.record_capacity);
   for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < count; r += gridDim.x * blockDim.x)
   {
-    const uint32_t head = lowerBound(b.keys_out, b.n, b.record_vid[r]);
+    const uint32_t vid = b.record_vid[r];
+    if (vid == kInvalidVoxel)
+    {
+      continue;
+    }
+    const uint32_t head = lowerBound(b.keys_out, b.n, vid);
     b.record_next[r] = atomicExch(&b.run_head[head], (int32_t)r);
   }
 }

@@ -16,7 +16,8 @@
 namespace ohmb200
 {
 constexpr unsigned kRecValid = 1u << 3, kRecExcludeStart = 1u << 4, kRecExcludeEnd = 1u << 5;
-constexpr uint32_t kMaxSegmentsPerItem = 8192;  // < 32768: tile counters are 15 bit + flag
+constexpr uint32_t kMaxSegmentsPerItem = 2048;  // < 32768: tile counters are 15 bit + flag
+constexpr uint32_t kRecordChunk = 256;         // ordered-miss records are reserved per warp in chunks
 constexpr uint32_t kTileFlag = 0x8000u;
 
 // Walk constants of one ray (64 bytes).
@@ -290,6 +291,63 @@ OHMB200_HD inline void resumeSegment(const double init[3], const double delta[3]
         }
       }
       axis = selectNextAxis(tn);
+    }
+  }
+}
+
+// The hot-path variant of resumeSegment: no ranges, a running linear voxel index instead of coordinates, fp64 step
+// counters (no int->double conversion in the loop) and a branch per stepped axis instead of predicating all three.
+// visit(idx) receives the voxel index inside the region.  Same arithmetic, same order of comparisons.
+template <typename Visit>
+OHMB200_HD __forceinline__ void resumeSegmentFast(const double init[3], const double delta[3], const int local0[3],
+                                                  const int total[3], uint32_t flags, const int st_in[3], int visits,
+                                                  const Geom &g, Visit &&visit)
+{
+  int s0 = st_in[0], s1 = st_in[1], s2 = st_in[2];
+  const int d0 = (flags & 1u) ? -1 : 1, d1 = (flags & 2u) ? -1 : 1, d2 = (flags & 4u) ? -1 : 1;
+  int p0 = (local0[0] + d0 * s0) % g.dim[0];
+  int p1 = (local0[1] + d1 * s1) % g.dim[1];
+  int p2 = (local0[2] + d2 * s2) % g.dim[2];
+  p0 += (p0 < 0) ? g.dim[0] : 0;
+  p1 += (p1 < 0) ? g.dim[1] : 0;
+  p2 += (p2 < 0) ? g.dim[2] : 0;
+  const int stride1 = g.dim[0], stride2 = g.dim[0] * g.dim[1];
+  int idx = p0 + p1 * stride1 + p2 * stride2;
+  const int step0 = d0, step1 = d1 * stride1, step2 = d2 * stride2;
+  double m0 = (double)s0, m1 = (double)s1, m2 = (double)s2;
+  double t0 = (s0 < total[0]) ? (s0 == 0 ? init[0] : init[0] + delta[0] * m0) : (double)INFINITY;
+  double t1 = (s1 < total[1]) ? (s1 == 0 ? init[1] : init[1] + delta[1] * m1) : (double)INFINITY;
+  double t2 = (s2 < total[2]) ? (s2 == 0 ? init[2] : init[2] + delta[2] * m2) : (double)INFINITY;
+  for (int v = 0;;)
+  {
+    visit((uint32_t)idx);
+    if (++v >= visits)
+    {
+      break;
+    }
+    // walkSelectNextAxis: strict '<', ties go to the higher axis
+    const bool x_first = t0 < t1;
+    const bool low_first = x_first ? (t0 < t2) : (t1 < t2);
+    if (!low_first)
+    {
+      ++s2;
+      m2 += 1.0;
+      idx += step2;
+      t2 = (s2 < total[2]) ? init[2] + delta[2] * m2 : (double)INFINITY;
+    }
+    else if (x_first)
+    {
+      ++s0;
+      m0 += 1.0;
+      idx += step0;
+      t0 = (s0 < total[0]) ? init[0] + delta[0] * m0 : (double)INFINITY;
+    }
+    else
+    {
+      ++s1;
+      m1 += 1.0;
+      idx += step1;
+      t1 = (s1 < total[1]) ? init[1] + delta[1] * m1 : (double)INFINITY;
     }
   }
 }

@@ -61,6 +61,7 @@ static bool checkRay(const Geom &g, const double start[3], const double end[3], 
   const double len2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
   const double length = (len2 > 1e-6) ? sqrt(len2) : 0;
   std::vector<Visit> seg;
+  std::vector<uint32_t> fast_idx;
   int last_flags = 0;
   enumerateSegments(rec, g, [&](const int r[3], const int st[3], int n) {
     ++g_segments;
@@ -76,6 +77,9 @@ static bool checkRay(const Geom &g, const double start[3], const double end[3], 
                           seg.push_back(v);
                           last_flags += last_of_ray ? 1 : 0;
                         });
+    // the hot-path variant must visit the same voxels (as linear indices inside the region)
+    resumeSegmentFast(rec.initial, rec.delta, local0, total, rec.flags, st, n, g,
+                      [&](uint32_t idx) { fast_idx.push_back(idx); });
   });
   ++g_rays;
   g_visits += (long long)seq.size();
@@ -88,6 +92,11 @@ static bool checkRay(const Geom &g, const double start[3], const double end[3], 
     ok = ok && (i == 0 || memcmp(&seq[i].enter, &seg[i].enter, sizeof(double)) == 0);
   }
   ok = ok && (seq.empty() || last_flags == 1);
+  ok = ok && fast_idx.size() == seg.size();
+  for (size_t i = 0; ok && i < seg.size(); ++i)
+  {
+    ok = fast_idx[i] == (uint32_t)(seg[i].l[0] + seg[i].l[1] * g.dim[0] + seg[i].l[2] * g.dim[0] * g.dim[1]);
+  }
   if (!ok)
   {
     fprintf(stderr, "MISMATCH flags %u: (%.17g %.17g %.17g) -> (%.17g %.17g %.17g): sequential %zu visits, segments %zu\n",
