@@ -7,7 +7,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libohmb200.so")
 SOURCES = [os.path.join(HERE, "csrc", "ohmb200.cu")]
-DEPS = SOURCES + [os.path.join(HERE, "csrc", "ohmb200_device.cuh"), os.path.join(ROOT, "include", "ohmb200.h")]
+DEPS = SOURCES + [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc")) if f.endswith(".cuh")] + [
+    os.path.join(ROOT, "include", "ohmb200.h")]
 
 # --fmad=false: voxel sequences must match the CPU mapper bit for bit (see ohmb200_device.cuh).
 NVCC_FLAGS = [

@@ -16,6 +16,7 @@
 #include "ohmb200.h"
 #include "ohmb200_device.cuh"
 #include "ohmb200_regions.cuh"
+#include "ohmb200_ndt.cuh"
 
 #include <cub/block/block_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
@@ -835,8 +836,15 @@ int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_i
     }
     {
       KernelScope scope(m, kKWalkRegions);
-      walkRegions<<<m->sm_count * m->walk_ctas_per_sm, kWalkThreads, m->tile_bytes, s>>>(m->dm, m->geom, m->mp, b,
-                                                                                      has_samples ? 1 : 0);
+      if (m->mode == OHMB200_MODE_NDT)
+      {
+        walkRegionsNdt<<<m->sm_count * m->walk_ctas_per_sm, kWalkThreads, m->tile_bytes, s>>>(m->dm, m->geom, m->mp, b);
+      }
+      else
+      {
+        walkRegions<<<m->sm_count * m->walk_ctas_per_sm, kWalkThreads, m->tile_bytes, s>>>(m->dm, m->geom, m->mp, b,
+                                                                                        has_samples ? 1 : 0);
+      }
     }
     if (has_samples)
     {
@@ -846,7 +854,14 @@ int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_i
       }
       {
         KernelScope scope(m, kKSamples);
-        applySamples<<<blocks, threads, 0, s>>>(m->dm, m->geom, m->mp, b);
+        if (m->mode == OHMB200_MODE_NDT)
+        {
+          applySamplesNdt<<<blocks, threads, 0, s>>>(m->dm, m->geom, m->mp, b);
+        }
+        else
+        {
+          applySamples<<<blocks, threads, 0, s>>>(m->dm, m->geom, m->mp, b);
+        }
       }
     }
     CUDA_TRY(cudaGetLastError());
@@ -1068,13 +1083,26 @@ ohmb200_map *ohmb200_create(const ohmb200_params *params, int mode, size_t devic
   {
     m->algo = atoi(env) ? 1 : 0;
   }
-  if (m->tile_bytes > 200u * 1024u || mode != OHMB200_MODE_OCCUPANCY)
+  const bool ndt = mode == OHMB200_MODE_NDT || mode == OHMB200_MODE_NDT_TM;
+  if (ndt)
+  {
+    m->tile_bytes = ((m->tile_bytes + 15u) & ~(size_t)15u) + sizeof(uint32_t) * ((m->geom.vpr + 31u) / 32u);
+    m->algo = 1;  // NDT runs on the region-binned path only
+  }
+  if (m->tile_bytes > 200u * 1024u || mode == OHMB200_MODE_TSDF)
   {
     m->algo = 0;
   }
+  if (mode == OHMB200_MODE_NDT_TM || mode == OHMB200_MODE_TSDF || (ndt && m->algo == 0))
+  {
+    setError(OHMB200_E_INVALID, "ohmb200_create: mode %d is not implemented on the device yet (occupancy and NDT-OM are)", mode);
+    delete m;
+    return nullptr;
+  }
   if (m->algo == 1)
   {
-    if (cudaFuncSetAttribute(walkRegions, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->tile_bytes) != cudaSuccess)
+    if (cudaFuncSetAttribute(walkRegions, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->tile_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(walkRegionsNdt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->tile_bytes) != cudaSuccess)
     {
       cudaGetLastError();
       m->algo = 0;

@@ -524,7 +524,8 @@ __device__ inline uint32_t updateIncidentNormal(uint32_t packed, float ix, float
   count = ((nx != 0 || ny != 0 || nz != 0) && count) ? count : 0;
   const float w = 1.0f / (float)(count + 1u);
   float len2 = ix * ix + iy * iy + iz * iz;
-  float s = (len2 > 1e-6f) ? 1.0f / sqrtf(len2) : 0.0f;
+  // the reference forms this reciprocal in double (its `sqrt(float)` is the double overload) and narrows it
+  float s = (len2 > 1e-6f) ? (float)(1.0 / sqrt((double)len2)) : 0.0f;
   ix *= s;
   iy *= s;
   iz *= s;
@@ -532,7 +533,7 @@ __device__ inline uint32_t updateIncidentNormal(uint32_t packed, float ix, float
   ny += (iy - ny) * w;
   nz += (iz - nz) * w;
   len2 = nx * nx + ny * ny + nz * nz;
-  s = (len2 > 1e-6f) ? 1.0f / sqrtf(len2) : 0.0f;
+  s = (len2 > 1e-6f) ? (float)(1.0 / sqrt((double)len2)) : 0.0f;
   nx *= s;
   ny *= s;
   nz *= s;

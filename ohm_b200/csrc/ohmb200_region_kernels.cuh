@@ -497,3 +497,390 @@ __global__ void linkRecords(Batch b)
     b.record_next[r] = atomicExch(&b.run_head[head], (int32_t)r);
   }
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// NDT (GpuNdtMap, NdtMode::kOccupancy): RayMapperNdt.cpp:84-407
+// ---------------------------------------------------------------------------------------------------------
+
+// NDT miss adjustment of one visit to a voxel with an established Gaussian, added straight to the occupancy slab.
+// Such a voxel receives no sample in this batch (it would be flagged), so its mean/covariance are constant for the
+// whole batch; the adjustments are <= 0, and sum-then-clamp equals the sequential clamp-each-time.
+__device__ __noinline__ void ndtVisit(const DeviceMap &dm, const Geom &g, const MapParams &mp, const Batch &b, uint32_t ray,
+                                uint32_t slot, uint32_t idx)
+{
+  double sensor[3], sample[3];
+  loadRay(b, ray, sensor, sample);
+  unsigned filter_flags = 0;
+  applyRayFilter(mp, sensor, sample, filter_flags);  // the mapper hands calculateMissNdt the filtered points
+  const uint32_t vid = slot * g.vpr + idx;
+  int r[3];
+  unpackRegion(dm.keys[slot], r);
+  const int l[3] = { (int)(idx % (uint32_t)g.dim[0]), (int)((idx / (uint32_t)g.dim[0]) % (uint32_t)g.dim[1]),
+                     (int)(idx / ((uint32_t)g.dim[0] * (uint32_t)g.dim[1])) };
+  const uint2 vm = dm.mean[vid];
+  double mean[3];
+  subVoxelToLocal(vm.x, g.res, mean);
+  float cov[6];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+  {
+    mean[a] += voxelCentreAxis(g, r[a], l[a], a);
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k)
+  {
+    cov[k] = dm.covariance[(size_t)vid * 6 + k];
+  }
+  bool valid, is_miss;
+  const float adj = ndtMissAdjustment(cov, sensor, sample, mean, mp.adaptation_rate, mp.sensor_noise, valid, is_miss);
+  if (valid && adj != 0.0f)
+  {
+    atomicAdd(&dm.occupancy[vid], adj);
+  }
+}
+
+// walkRegions for NDT maps: same counter tile, plus a bit per voxel saying "established Gaussian" (mean count >=
+// sample threshold), staged from the mean layer when the work item starts.
+__global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsNdt(const __grid_constant__ DeviceMap dm, const __grid_constant__ Geom g,
+                                                                  const __grid_constant__ MapParams mp, const __grid_constant__ Batch b)
+{
+  extern __shared__ uint32_t tile[];
+  __shared__ WorkItem item;
+  __shared__ uint32_t sample_range[2];
+  __shared__ unsigned long long record_chunk[kWalkThreads / 32];
+  const uint32_t words = (g.vpr + 1u) >> 1;
+  const uint32_t kind_words = (g.vpr + 31u) >> 5;
+  uint32_t *kind = tile + ((words + 3u) & ~3u);
+  const uint32_t tid = threadIdx.x;
+  const uint32_t warp = tid >> 5;
+  if ((tid & 31u) == 0)
+  {
+    record_chunk[warp] = (unsigned long long)kRecordChunk;
+  }
+  for (;;)
+  {
+    __syncthreads();
+    if (tid == 0)
+    {
+      const uint32_t w = atomicAdd(&b.counters->work_next, 1u);
+      if (w < min(b.counters->item_count, b.item_capacity))
+      {
+        item = b.items[w];
+      }
+      else
+      {
+        item.slot = 0xFFFFFFFFu;
+      }
+    }
+    __syncthreads();
+    if (item.slot == 0xFFFFFFFFu)
+    {
+      return;
+    }
+    const uint32_t slot = item.slot;
+    const uint32_t vbase = slot * g.vpr;
+    for (uint32_t w = tid; w < words; w += blockDim.x)
+    {
+      tile[w] = 0;
+    }
+    for (uint32_t w = tid; w < kind_words; w += blockDim.x)
+    {
+      kind[w] = 0;
+    }
+    if (tid < 2)
+    {
+      sample_range[tid] = lowerBound(b.keys_out, b.n, vbase + tid * g.vpr);
+    }
+    __syncthreads();
+    for (uint32_t v = tid; v < g.vpr; v += blockDim.x)
+    {
+      if (dm.mean[vbase + v].y >= mp.sample_threshold)
+      {
+        atomicOr(&kind[v >> 5], 1u << (v & 31u));
+      }
+    }
+    for (uint32_t s = sample_range[0] + tid; s < sample_range[1]; s += blockDim.x)
+    {
+      const uint32_t v = b.keys_out[s] - vbase;
+      atomicOr(&tile[v >> 1], kTileFlag << ((v & 1u) * 16u));
+    }
+    __syncthreads();
+
+    for (uint32_t s = item.begin + tid; s < item.end; s += blockDim.x)
+    {
+      const uint4 raw = reinterpret_cast<const uint4 *>(b.segments)[s];
+      const uint32_t ray = raw.x;
+      const int st[3] = { (int)(raw.y & 0xffffu), (int)(raw.y >> 16), (int)(raw.z & 0xffffu) };
+      const int visits = (int)(raw.z >> 16);
+      const RayRec *rp = b.recs + ray;
+      const uint4 tail = reinterpret_cast<const uint4 *>(rp)[3];
+      const uint32_t flags = (tail.z >> 8) & 0xffu;
+      const int total[3] = { (int)(tail.z >> 16), (int)(tail.w & 0xffffu), (int)(tail.w >> 16) };
+      const int local0[3] = { (int)((tail.y >> 16) & 0xffu), (int)(tail.y >> 24), (int)(tail.z & 0xffu) };
+      const double init[3] = { rp->initial[0], rp->initial[1], rp->initial[2] };
+      const double delta[3] = { rp->delta[0], rp->delta[1], rp->delta[2] };
+      auto count_visit = [&](uint32_t idx) {
+        const uint32_t shift = (idx & 1u) * 16u;
+        const uint32_t old = atomicAdd(&tile[idx >> 1], 1u << shift);
+        if ((old >> shift) & kTileFlag)
+        {
+          const unsigned group = __activemask();
+          const uint32_t n = (uint32_t)__popc(group);
+          const uint32_t rank = (uint32_t)__popc(group & ((1u << (tid & 31u)) - 1u));
+          uint32_t at = 0;
+          if (rank == 0)
+          {
+            const unsigned long long state = atomicAdd(&record_chunk[warp], (unsigned long long)n);
+            const uint32_t used = (uint32_t)state;
+            if (used + n <= kRecordChunk)
+            {
+              at = (uint32_t)(state >> 32) + used;
+            }
+            else
+            {
+              at = atomicAdd(&b.counters->record_count, kRecordChunk);
+              atomicExch(&record_chunk[warp], ((unsigned long long)at << 32) | n);
+            }
+          }
+          at = __shfl_sync(group, at, __ffs(group) - 1) + rank;
+          if (at < b.record_capacity)
+          {
+            b.record_vid[at] = vbase + idx;
+            b.record_ray[at] = ray;
+          }
+          else
+          {
+            b.counters->record_overflow = 1;
+            b.counters->overflow_seen = 1;
+          }
+        }
+        else if ((kind[idx >> 5] >> (idx & 31u)) & 1u)
+        {
+          ndtVisit(dm, g, mp, b, ray, slot, idx);
+        }
+      };
+      if (dm.traversal)
+      {
+        const int dx = g.dim[0], dxy = g.dim[0] * g.dim[1];
+        resumeSegment<true>(init, delta, local0, total, flags, st, visits, b.ray_length[ray], g,
+                            [&](const int l[3], double t_enter, double t_exit, bool last_of_ray) {
+                              const uint32_t idx = (uint32_t)(l[0] + l[1] * dx + l[2] * dxy);
+                              count_visit(idx);
+                              atomicAdd(&dm.traversal[vbase + idx], (float)(t_exit - t_enter));
+                              if (last_of_ray)
+                              {
+                                b.last_exit[ray] = t_exit;
+                              }
+                            });
+      }
+      else
+      {
+        resumeSegmentFast(init, delta, local0, total, flags, st, visits, g, count_visit);
+      }
+    }
+    __syncthreads();
+
+    // Fold.  Plain voxels: k identical misses (RayMapperNdt applies no exclusion flags).  Gaussian voxels: the
+    // adjustments are already in the slab; apply occupancyAdjustDown's clamp.
+    float *occ = dm.occupancy + (size_t)vbase;
+    for (uint32_t v = tid; v < g.vpr; v += blockDim.x)
+    {
+      const uint32_t half = (tile[v >> 1] >> ((v & 1u) * 16u)) & 0xffffu;
+      if (half == 0 || (half & kTileFlag))
+      {
+        continue;
+      }
+      const bool gaussian = (kind[v >> 5] >> (v & 31u)) & 1u;
+      int *addr = reinterpret_cast<int *>(occ + v);
+      int seen = *reinterpret_cast<volatile int *>(addr);
+      for (;;)
+      {
+        const float cur = __int_as_float(seen);
+        const float next = gaussian ? fmaxf(mp.min_value, cur) : missRepeat(cur, half, mp, 0u);
+        if (__float_as_int(next) == seen)
+        {
+          break;
+        }
+        const int prev = atomicCAS(addr, seen, __float_as_int(next));
+        if (prev == seen)
+        {
+          break;
+        }
+        seen = prev;
+      }
+    }
+  }
+}
+
+// Sample-voxel updates of RayMapperNdt (RayMapperNdt.cpp:284-404), one thread per voxel, hits in ray order; the
+// recorded misses of an interval are applied with the voxel state of that moment.
+__global__ void __launch_bounds__(128) applySamplesNdt(DeviceMap dm, Geom g, MapParams mp, Batch b)
+{
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned samples = 0, ordered = 0;
+  if (t < b.counters->run_count)
+  {
+    const uint32_t head = b.run_list[t];
+    const uint32_t vid = b.keys_out[head];
+    uint32_t k = 1;
+    while (head + k < b.n && b.keys_out[head + k] == vid)
+    {
+      ++k;
+    }
+    uint32_t tail = 0;
+    for (int32_t rec = b.run_head[head]; rec >= 0; rec = b.record_next[rec])
+    {
+      const uint32_t ray = b.record_ray[rec];
+      uint32_t lo = 0, hi = k;
+      while (lo < hi)
+      {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (b.vals_out[head + mid] < ray)
+        {
+          lo = mid + 1;
+        }
+        else
+        {
+          hi = mid;
+        }
+      }
+      b.record_vid[rec] = lo;  // interval of this record (the voxel id is no longer needed)
+      if (lo < k)
+      {
+        ++b.interval_count[head + lo];
+      }
+      else
+      {
+        ++tail;
+      }
+      ++ordered;
+    }
+
+    const uint32_t slot = vid / g.vpr;
+    const uint32_t local = vid - slot * g.vpr;
+    Key key;
+    unpackRegion(dm.keys[slot], key.r);
+    key.l[0] = (int)(local % (uint32_t)g.dim[0]);
+    key.l[1] = (int)((local / (uint32_t)g.dim[0]) % (uint32_t)g.dim[1]);
+    key.l[2] = (int)(local / ((uint32_t)g.dim[0] * (uint32_t)g.dim[1]));
+    double centre[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+    {
+      centre[a] = voxelCentreAxis(g, key.r[a], key.l[a], a);
+    }
+    float value = dm.occupancy[vid];
+    uint2 vm = dm.mean[vid];
+    float cov[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c)
+    {
+      cov[c] = dm.covariance[(size_t)vid * 6 + c];
+    }
+    uint32_t incident = dm.incident ? dm.incident[vid] : 0;
+    uint32_t touch = 0;
+    bool touch_set = false;
+    float traversal_add = 0.0f;
+    for (uint32_t j = 0; j <= k; ++j)
+    {
+      const uint32_t misses = (j < k) ? b.interval_count[head + j] : tail;
+      if (misses)
+      {
+        double mean[3];
+        subVoxelToLocal(vm.x, g.res, mean);
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+        {
+          mean[a] += centre[a];
+        }
+        uint32_t found = 0;
+        for (int32_t rec = b.run_head[head]; rec >= 0 && found < misses; rec = b.record_next[rec])
+        {
+          if (b.record_vid[rec] != j)
+          {
+            continue;
+          }
+          ++found;
+          double sensor[3], sample[3];
+          loadRay(b, b.record_ray[rec], sensor, sample);
+          unsigned filter_flags = 0;
+          applyRayFilter(mp, sensor, sample, filter_flags);
+          value = ndtMissOnce(value, cov, sensor, sample, mean, vm.y, mp);
+        }
+      }
+      if (j == k)
+      {
+        break;
+      }
+      const uint32_t ray = b.vals_out[head + j];
+      double start[3], end[3];
+      loadRay(b, ray, start, end);
+      double mean[3];
+      subVoxelToLocal(vm.x, g.res, mean);
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+      {
+        mean[a] += centre[a];
+      }
+      const float initial = value;
+      float adjusted = initial;
+      const bool reset = ndtHit(cov, adjusted, end, mean, vm.y, mp.hit_value, (float)g.res, mp.reinit_threshold,
+                                mp.reinit_count);
+      value = adjustUp(initial, adjusted, mp);
+      vm.y = reset ? 0u : vm.y;
+      const double local_pt[3] = { end[0] - centre[0], end[1] - centre[1], end[2] - centre[2] };
+      vm.x = subVoxelUpdate(vm.x, vm.y, local_pt, g.res);
+      ++vm.y;
+      if (dm.traversal)
+      {
+        const double d[3] = { end[0] - start[0], end[1] - start[1], end[2] - start[2] };
+        const double len = sqrt((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]);
+        traversal_add += (float)(len - b.last_exit[ray]);
+      }
+      if (dm.touch_time && b.timestamps)
+      {
+        touch = encodeTouchTime(b.time_base, b.timestamps[ray]);
+        touch_set = true;
+      }
+      if (dm.incident)
+      {
+        incident = updateIncidentNormal(incident, (float)(start[0] - end[0]), (float)(start[1] - end[1]),
+                                        (float)(start[2] - end[2]), vm.y - 1u);
+      }
+      ++samples;
+    }
+    dm.occupancy[vid] = value;
+    dm.mean[vid] = vm;
+#pragma unroll
+    for (int c = 0; c < 6; ++c)
+    {
+      dm.covariance[(size_t)vid * 6 + c] = cov[c];
+    }
+    if (dm.incident)
+    {
+      dm.incident[vid] = incident;
+    }
+    if (touch_set)
+    {
+      dm.touch_time[vid] = touch;
+    }
+    if (dm.traversal)
+    {
+      atomicAdd(&dm.traversal[vid], traversal_add);
+    }
+  }
+  __syncwarp();
+  const unsigned s = __reduce_add_sync(0xffffffffu, samples);
+  const unsigned o = __reduce_add_sync(0xffffffffu, ordered);
+  if ((threadIdx.x & 31) == 0)
+  {
+    if (s)
+    {
+      atomicAdd(&b.counters->sample_updates, (unsigned long long)s);
+    }
+    if (o)
+    {
+      atomicAdd(&b.counters->ordered_records, (unsigned long long)o);
+    }
+  }
+}

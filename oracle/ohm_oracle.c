@@ -751,7 +751,10 @@ uint32_t oracle_update_incident_normal(uint32_t packed, const float incident_in[
   count = ((n[0] != 0 || n[1] != 0 || n[2] != 0) && count) ? count : 0;
   const float one_on_count_plus_one = 1.0f / (float)(count + 1u);
   float len2 = inc[0] * inc[0] + inc[1] * inc[1] + inc[2] * inc[2];
-  float s = (len2 > 1e-6f) ? 1.0f / sqrtf(len2) : 0.0f;
+  /* `1.0f / sqrt(float)` in the reference resolves to the double sqrt (only <cmath>'s ::sqrt(double) is visible in
+   * namespace ohm), so the reciprocal is formed in double and narrowed by glm's `vec *= scalar`; verified against
+   * the reference itself (oracle/_ref, tests/test_oracle_vs_ref.py). */
+  float s = (len2 > 1e-6f) ? (float)(1.0 / sqrt((double)len2)) : 0.0f;
   for (int a = 0; a < 3; ++a)
   {
     inc[a] *= s;
@@ -761,7 +764,7 @@ uint32_t oracle_update_incident_normal(uint32_t packed, const float incident_in[
     n[a] += (inc[a] - n[a]) * one_on_count_plus_one;
   }
   len2 = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
-  s = (len2 > 1e-6f) ? 1.0f / sqrtf(len2) : 0.0f;
+  s = (len2 > 1e-6f) ? (float)(1.0 / sqrt((double)len2)) : 0.0f;
   for (int a = 0; a < 3; ++a)
   {
     n[a] *= s;
