@@ -121,25 +121,35 @@ def sweep_rays():
     return np.ascontiguousarray(rays)
 
 
-def cpu_baseline(rays, reps):
-    """The oracle port of RayMapperOccupancy, single thread (the reference mapper is single-threaded by design,
-    ohm/RayMapperOccupancy.h:25-27), on `reps` fresh-map passes of the same sweep."""
+def cpu_mapper():
+    """(constructor, kind): the reference's own RayMapperOccupancy when oracle/_ref was built from /root/reference
+    (it travels to the GPU box as a prebuilt .so), else the C port of it."""
     from oracle import pyoracle as po
+    from oracle import pyref as pr
     po.lib()
+    if pr.available(build=False):
+        return pr.ReferenceMap, "reference"
+    return po.OracleMap, "port"
+
+
+def cpu_baseline(rays, reps):
+    """ohm's CPU RayMapperOccupancy, single thread (the mapper is single-threaded by design,
+    ohm/RayMapperOccupancy.h:25-27), on `reps` fresh-map passes of the same sweep."""
+    ctor, kind = cpu_mapper()
     n = rays.shape[0] // 2
     times = []
-    stats = None
     for _ in range(reps):
-        m = po.OracleMap(RESOLUTION)
+        m = ctor(RESOLUTION)
         t0 = time.perf_counter()
         m.integrate_rays(rays)
         times.append(time.perf_counter() - t0)
-        stats = m.stats()
         m.close()
     t = float(np.median(times))
-    return {"value": n / t / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"{reps} x full config-2 sweep ({n} rays, {stats['voxel_visits']} voxel visits) into a fresh map, "
-                      f"median {t:.3f} s/sweep", "seconds_per_sweep": t}
+    what = ("ohm::RayMapperOccupancy built from the reference sources (oracle/_ref)" if kind == "reference"
+            else "C port of ohm::RayMapperOccupancy (oracle/ohm_oracle.c)")
+    return {"value": n / t / 1e6, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": f"{reps} x full config-2 sweep ({n} rays) into a fresh map, median {t:.3f} s/sweep; {what}",
+            "seconds_per_sweep": t}
 
 
 def run_reference(args):
@@ -148,31 +158,30 @@ def run_reference(args):
         return
     rays = sweep_rays()
     n = rays.shape[0] // 2
-    from oracle import pyoracle as po
-    po.lib()
+    ctor, kind = cpu_mapper()
     for _ in range(min(args.warmup, 1)):
-        m = po.OracleMap(RESOLUTION)
+        m = ctor(RESOLUTION)
         m.integrate_rays(rays)
         m.close()
     t_total = 0.0
-    visits = 0
     for _ in range(args.steps):
-        m = po.OracleMap(RESOLUTION)
+        m = ctor(RESOLUTION)
         t0 = time.perf_counter()
         m.integrate_rays(rays)
         t_total += time.perf_counter() - t0
-        visits = m.stats()["voxel_visits"]
         m.close()
     ms = 1e3 * t_total / args.steps
     value = n / (ms * 1e-3) / 1e6
+    what = ("ohm::RayMapperOccupancy, the reference's own CPU mapper compiled unmodified from its sources (oracle/_ref)"
+            if kind == "reference" else "C port of ohm::RayMapperOccupancy (oracle/ohm_oracle.c)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64 walk / f32 log-odds", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "rays_per_step": n, "voxel_visits_per_step": visits,
-                   "note": "CPU RayMapperOccupancy restated in C (oracle/ohm_oracle.c), 1 thread — the reference mapper is "
-                           "single-threaded by design; each step is the full sweep into a fresh map"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+        "config": {"workload": WORKLOAD, "rays_per_step": n,
+                   "note": f"{what}; 1 thread — the mapper is single-threaded by design (ohm/RayMapperOccupancy.h:25-27); "
+                           "each step is the full sweep into a fresh map"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind,
                          "sample": f"{args.steps} x full sweep of {n} rays"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
