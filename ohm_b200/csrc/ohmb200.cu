@@ -525,6 +525,8 @@ struct ohmb200_map
   size_t region_layer_bytes[OHMB200_LAYER_COUNT] = {};
   cudaStream_t own_stream = nullptr;
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t side_stream = nullptr;  // sample path of a batch, concurrent with the segment path
+  cudaEvent_t fork_event = nullptr, join_event = nullptr;
   cudaStream_t stream = nullptr;
   Counters *d_counters = nullptr;
   Counters *h_counters = nullptr;  // pinned
@@ -813,17 +815,26 @@ int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_i
       KernelScope scope(m, kKPrepRays);
       prepRays<<<blocks, threads, 0, s>>>(m->dm, m->geom, m->mp, b, m->mode);
     }
+    // The sample path (sort -> run heads) and the segment path (plan -> scatter) only meet at walkRegions: run them
+    // on two streams.  (With per-kernel profiling on they are serialised so that the event pairs stay meaningful.)
+    const bool fork = has_samples && !m->profiling;
+    cudaStream_t sample_stream = fork ? m->side_stream : s;
+    if (fork)
+    {
+      CUDA_TRY(cudaEventRecord(m->fork_event, s));
+      CUDA_TRY(cudaStreamWaitEvent(sample_stream, m->fork_event, 0));
+    }
     if (has_samples)
     {
       {
         KernelScope scope(m, kKSort);
         size_t temp = m->cub_temp_bytes;
         cub::DeviceRadixSort::SortPairs(m->cub_temp, temp, b.keys_in, b.keys_out, b.vals_in, b.vals_out, (int)n, 0,
-                                        m->sort_bits, s);
+                                        m->sort_bits, sample_stream);
       }
       {
         KernelScope scope(m, kKMark);
-        markRuns<<<blocks, threads, 0, s>>>(m->dm, b);
+        markRuns<<<blocks, threads, 0, sample_stream>>>(m->dm, b);
       }
     }
     {
@@ -833,6 +844,11 @@ int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_i
     {
       KernelScope scope(m, kKEmit);
       emitSegments<<<blocks, threads, 0, s>>>(m->dm, m->geom, b);
+    }
+    if (fork)
+    {
+      CUDA_TRY(cudaEventRecord(m->join_event, sample_stream));
+      CUDA_TRY(cudaStreamWaitEvent(s, m->join_event, 0));
     }
     {
       KernelScope scope(m, kKWalkRegions);
@@ -1133,6 +1149,9 @@ ohmb200_map *ohmb200_create(const ohmb200_params *params, int mode, size_t devic
   bool ok = true;
   ok = ok && cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&m->side_stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&m->fork_event, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&m->join_event, cudaEventDisableTiming) == cudaSuccess;
   m->stream = m->own_stream;
   for (int i = 0; i < 2 && ok; ++i)
   {
@@ -1246,6 +1265,18 @@ void ohmb200_destroy(ohmb200_map *m)
   if (m->copy_stream)
   {
     cudaStreamDestroy(m->copy_stream);
+  }
+  if (m->side_stream)
+  {
+    cudaStreamDestroy(m->side_stream);
+  }
+  if (m->fork_event)
+  {
+    cudaEventDestroy(m->fork_event);
+  }
+  if (m->join_event)
+  {
+    cudaEventDestroy(m->join_event);
   }
   cudaGetLastError();
   delete m;
