@@ -114,6 +114,8 @@ struct Batch
   uint32_t seg_capacity;
   WorkItem *items;         // (region, segment range) work list
   uint32_t item_capacity;
+  unsigned long long *record_keys;         // TSDF: (voxel id << 32 | ray) of every visit that must be replayed in order
+  unsigned long long *record_keys_sorted;
   Counters *counters;
 };
 
@@ -461,6 +463,7 @@ __global__ void __launch_bounds__(256) resolveMisses(DeviceMap dm, Geom g, MapPa
 }
 
 #include "ohmb200_region_kernels.cuh"
+#include "ohmb200_tsdf_kernels.cuh"
 
 __global__ void fillFloat(float *dst, size_t n, float value)
 {
@@ -501,12 +504,14 @@ enum KernelId
   kKEmit,
   kKWalkRegions,
   kKLink,
+  kKTsdfMark,
+  kKTsdfReplay,
   kKernelCount
 };
 static const char *kKernelNames[kKernelCount] = { "prepSamples",  "radixSort",     "markRuns",      "walkRays",
                                                   "applySamples", "resolveMisses", "gatherRegions", "fillFloat",
                                                   "prepRays",     "planRegions",   "emitSegments",  "walkRegions",
-                                                  "linkRecords" };
+                                                  "linkRecords",  "walkRegionsTsdf<mark>", "replayTsdf" };
 static_assert(kKernelCount <= OHMB200_KERNEL_SLOTS, "raise OHMB200_KERNEL_SLOTS");
 
 struct ohmb200_map
@@ -517,6 +522,8 @@ struct ohmb200_map
   int algo = 1;           // 1 = region-binned walk (shared-memory tiles), 0 = one thread per ray (global counters)
   size_t tile_bytes = 0;  // dynamic shared memory of walkRegions
   int walk_ctas_per_sm = 1;
+  uint32_t *tsdf_flags = nullptr;  // TSDF: one bit per voxel, "replay this voxel's visits in order"
+  size_t tsdf_flag_bytes = 0;
   ohmb200_params params{};
   Geom geom{};
   MapParams mp{};
@@ -758,6 +765,13 @@ int ensureScratch(ohmb200_map *m, size_t n)
     rc |= deviceAlloc(b.segments, b.seg_capacity);
     b.item_capacity = m->dm.capacity + b.seg_capacity / kMaxSegmentsPerItem + 16;
     rc |= deviceAlloc(b.items, b.item_capacity);
+    if (m->mode == OHMB200_MODE_TSDF)
+    {
+      cudaFree(b.record_keys);
+      cudaFree(b.record_keys_sorted);
+      rc |= deviceAlloc(b.record_keys, b.record_capacity);
+      rc |= deviceAlloc(b.record_keys_sorted, b.record_capacity);
+    }
   }
   if (rc)
   {
@@ -766,6 +780,13 @@ int ensureScratch(ohmb200_map *m, size_t n)
   m->cub_temp_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, m->cub_temp_bytes, b.keys_in, b.keys_out, b.vals_in, b.vals_out, (int)cap, 0,
                                   m->sort_bits, m->stream);
+  if (m->mode == OHMB200_MODE_TSDF && m->algo == 1)
+  {
+    size_t keys_bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, keys_bytes, b.record_keys, b.record_keys_sorted, (int)b.record_capacity, 0, 64,
+                                   m->stream);
+    m->cub_temp_bytes = std::max(m->cub_temp_bytes, keys_bytes);
+  }
   CUDA_TRY(cudaMalloc(&m->cub_temp, std::max<size_t>(m->cub_temp_bytes, 16)));
   m->scratch_rays = cap;
   return OHMB200_OK;
@@ -849,6 +870,40 @@ int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_i
     {
       CUDA_TRY(cudaEventRecord(m->join_event, sample_stream));
       CUDA_TRY(cudaStreamWaitEvent(s, m->join_event, 0));
+    }
+    if (m->mode == OHMB200_MODE_TSDF)
+    {
+      const unsigned grid = m->sm_count * m->walk_ctas_per_sm;
+      CUDA_TRY(cudaMemsetAsync(m->tsdf_flags, 0, m->tsdf_flag_bytes, s));
+      CUDA_TRY(cudaMemsetAsync(b.record_keys, 0xFF, sizeof(unsigned long long) * b.record_capacity, s));
+      {
+        KernelScope scope(m, kKTsdfMark);
+        walkRegionsTsdf<false><<<grid, kWalkThreads, m->tile_bytes, s>>>(m->dm, m->geom, m->mp, b, m->tsdf_flags);
+      }
+      {
+        KernelScope scope(m, kKWalkRegions);
+        walkRegionsTsdf<true><<<grid, kWalkThreads, m->tile_bytes, s>>>(m->dm, m->geom, m->mp, b, m->tsdf_flags);
+      }
+      // The ordered records are sorted by (voxel, ray) with a host-known count: the one host wait of the TSDF path.
+      CUDA_TRY(cudaMemcpyAsync(m->h_counters, m->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(cudaStreamSynchronize(s));
+      const uint32_t records = std::min(m->h_counters->record_count, b.record_capacity);
+      if (records)
+      {
+        {
+          KernelScope scope(m, kKSort);
+          size_t temp = m->cub_temp_bytes;
+          cub::DeviceRadixSort::SortKeys(m->cub_temp, temp, b.record_keys, b.record_keys_sorted, (int)records, 0, 64, s);
+        }
+        {
+          KernelScope scope(m, kKTsdfReplay);
+          replayTsdf<<<(records + 127) / 128, 128, 0, s>>>(m->dm, m->geom, m->mp, b, records);
+        }
+      }
+      CUDA_TRY(cudaGetLastError());
+      m->rays_in += n;
+      ++m->batches;
+      return OHMB200_OK;
     }
     {
       KernelScope scope(m, kKWalkRegions);
@@ -1105,11 +1160,16 @@ ohmb200_map *ohmb200_create(const ohmb200_params *params, int mode, size_t devic
     m->tile_bytes = ((m->tile_bytes + 15u) & ~(size_t)15u) + sizeof(uint32_t) * ((m->geom.vpr + 31u) / 32u);
     m->algo = 1;  // NDT runs on the region-binned path only
   }
-  if (m->tile_bytes > 200u * 1024u || mode == OHMB200_MODE_TSDF)
+  const bool tsdf = mode == OHMB200_MODE_TSDF;
+  if (tsdf)
+  {
+    m->algo = 1;
+  }
+  if (m->tile_bytes > 200u * 1024u)
   {
     m->algo = 0;
   }
-  if (mode == OHMB200_MODE_NDT_TM || mode == OHMB200_MODE_TSDF || (ndt && m->algo == 0))
+  if (mode == OHMB200_MODE_NDT_TM || ((ndt || tsdf) && m->algo == 0))
   {
     setError(OHMB200_E_INVALID, "ohmb200_create: mode %d is not implemented on the device yet (occupancy and NDT-OM are)", mode);
     delete m;
@@ -1118,7 +1178,9 @@ ohmb200_map *ohmb200_create(const ohmb200_params *params, int mode, size_t devic
   if (m->algo == 1)
   {
     if (cudaFuncSetAttribute(walkRegions, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->tile_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(walkRegionsNdt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->tile_bytes) != cudaSuccess)
+        cudaFuncSetAttribute(walkRegionsNdt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->tile_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(walkRegionsTsdf<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->tile_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(walkRegionsTsdf<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->tile_bytes) != cudaSuccess)
     {
       cudaGetLastError();
       m->algo = 0;
@@ -1126,6 +1188,10 @@ ohmb200_map *ohmb200_create(const ohmb200_params *params, int mode, size_t devic
     m->walk_ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (220u * 1024u) / (m->tile_bytes + 1024u)));
   }
   size_t bytes_per_region = (m->algo == 0) ? sizeof(uint32_t) * m->geom.vpr : 3 * sizeof(uint32_t);  // pending / counters
+  if (tsdf)
+  {
+    bytes_per_region += sizeof(uint32_t) * ((m->geom.vpr + 31u) / 32u);
+  }
   for (int l = 0; l < OHMB200_LAYER_COUNT; ++l)
   {
     if (m->params.layers & (1u << l))
@@ -1181,6 +1247,11 @@ ohmb200_map *ohmb200_create(const ohmb200_params *params, int mode, size_t devic
       ok = ok && cudaMalloc(&m->layer_slab[l], kLayerBytes[l] * voxels) == cudaSuccess;
     }
   }
+  if (tsdf)
+  {
+    m->tsdf_flag_bytes = sizeof(uint32_t) * ((m->geom.vpr + 31u) / 32u) * capacity;
+    ok = ok && cudaMalloc(&m->tsdf_flags, m->tsdf_flag_bytes) == cudaSuccess;
+  }
   if (!ok)
   {
     setError(OHMB200_E_CUDA, "ohmb200_create: device allocation failed (%zu region slots x %zu bytes): %s", capacity,
@@ -1224,7 +1295,8 @@ void ohmb200_destroy(ohmb200_map *m)
                       b.last_exit,      m->cub_temp,        m->d_rays[0],       m->d_rays[1],     m->d_intensities[0],
                       m->d_intensities[1], m->d_timestamps[0], m->d_timestamps[1], m->d_gather,    m->d_gather_slots,
                       b.recs,           b.ray_length,       b.record_vid,       b.seg_count,      b.seg_offset,
-                      b.seg_cursor,     b.segments,         b.items };
+                      b.seg_cursor,     b.segments,         b.items,            b.record_keys,    b.record_keys_sorted,
+                      m->tsdf_flags };
   for (void *p : to_free)
   {
     if (p)
