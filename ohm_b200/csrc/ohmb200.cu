@@ -907,7 +907,7 @@ int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_i
     }
     {
       KernelScope scope(m, kKWalkRegions);
-      if (m->mode == OHMB200_MODE_NDT)
+      if ((m->mode == OHMB200_MODE_NDT || m->mode == OHMB200_MODE_NDT_TM))
       {
         walkRegionsNdt<<<m->sm_count * m->walk_ctas_per_sm, kWalkThreads, m->tile_bytes, s>>>(m->dm, m->geom, m->mp, b);
       }
@@ -925,7 +925,7 @@ int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_i
       }
       {
         KernelScope scope(m, kKSamples);
-        if (m->mode == OHMB200_MODE_NDT)
+        if ((m->mode == OHMB200_MODE_NDT || m->mode == OHMB200_MODE_NDT_TM))
         {
           applySamplesNdt<<<blocks, threads, 0, s>>>(m->dm, m->geom, m->mp, b);
         }
@@ -1169,9 +1169,9 @@ ohmb200_map *ohmb200_create(const ohmb200_params *params, int mode, size_t devic
   {
     m->algo = 0;
   }
-  if (mode == OHMB200_MODE_NDT_TM || ((ndt || tsdf) && m->algo == 0))
+  if ((ndt || tsdf) && m->algo == 0)
   {
-    setError(OHMB200_E_INVALID, "ohmb200_create: mode %d is not implemented on the device yet (occupancy and NDT-OM are)", mode);
+    setError(OHMB200_E_INVALID, "ohmb200_create: mode %d needs a region whose counter tile fits in shared memory", mode);
     delete m;
     return nullptr;
   }

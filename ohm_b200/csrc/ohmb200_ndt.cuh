@@ -49,11 +49,9 @@ OHMB200_HD __forceinline__ void solveTriangular(const float cov[6], const double
   x[2] = d / cov[5];
 }
 
-// Returns the log-odds adjustment of an NDT miss for a voxel with an established Gaussian (count >= threshold and
-// observed); `valid` is false when the probability is NaN (the reference skips the update then).
-OHMB200_HD inline float ndtMissAdjustment(const float cov[6], const double sensor[3], const double sample[3],
-                                          const double mean[3], float adaptation_rate, float sensor_noise, bool &valid,
-                                          bool &is_miss)
+// calculateSampleLikelihoods (CovarianceVoxelCompute.h:227-267): p(x_ML | N(mu, P)) and p(x_ML | z).
+OHMB200_HD inline void ndtLikelihoods(const float cov[6], const double sensor[3], const double sample[3],
+                                      const double mean[3], float sensor_noise, double &p_voxel, double &p_sample)
 {
   double s2s[3], ray[3], m2s[3], a[3], bn[3], tmp[3], sol[3], x_ml[3];
 #pragma unroll
@@ -78,20 +76,62 @@ OHMB200_HD inline float ndtMissAdjustment(const float cov[6], const double senso
     tmp[i] = x_ml[i] - mean[i];
   }
   solveTriangular(cov, tmp, sol);
-  const double p_voxel = exp(-0.5 * dot3(sol, sol));
+  p_voxel = exp(-0.5 * dot3(sol, sol));
   const double noise_var = sensor_noise * sensor_noise;
 #pragma unroll
   for (int i = 0; i < 3; ++i)
   {
     tmp[i] = x_ml[i] - sample[i];
   }
-  const double p_sample = exp(-0.5 * dot3(tmp, tmp) / noise_var);
+  p_sample = exp(-0.5 * dot3(tmp, tmp) / noise_var);
+}
+
+// Returns the log-odds adjustment of an NDT miss for a voxel with an established Gaussian (count >= threshold and
+// observed); `valid` is false when the probability is NaN (the reference skips the update then).
+OHMB200_HD inline float ndtMissAdjustment(const float cov[6], const double sensor[3], const double sample[3],
+                                          const double mean[3], float adaptation_rate, float sensor_noise, bool &valid,
+                                          bool &is_miss)
+{
+  double p_voxel, p_sample;
+  ndtLikelihoods(cov, sensor, sample, mean, sensor_noise, p_voxel, p_sample);
   const double scaling = 0.5 * adaptation_rate;
   const double prod = p_voxel * (1.0 - p_sample);
   const double update = 0.5 - scaling * prod;
   is_miss = prod < scaling;
   valid = update == update;
   return valid ? (float)log(update / (1.0 - update)) : 0.0f;
+}
+
+// NDT-TM: calculateHitMissUpdateOnHit (CovarianceVoxelCompute.h:447-505), reinitialise_permeability_with_covariance = true
+// (RayMapperNdt.cpp:325).  hm = {hit_count, miss_count}.
+OHMB200_HD inline void ndtHitMissOnHit(const float cov[6], float value, uint2 &hm, const double sensor[3],
+                                       const double sample[3], const double mean[3], uint32_t count, const MapParams &p)
+{
+  const bool needs_reset =
+    value == INFINITY || (count == 0 || (value < p.reinit_threshold && count >= p.reinit_count));
+  const uint32_t initial_hit = (!needs_reset) ? hm.x : 0;
+  const uint32_t initial_miss = (!needs_reset) ? hm.y : 0;
+  double p_voxel, p_sample;
+  ndtLikelihoods(cov, sensor, sample, mean, p.sensor_noise, p_voxel, p_sample);
+  const double prod = p_voxel * p_sample;
+  const double eta = 0.5 * p.adaptation_rate;
+  const bool inc_hit = needs_reset || count < p.sample_threshold || (count >= p.sample_threshold && prod >= eta);
+  const bool inc_miss = !needs_reset && count >= p.sample_threshold && prod < eta && p_voxel >= eta;
+  hm.x = initial_hit + (inc_hit ? 1u : 0u);
+  hm.y = initial_miss + (inc_miss ? 1u : 0u);
+}
+
+// NDT-TM: calculateIntensityUpdateOnHit (CovarianceVoxelCompute.h:391-411).  im = {mean, covariance}.
+OHMB200_HD inline void ndtIntensityOnHit(float2 &im, float value, float sample, uint32_t count, const MapParams &p)
+{
+  const bool needs_reset = count == 0 || (value < p.reinit_threshold && count >= p.reinit_count);
+  const float delta = im.x - sample;
+  const float n = (float)count;
+  const float inv = 1.0f / (n + 1.0f);
+  const float mean = (!needs_reset) ? inv * (n * im.x + sample) : sample;
+  const float cv = (!needs_reset) ? inv * (n * im.y + inv * delta * delta) : p.initial_intensity_cov;
+  im.x = mean;
+  im.y = cv;
 }
 
 // calculateHitWithCovariance.  Returns true when the covariance was (re)initialised (the mean must restart).
@@ -171,10 +211,11 @@ OHMB200_HD __forceinline__ float adjustDown(float initial, float adjusted, const
 // One full NDT miss on a voxel whose state is known (used when replaying ordered misses of a flagged voxel):
 // calculateMissNdt + occupancyAdjustDown (RayMapperNdt.cpp:198-214).
 OHMB200_HD inline float ndtMissOnce(float value, const float cov[6], const double sensor[3], const double sample[3],
-                                    const double mean[3], uint32_t count, const MapParams &p)
+                                    const double mean[3], uint32_t count, const MapParams &p, bool &is_miss)
 {
   const float initial = value;
   float adjusted;
+  is_miss = true;
   if (initial == INFINITY)
   {
     adjusted = p.miss_value;
@@ -185,7 +226,7 @@ OHMB200_HD inline float ndtMissOnce(float value, const float cov[6], const doubl
   }
   else
   {
-    bool valid, is_miss;
+    bool valid;
     const float adj = ndtMissAdjustment(cov, sensor, sample, mean, p.adaptation_rate, p.sensor_noise, valid, is_miss);
     adjusted = valid ? initial + adj : initial;
   }

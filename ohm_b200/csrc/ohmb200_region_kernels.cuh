@@ -537,6 +537,10 @@ __device__ __noinline__ void ndtVisit(const DeviceMap &dm, const Geom &g, const 
   {
     atomicAdd(&dm.occupancy[vid], adj);
   }
+  if (dm.hit_miss && is_miss)
+  {
+    atomicAdd(&dm.hit_miss[vid].y, 1u);  // NDT-TM miss count (RayMapperNdt.cpp:203-209)
+  }
 }
 
 // walkRegions for NDT maps: same counter tile, plus a bit per voxel saying "established Gaussian" (mean count >=
@@ -691,6 +695,10 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsNdt(const __grid_c
         continue;
       }
       const bool gaussian = (kind[v >> 5] >> (v & 31u)) & 1u;
+      if (dm.hit_miss && !gaussian)
+      {
+        atomicAdd(&dm.hit_miss[vbase + v].y, half);  // every plain NDT miss counts as a miss
+      }
       int *addr = reinterpret_cast<int *>(occ + v);
       int seen = *reinterpret_cast<volatile int *>(addr);
       for (;;)
@@ -781,6 +789,9 @@ __global__ void __launch_bounds__(128) applySamplesNdt(DeviceMap dm, Geom g, Map
     uint32_t touch = 0;
     bool touch_set = false;
     float traversal_add = 0.0f;
+    const bool ndt_tm = mp.ndt_tm && dm.hit_miss && dm.intensity;
+    uint2 hm = ndt_tm ? dm.hit_miss[vid] : make_uint2(0, 0);
+    float2 im = ndt_tm ? dm.intensity[vid] : make_float2(0, 0);
     for (uint32_t j = 0; j <= k; ++j)
     {
       const uint32_t misses = (j < k) ? b.interval_count[head + j] : tail;
@@ -805,7 +816,9 @@ __global__ void __launch_bounds__(128) applySamplesNdt(DeviceMap dm, Geom g, Map
           loadRay(b, b.record_ray[rec], sensor, sample);
           unsigned filter_flags = 0;
           applyRayFilter(mp, sensor, sample, filter_flags);
-          value = ndtMissOnce(value, cov, sensor, sample, mean, vm.y, mp);
+          bool is_miss;
+          value = ndtMissOnce(value, cov, sensor, sample, mean, vm.y, mp, is_miss);
+          hm.y += is_miss ? 1u : 0u;
         }
       }
       if (j == k)
@@ -824,6 +837,11 @@ __global__ void __launch_bounds__(128) applySamplesNdt(DeviceMap dm, Geom g, Map
       }
       const float initial = value;
       float adjusted = initial;
+      if (ndt_tm)
+      {
+        ndtHitMissOnHit(cov, adjusted, hm, start, end, mean, vm.y, mp);
+        ndtIntensityOnHit(im, adjusted, b.intensities ? b.intensities[ray] : 0.0f, vm.y, mp);
+      }
       const bool reset = ndtHit(cov, adjusted, end, mean, vm.y, mp.hit_value, (float)g.res, mp.reinit_threshold,
                                 mp.reinit_count);
       value = adjustUp(initial, adjusted, mp);
@@ -867,6 +885,11 @@ __global__ void __launch_bounds__(128) applySamplesNdt(DeviceMap dm, Geom g, Map
     if (dm.traversal)
     {
       atomicAdd(&dm.traversal[vid], traversal_add);
+    }
+    if (ndt_tm)
+    {
+      dm.hit_miss[vid] = hm;
+      dm.intensity[vid] = im;
     }
   }
   __syncwarp();

@@ -110,3 +110,21 @@ def test_ndt_lidar_two_sweeps(gpu):
     compare_maps(g, c, tol_layers=OCC_TOL)
     st = check_counts(g, c)
     assert st["sample_updates"] == 2 * 131072
+
+
+def test_ndt_tm_intensity_and_hit_miss(gpu):
+    """NdtMode::kTraversability: intensity mean/covariance and hit/miss counts (CovarianceVoxelCompute.h:391-505)."""
+    g, c = make_pair(0.25, mode="ndt_tm")
+    assert g.params.ndt_tm == 1 and gm.LAYER_HIT_MISS in g.layers() and gm.LAYER_INTENSITY in g.layers()
+    rng = np.random.RandomState(9)
+    n = 4096
+    rays = np.empty((2 * n, 3))
+    rays[0::2] = [0.05, 0.05, 0.05]
+    pts = rng.uniform(-6, 6, size=(n, 3))
+    pts[:2048, 2] = -1.0 + rng.normal(scale=0.02, size=2048)
+    rays[1::2] = pts
+    intensities = rng.uniform(0, 255, n).astype(np.float32)
+    for _ in range(3):
+        integrate_both(g, c, rays, intensities=intensities, batch=1500)
+    compare_maps(g, c, tol_layers=OCC_TOL)
+    check_counts(g, c)
