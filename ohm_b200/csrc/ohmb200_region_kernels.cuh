@@ -269,6 +269,7 @@ __global__ void __launch_bounds__(128) emitSegments(DeviceMap dm, Geom g, Batch 
 }
 
 constexpr int kWalkThreads = 512;
+constexpr uint32_t kLengthBins = 128;  // visits per segment <= 3 * 255; 127+ share a bin
 
 // Persistent CTAs: one (region, segment range) work item at a time against a shared-memory counter tile.
 __global__ void __launch_bounds__(kWalkThreads, 2) walkRegions(DeviceMap dm, Geom g, MapParams mp, Batch b, int has_samples)
@@ -278,6 +279,10 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegions(DeviceMap dm, Geo
   __shared__ uint32_t sample_range[2];
   // per-warp reservation of ordered-miss record slots: (base << 32) | used
   __shared__ unsigned long long record_chunk[kWalkThreads / 32];
+  // segments of the item ordered by decreasing visit count: lanes of a warp then walk segments of (nearly) equal
+  // length, and a thread's strided share mixes long and short ones
+  __shared__ uint16_t order[kMaxSegmentsPerItem];
+  __shared__ uint32_t length_bins[kLengthBins];
   const uint32_t words = (g.vpr + 1u) >> 1;
   const uint32_t tid = threadIdx.x;
   const uint32_t warp = tid >> 5;
@@ -327,7 +332,18 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegions(DeviceMap dm, Geo
     {
       sample_range[tid] = lowerBound(b.keys_out, b.n, vbase + tid * g.vpr);
     }
+    if (tid < kLengthBins)
+    {
+      length_bins[tid] = 0;
+    }
     __syncthreads();
+    const uint32_t n_segments = item.end - item.begin;
+    const uint32_t *segment_words = reinterpret_cast<const uint32_t *>(b.segments + item.begin);
+    for (uint32_t k = tid; k < n_segments; k += blockDim.x)
+    {
+      const uint32_t visits = segment_words[4 * k + 2] >> 16;
+      atomicAdd(&length_bins[kLengthBins - 1u - min(visits, kLengthBins - 1u)], 1u);
+    }
     if (has_samples)
     {
       // Voxels that also receive samples in this batch: their misses must stay ordered against the hits.
@@ -336,11 +352,44 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegions(DeviceMap dm, Geo
         const uint32_t v = b.keys_out[s] - vbase;
         atomicOr(&tile[v >> 1], kTileFlag << ((v & 1u) * 16u));
       }
-      __syncthreads();
     }
-
-    for (uint32_t s = item.begin + tid; s < item.end; s += blockDim.x)
+    __syncthreads();
+    if (warp == 0)
     {
+      // exclusive scan of the 128 bins by one warp (4 bins per lane)
+      uint32_t c[4], sum = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+      {
+        c[k] = length_bins[tid * 4 + k];
+        sum += c[k];
+      }
+      uint32_t incl = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1)
+      {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+        incl += (tid >= (uint32_t)d) ? up : 0u;
+      }
+      uint32_t base = incl - sum;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+      {
+        length_bins[tid * 4 + k] = base;
+        base += c[k];
+      }
+    }
+    __syncthreads();
+    for (uint32_t k = tid; k < n_segments; k += blockDim.x)
+    {
+      const uint32_t visits = segment_words[4 * k + 2] >> 16;
+      order[atomicAdd(&length_bins[kLengthBins - 1u - min(visits, kLengthBins - 1u)], 1u)] = (uint16_t)k;
+    }
+    __syncthreads();
+
+    for (uint32_t k = tid; k < n_segments; k += blockDim.x)
+    {
+      const uint32_t s = item.begin + order[k];
       const uint4 raw = reinterpret_cast<const uint4 *>(b.segments)[s];
       const uint32_t ray = raw.x;
       const int st[3] = { (int)(raw.y & 0xffffu), (int)(raw.y >> 16), (int)(raw.z & 0xffffu) };

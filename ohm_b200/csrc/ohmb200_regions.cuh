@@ -112,6 +112,7 @@ OHMB200_HD inline void enumerateSegments(const RayRec &rec, const Geom &g, Emit 
   }
   const bool exclude_start = (rec.flags & kRecExcludeStart) != 0;
   const bool exclude_end = (rec.flags & kRecExcludeEnd) != 0;
+  const double inv_delta[3] = { 1.0 / rec.delta[0], 1.0 / rec.delta[1], 1.0 / rec.delta[2] };  // estimates only
   if (T == 0)
   {
     // start and end share a voxel: only the end-voxel visit can happen (LineWalkCompute.h:392-410)
@@ -193,20 +194,31 @@ OHMB200_HD inline void enumerateSegments(const RayRec &rec, const Geom &g, Emit 
       }
       const int rem = total[b] - st[b];
       const int k = (dir[b] > 0) ? g.dim[b] - l[b] : l[b] + 1;
-      // candidate new step counts n in [st, hi]; step number n is taken at time T_b(n - 1)
+      // candidate new step counts n in [st, hi]; step number n is taken at time T_b(n - 1) and "step n precedes the
+      // crossing" is monotone in n.  Start from the estimate (ct - initial) / delta and walk to the boundary with
+      // exact evaluations (typically two).
       int lo = st[b];
-      int hi = st[b] + min(rem, k - 1);
-      while (lo < hi)
+      const int hi = st[b] + min(rem, k - 1);
+      if (lo < hi)
       {
-        const int mid = (lo + hi + 1) >> 1;
-        if (stepPrecedes(stepTime(rec.initial[b], rec.delta[b], mid - 1), b, ct, ca))
+        const double guess = (ct - rec.initial[b]) * inv_delta[b];
+        int n = (guess >= (double)hi) ? hi : ((guess > (double)lo) ? (int)guess + 1 : lo);  // NaN -> lo
+        n = min(max(n, lo), hi);
+        if (n > lo && !stepPrecedes(stepTime(rec.initial[b], rec.delta[b], n - 1), b, ct, ca))
         {
-          lo = mid;
+          do
+          {
+            --n;
+          } while (n > lo && !stepPrecedes(stepTime(rec.initial[b], rec.delta[b], n - 1), b, ct, ca));
         }
         else
         {
-          hi = mid - 1;
+          while (n < hi && stepPrecedes(stepTime(rec.initial[b], rec.delta[b], n), b, ct, ca))
+          {
+            ++n;
+          }
         }
+        lo = n;
       }
       nst[b] = lo;
     }
