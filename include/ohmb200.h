@@ -55,7 +55,8 @@ enum ohmb200_filter
 {
   OHMB200_FILTER_NONE = 0,
   OHMB200_FILTER_GOOD_RAY = 1,  /* goodRayFilter(max_range); the OccupancyMap default, range 1e10 */
-  OHMB200_FILTER_CLIP_RANGE = 2 /* clipRayFilter(max_length): clip + kRffClippedEnd               */
+  OHMB200_FILTER_CLIP_RANGE = 2, /* clipRayFilter(max_length): clip + kRffClippedEnd              */
+  OHMB200_FILTER_CLIP_BOX = 3    /* clipBounded(Aabb clip_box) (ohm/RayFilter.cpp:57-76)           */
 };
 
 /* RayFlag — ohm/RayFlag.h:16-60 (same bit values). */
@@ -101,6 +102,7 @@ typedef struct ohmb200_params
   uint32_t layers;          /* bitset of (1u << OHMB200_LAYER_*) */
   int32_t filter_kind;      /* ohmb200_filter */
   double filter_range;      /* max_range / max_length for the filter */
+  double clip_box[6];       /* OHMB200_FILTER_CLIP_BOX: min xyz, max xyz */
   float sensor_noise;       /* NDT */
   float adaptation_rate;
   float reinit_threshold;

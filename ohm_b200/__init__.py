@@ -8,5 +8,5 @@ from .gpumap import (  # noqa: F401
     LAYER_INTENSITY, LAYER_HIT_MISS, LAYER_TSDF,
     RF_DEFAULT, RF_END_POINT_AS_FREE, RF_STOP_ON_FIRST_OCCUPIED, RF_EXCLUDE_ORIGIN, RF_EXCLUDE_SAMPLE,
     RF_EXCLUDE_RAY, RF_EXCLUDE_UNOBSERVED, RF_EXCLUDE_FREE, RF_EXCLUDE_OCCUPIED, RF_REVERSE_WALK,
-    FILTER_NONE, FILTER_GOOD_RAY, FILTER_CLIP_RANGE,
+    FILTER_NONE, FILTER_GOOD_RAY, FILTER_CLIP_RANGE, FILTER_CLIP_BOX,
 )

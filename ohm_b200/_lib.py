@@ -27,6 +27,7 @@ class Params(C.Structure):
         ("layers", C.c_uint32),
         ("filter_kind", C.c_int32),
         ("filter_range", C.c_double),
+        ("clip_box", C.c_double * 6),
         ("sensor_noise", C.c_float),
         ("adaptation_rate", C.c_float),
         ("reinit_threshold", C.c_float),

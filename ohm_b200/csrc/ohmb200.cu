@@ -657,6 +657,7 @@ void refreshParams(ohmb200_map *m)
   mp.sat_max = p.saturate_max ? p.max_value : 3.402823466e+38f;
   mp.filter_kind = p.filter_kind;
   mp.filter_range = p.filter_range;
+  memcpy(mp.clip_box, p.clip_box, sizeof(mp.clip_box));
   mp.sensor_noise = p.sensor_noise;
   mp.adaptation_rate = p.adaptation_rate;
   mp.reinit_threshold = p.reinit_threshold;

@@ -44,6 +44,7 @@ struct MapParams
   float sat_min, sat_max;  // lowest()/max() when saturation is disabled (RayMapperOccupancy.cpp:94-95)
   int filter_kind;
   double filter_range;
+  double clip_box[6];
   float sensor_noise, adaptation_rate, reinit_threshold, initial_intensity_cov;
   uint32_t reinit_count, sample_threshold;
   int ndt_tm;
@@ -225,6 +226,79 @@ OHMB200_HD inline bool applyRayFilter(const MapParams &p, double start[3], doubl
   for (int a = 0; a < 3; ++a)
   {
     good = good && !isnan(start[a]) && !isinf(start[a]) && !isnan(end[a]) && !isinf(end[a]);
+  }
+  if (p.filter_kind == 3)
+  {
+    // clipBounded (RayFilter.cpp:57-76) -> Aabb::clipLine / rayIntersect / contains (Aabb.h:309-450).
+    // No NaN/inf screening here, exactly like the reference filter.
+    const double *lo = p.clip_box, *hi = p.clip_box + 3;
+    const double origin[3] = { start[0], start[1], start[2] };
+    double dir[3] = { end[0] - start[0], end[1] - start[1], end[2] - start[2] };
+    const double d2 = (dir[0] * dir[0] + dir[1] * dir[1]) + dir[2] * dir[2];
+    unsigned clip = 0;
+    if (!(d2 < 1e-9))
+    {
+      const double length = sqrt(d2);
+      double inv[3];
+      bool sign[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+      {
+        dir[a] /= length;
+        inv[a] = 1.0 / dir[a];
+        sign[a] = dir[a] < 0.0;
+      }
+      double t0 = ((sign[0] ? hi[0] : lo[0]) - origin[0]) * inv[0];
+      double t1 = ((sign[0] ? lo[0] : hi[0]) - origin[0]) * inv[0];
+      double tmin = ((sign[1] ? hi[1] : lo[1]) - origin[1]) * inv[1];
+      double tmax = ((sign[1] ? lo[1] : hi[1]) - origin[1]) * inv[1];
+      bool miss = (t0 > tmax) || (tmin > t1);
+      t0 = (tmin > t0 || isnan(t0)) ? tmin : t0;
+      t1 = (tmax < t1 || isnan(t1)) ? tmax : t1;
+      tmin = ((sign[2] ? hi[2] : lo[2]) - origin[2]) * inv[2];
+      tmax = ((sign[2] ? lo[2] : hi[2]) - origin[2]) * inv[2];
+      miss = miss || (t0 > tmax) || (tmin > t1);
+      t0 = (tmin > t0 || isnan(t0)) ? tmin : t0;
+      t1 = (tmax < t1 || isnan(t1)) ? tmax : t1;
+      if (!miss)
+      {
+        if (t0 > 0 && t0 < length)
+        {
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+          {
+            start[a] = origin[a] + dir[a] * t0;
+          }
+          clip |= 1u;
+        }
+        if (t1 > 0 && t1 < length)
+        {
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+          {
+            end[a] = origin[a] + dir[a] * t1;
+          }
+          clip |= 2u;
+        }
+      }
+    }
+    if (clip)
+    {
+      bool s_in = true, e_in = true;
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+      {
+        s_in = s_in && !(hi[a] < start[a]) && !(lo[a] > start[a]);
+        e_in = e_in && !(hi[a] < end[a]) && !(lo[a] > end[a]);
+      }
+      if (!s_in && !e_in)
+      {
+        return false;
+      }
+    }
+    filter_flags |= (clip & 1u) ? kRffClippedStart : 0u;
+    filter_flags |= (clip & 2u) ? kRffClippedEnd : 0u;
+    return true;
   }
   double ray[3] = { end[0] - start[0], end[1] - start[1], end[2] - start[2] };
   const double len2 = (ray[0] * ray[0] + ray[1] * ray[1]) + ray[2] * ray[2];

@@ -31,7 +31,7 @@ LAYER_DTYPES = {
 }
 MODE_OCCUPANCY, MODE_NDT, MODE_NDT_TM, MODE_TSDF = 0, 1, 2, 3
 MODES = {"occupancy": MODE_OCCUPANCY, "ndt": MODE_NDT, "ndt_tm": MODE_NDT_TM, "tsdf": MODE_TSDF}
-FILTER_NONE, FILTER_GOOD_RAY, FILTER_CLIP_RANGE = 0, 1, 2
+FILTER_NONE, FILTER_GOOD_RAY, FILTER_CLIP_RANGE, FILTER_CLIP_BOX = 0, 1, 2, 3
 
 # ohm/RayFlag.h:16-60
 RF_DEFAULT = 0
@@ -63,9 +63,9 @@ def default_params(resolution, **overrides):
 
 def apply_overrides(p, overrides):
     for k, v in overrides.items():
-        if k in ("region_dim", "origin"):
+        if k in ("region_dim", "origin", "clip_box"):
             arr = getattr(p, k)
-            for i in range(3):
+            for i in range(len(v)):
                 arr[i] = v[i]
         elif k == "layers" and not isinstance(v, int):
             bits = 0

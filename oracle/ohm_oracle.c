@@ -604,6 +604,75 @@ static int apply_filter(const oracle_map *m, double start[3], double end[3], uns
     }
     return good;
   }
+  case ORC_FILTER_CLIP_BOX: {
+    /* clipBounded (RayFilter.cpp:57-76) -> Aabb::clipLine / rayIntersect / contains (Aabb.h:309-450) */
+    const double *lo = m->p.clip_box, *hi = m->p.clip_box + 3;
+    const double origin[3] = { start[0], start[1], start[2] };
+    double dir[3] = { end[0] - start[0], end[1] - start[1], end[2] - start[2] };
+    unsigned clip = 0;
+    int clipped = 0;
+    if (!(dot3(dir, dir) < 1e-9))
+    {
+      const double length = sqrt(dot3(dir, dir));
+      double inv[3], t0, t1, tmin, tmax;
+      int sign[3], miss;
+      for (int a = 0; a < 3; ++a)
+      {
+        dir[a] /= length;
+        inv[a] = 1.0 / dir[a];
+        sign[a] = dir[a] < 0.0;
+      }
+      t0 = ((sign[0] ? hi[0] : lo[0]) - origin[0]) * inv[0];
+      t1 = ((sign[0] ? lo[0] : hi[0]) - origin[0]) * inv[0];
+      tmin = ((sign[1] ? hi[1] : lo[1]) - origin[1]) * inv[1];
+      tmax = ((sign[1] ? lo[1] : hi[1]) - origin[1]) * inv[1];
+      miss = (t0 > tmax) + (tmin > t1);
+      t0 = (tmin > t0 || isnan(t0)) ? tmin : t0;
+      t1 = (tmax < t1 || isnan(t1)) ? tmax : t1;
+      tmin = ((sign[2] ? hi[2] : lo[2]) - origin[2]) * inv[2];
+      tmax = ((sign[2] ? lo[2] : hi[2]) - origin[2]) * inv[2];
+      miss = !!((t0 > tmax) + (tmin > t1) + !!miss);
+      t0 = (tmin > t0 || isnan(t0)) ? tmin : t0;
+      t1 = (tmax < t1 || isnan(t1)) ? tmax : t1;
+      if (!miss)
+      {
+        if (t0 > 0 && t0 < length)
+        {
+          for (int a = 0; a < 3; ++a)
+          {
+            start[a] = origin[a] + dir[a] * t0;
+          }
+          clip |= 1u;
+          ++clipped;
+        }
+        if (t1 > 0 && t1 < length)
+        {
+          for (int a = 0; a < 3; ++a)
+          {
+            end[a] = origin[a] + dir[a] * t1;
+          }
+          clip |= 2u;
+          ++clipped;
+        }
+      }
+    }
+    if (clipped)
+    {
+      int s_in = 1, e_in = 1;
+      for (int a = 0; a < 3; ++a)
+      {
+        s_in = s_in && !(hi[a] < start[a]) && !(lo[a] > start[a]);
+        e_in = e_in && !(hi[a] < end[a]) && !(lo[a] > end[a]);
+      }
+      if (!s_in && !e_in)
+      {
+        return 0;
+      }
+    }
+    *filter_flags |= (clip & 1u) ? RFF_CLIPPED_START : 0u;
+    *filter_flags |= (clip & 2u) ? RFF_CLIPPED_END : 0u;
+    return 1;
+  }
   case ORC_FILTER_CLIP_RANGE: {
     const int good = vec_finite(start) && vec_finite(end);
     double ray[3] = { end[0] - start[0], end[1] - start[1], end[2] - start[2] };

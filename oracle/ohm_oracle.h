@@ -43,7 +43,8 @@ enum
 {
   ORC_FILTER_NONE = 0,
   ORC_FILTER_GOOD_RAY = 1,  /* goodRayFilter(max_range)  — the OccupancyMap default with 1e10 */
-  ORC_FILTER_CLIP_RANGE = 2 /* clipRayFilter(max_length) */
+  ORC_FILTER_CLIP_RANGE = 2, /* clipRayFilter(max_length) */
+  ORC_FILTER_CLIP_BOX = 3    /* clipBounded(clip_box) (RayFilter.cpp:57-76, Aabb.h:330-450) */
 };
 
 typedef struct oracle_params
@@ -61,6 +62,7 @@ typedef struct oracle_params
   uint32_t layers; /* bitset of (1u << ORC_LAYER_*) */
   int32_t filter_kind;
   double filter_range;
+  double clip_box[6]; /* ORC_FILTER_CLIP_BOX: min xyz, max xyz */
   /* NDT: ohm/private/NdtMapDetail.h:24-40 */
   float sensor_noise;
   float adaptation_rate;

@@ -25,7 +25,7 @@ LAYER_DTYPES = {
     LAYER_HIT_MISS: (np.uint32, 2),
     LAYER_TSDF: (np.float32, 2),
 }
-FILTER_NONE, FILTER_GOOD_RAY, FILTER_CLIP_RANGE = 0, 1, 2
+FILTER_NONE, FILTER_GOOD_RAY, FILTER_CLIP_RANGE, FILTER_CLIP_BOX = 0, 1, 2, 3
 
 
 class Params(C.Structure):
@@ -43,6 +43,7 @@ class Params(C.Structure):
         ("layers", C.c_uint32),
         ("filter_kind", C.c_int32),
         ("filter_range", C.c_double),
+        ("clip_box", C.c_double * 6),
         ("sensor_noise", C.c_float),
         ("adaptation_rate", C.c_float),
         ("reinit_threshold", C.c_float),
@@ -151,9 +152,9 @@ def default_params(resolution, **overrides):
 
 def apply_overrides(p, overrides):
     for k, v in overrides.items():
-        if k in ("region_dim", "origin"):
+        if k in ("region_dim", "origin", "clip_box"):
             arr = getattr(p, k)
-            for i in range(3):
+            for i in range(len(v)):
                 arr[i] = v[i]
         elif k == "layers" and not isinstance(v, int):
             bits = 0

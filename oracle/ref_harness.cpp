@@ -5,6 +5,7 @@
 // it only calls the reference's public API.
 #include "ohm_oracle.h"
 
+#include <ohm/Aabb.h>
 #include <ohm/DefaultLayer.h>
 #include <ohm/MapChunk.h>
 #include <ohm/MapLayer.h>
@@ -80,6 +81,12 @@ void applyParams(RefMap &r, const oracle_params &p)
   case ORC_FILTER_NONE:
     m.setRayFilter(ohm::RayFilterFunction());
     break;
+  case ORC_FILTER_CLIP_BOX: {
+    const ohm::Aabb box(glm::dvec3(p.clip_box[0], p.clip_box[1], p.clip_box[2]),
+                        glm::dvec3(p.clip_box[3], p.clip_box[4], p.clip_box[5]));
+    m.setRayFilter([box](glm::dvec3 *s, glm::dvec3 *e, unsigned *f) { return ohm::clipBounded(s, e, f, box); });
+    break;
+  }
   case ORC_FILTER_CLIP_RANGE:
     m.setRayFilter([range](glm::dvec3 *s, glm::dvec3 *e, unsigned *f) { return ohm::clipRayFilter(s, e, f, range); });
     break;

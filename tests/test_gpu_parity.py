@@ -248,3 +248,16 @@ def test_region_partition_union_matches_single_map(gpu):
     cs = c.stats()
     assert sum(p.stats()["voxel_visits"] for p in parts) == cs["voxel_visits"]
     assert sum(p.stats()["sample_updates"] for p in parts) == cs["sample_updates"]
+
+
+def test_clip_box_filter(gpu):
+    # GpuMapTest.cpp ClipBox / ClipBoxCompare: clipBounded(Aabb) — rays cut at the box, clipped ends take a miss
+    box = (-3.0, -2.0, -1.5, 4.0, 2.5, 1.0)
+    g, c = make_pair(0.25, filter_kind=gm.FILTER_CLIP_BOX, clip_box=box)
+    rays = random_rays(4096, 9.0, 17)
+    rng = np.random.RandomState(18)
+    rays[0:2000:2] = rng.uniform(-9, 9, size=(1000, 3))
+    rays[10] = rays[11]
+    integrate_both(g, c, rays, batch=1000)
+    compare_maps(g, c)
+    check_counts(g, c)

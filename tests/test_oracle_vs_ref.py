@@ -156,3 +156,17 @@ def test_lidar_sweep_config2():
     o.integrate_rays(rays)
     r.integrate_rays(rays)
     assert assert_identical(o, r) > 1000
+
+
+def test_clip_box_filter():
+    # tests/ohmtestgpu/GpuMapTest.cpp:640-647,762-771 ClipBox: clipBounded against an Aabb
+    box = (-3.0, -2.0, -1.5, 4.0, 2.5, 1.0)
+    kw = dict(filter_kind=po.FILTER_CLIP_BOX, clip_box=box)
+    o, r = po.OracleMap(0.25, **kw), pr.ReferenceMap(0.25, **kw)
+    rays = random_rays(4096, 9.0, 17)
+    rng = np.random.RandomState(18)
+    rays[0:2000:2] = rng.uniform(-9, 9, size=(1000, 3))   # also rays that start outside the box
+    rays[10] = rays[11]                                   # degenerate
+    o.integrate_rays(rays)
+    r.integrate_rays(rays)
+    assert_identical(o, r)
