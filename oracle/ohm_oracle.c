@@ -569,6 +569,37 @@ size_t oracle_walk_segment(const oracle_map *m, const double start[3], const dou
   return c.n;
 }
 
+/* Number of voxels walkSegmentKeys reports for each ray, from the keys alone: 1 + |dx|+|dy|+|dz| minus the excluded
+ * start/end voxels (LineWalkCompute.h:354-410).  An independent check of V for runs too large to walk on the CPU. */
+uint64_t oracle_count_walk_visits(const oracle_map *m, const double *rays, size_t element_count, unsigned walk_flags)
+{
+  uint64_t total = 0;
+  for (size_t i = 0; i + 1 < element_count; i += 2)
+  {
+    int32_t s[6], e[6];
+    if (!oracle_voxel_key(m, rays + 3 * i, s) || !oracle_voxel_key(m, rays + 3 * i + 3, e))
+    {
+      continue;
+    }
+    int64_t steps = 0;
+    for (int a = 0; a < 3; ++a)
+    {
+      const int64_t d = (int64_t)(e[3 + a] - s[3 + a]) + (int64_t)(int16_t)(e[a] - s[a]) * m->p.region_dim[a];
+      steps += d < 0 ? -d : d;
+    }
+    if (steps == 0)
+    {
+      total += (walk_flags & ORC_WALK_EXCLUDE_END) ? 0u : 1u;
+      continue;
+    }
+    int64_t visits = steps + 1;
+    visits -= (walk_flags & ORC_WALK_EXCLUDE_START) ? 1 : 0;
+    visits -= (walk_flags & ORC_WALK_EXCLUDE_END) ? 1 : 0;
+    total += (uint64_t)visits;
+  }
+  return total;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* Ray filters: ohm/RayFilter.cpp:15-55                                                        */
 /* ------------------------------------------------------------------------------------------ */

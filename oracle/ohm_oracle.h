@@ -107,6 +107,9 @@ void oracle_voxel_centre(const oracle_map *m, const int32_t key[6], double centr
 size_t oracle_walk_segment(const oracle_map *m, const double start[3], const double end[3], unsigned walk_flags,
                            int32_t *keys, double *enter, double *exit, size_t cap);
 
+/* Voxels a walk of every ray reports, computed from the start/end keys only (no walking). */
+uint64_t oracle_count_walk_visits(const oracle_map *m, const double *rays, size_t element_count, unsigned walk_flags);
+
 /* RayMapperOccupancy / RayMapperNdt / RayMapperTsdf ::integrateRays. rays = [origin,sample]* as f64 xyz. */
 size_t oracle_integrate_occupancy(oracle_map *m, const double *rays, size_t element_count, const float *intensities,
                                   const double *timestamps, unsigned ray_flags);

@@ -106,6 +106,8 @@ def lib():
         f = getattr(L, name)
         f.argtypes = [vp, dp, C.c_size_t, fp, dp, C.c_uint]
         f.restype = C.c_size_t
+    L.oracle_count_walk_visits.argtypes = [vp, dp, C.c_size_t, C.c_uint]
+    L.oracle_count_walk_visits.restype = C.c_uint64
     L.oracle_region_count.argtypes = [vp]
     L.oracle_region_count.restype = C.c_size_t
     L.oracle_region_keys.argtypes = [vp, C.POINTER(C.c_int16), C.c_size_t]
@@ -208,6 +210,10 @@ class OracleMap:
             "tsdf": self.L.oracle_integrate_tsdf,
         }[self.mode]
         return fn(self.h, _dptr(rays), n, ip, tp, int(ray_flags))
+
+    def count_walk_visits(self, rays, walk_flags=0):
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 3)
+        return int(self.L.oracle_count_walk_visits(self.h, _dptr(rays), rays.shape[0], int(walk_flags)))
 
     def stats(self):
         s = Stats()

@@ -21,18 +21,13 @@ sys.path.insert(0, ROOT)
 
 
 def key_l1_visits(rays, resolution, include_end):
-    """Independent (numpy) count of the voxels a walk visits: 1 + |dx|+|dy|+|dz| per ray, minus the excluded end
-    voxel — from vectorised key maths (ohm/MapCoord.h:37-93), no walking."""
-    start, end = rays[0::2], rays[1::2]
-    region = 32 * resolution
-
-    def keys(p):
-        rc = np.floor(p / region + 0.5)
-        local = np.floor((p - (rc * region - 0.5 * region)) / resolution)
-        return (rc * 32 + local).astype(np.int64)
-
-    l1 = np.abs(keys(end) - keys(start)).sum(axis=1)
-    return int((l1 + (1 if include_end else 0)).sum())
+    """Independent count of the voxels a walk visits — 1 + |dx|+|dy|+|dz| per ray minus the excluded end voxel — from
+    the oracle's key maths alone (ohm/MapCoord.h:37-93, epsilon snaps included); no walking, so it scales to full size."""
+    from oracle import pyoracle as po
+    m = po.OracleMap(resolution)
+    n = m.count_walk_visits(rays, 0 if include_end else 2)
+    m.close()
+    return n
 
 
 def run(mode, resolution, sweeps, cpu_sweeps, device_gib):
