@@ -213,7 +213,7 @@ OHMB200_API int ohmb200_region_owner(const int16_t key_xyz[3], int world);
 
 /* Per-kernel CUDA-event timing on the map's stream (bench.py's roofline numbers).  When enabled every launch is
  * bracketed by events; ohmb200_kernel_times drains {name -> accumulated ms, launches}. */
-#define OHMB200_KERNEL_SLOTS 16
+#define OHMB200_KERNEL_SLOTS 24
 typedef struct ohmb200_kernel_time
 {
   char name[32];

@@ -75,11 +75,12 @@ struct Counters
   uint32_t item_count;
   uint32_t work_next;
   uint32_t segment_overflow;
+  uint32_t gauss_count;  // NDT: reserved Gaussian-visit record slots
   // sticky
   int table_full;
   int overflow_seen;
 };
-constexpr int kPerBatchCounterWords = 8;  // record_count .. segment_overflow
+constexpr int kPerBatchCounterWords = 9;  // record_count .. gauss_count
 
 struct Batch
 {
@@ -114,6 +115,8 @@ struct Batch
   uint32_t seg_capacity;
   WorkItem *items;         // (region, segment range) work list
   uint32_t item_capacity;
+  unsigned long long *gauss_keys;          // NDT: (voxel id << 32 | ray) of visits to voxels with an established Gaussian
+  uint32_t gauss_capacity;
   unsigned long long *record_keys;         // TSDF: (voxel id << 32 | ray) of every visit that must be replayed in order
   unsigned long long *record_keys_sorted;
   Counters *counters;
@@ -506,12 +509,15 @@ enum KernelId
   kKLink,
   kKTsdfMark,
   kKTsdfReplay,
+  kKNdtGauss,
+  kKNdtClamp,
   kKernelCount
 };
 static const char *kKernelNames[kKernelCount] = { "prepSamples",  "radixSort",     "markRuns",      "walkRays",
                                                   "applySamples", "resolveMisses", "gatherRegions", "fillFloat",
                                                   "prepRays",     "planRegions",   "emitSegments",  "walkRegions",
-                                                  "linkRecords",  "walkRegionsTsdf<mark>", "replayTsdf" };
+                                                  "linkRecords",  "walkRegionsTsdf<mark>", "replayTsdf",
+                                                  "ndtGaussianMisses", "ndtClampGaussians" };
 static_assert(kKernelCount <= OHMB200_KERNEL_SLOTS, "raise OHMB200_KERNEL_SLOTS");
 
 struct ohmb200_map
@@ -766,6 +772,12 @@ int ensureScratch(ohmb200_map *m, size_t n)
     rc |= deviceAlloc(b.segments, b.seg_capacity);
     b.item_capacity = m->dm.capacity + b.seg_capacity / kMaxSegmentsPerItem + 16;
     rc |= deviceAlloc(b.items, b.item_capacity);
+    if (m->mode == OHMB200_MODE_NDT || m->mode == OHMB200_MODE_NDT_TM)
+    {
+      cudaFree(b.gauss_keys);
+      b.gauss_capacity = (uint32_t)std::min<size_t>(std::max<size_t>(cap * 16, 1u << 20), 1u << 28);
+      rc |= deviceAlloc(b.gauss_keys, b.gauss_capacity);
+    }
     if (m->mode == OHMB200_MODE_TSDF)
     {
       cudaFree(b.record_keys);
@@ -910,12 +922,24 @@ int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_i
       KernelScope scope(m, kKWalkRegions);
       if ((m->mode == OHMB200_MODE_NDT || m->mode == OHMB200_MODE_NDT_TM))
       {
+        CUDA_TRY(cudaMemsetAsync(b.gauss_keys, 0xFF, sizeof(unsigned long long) * b.gauss_capacity, s));
         walkRegionsNdt<<<m->sm_count * m->walk_ctas_per_sm, kWalkThreads, m->tile_bytes, s>>>(m->dm, m->geom, m->mp, b);
       }
       else
       {
         walkRegions<<<m->sm_count * m->walk_ctas_per_sm, kWalkThreads, m->tile_bytes, s>>>(m->dm, m->geom, m->mp, b,
                                                                                         has_samples ? 1 : 0);
+      }
+    }
+    if (m->mode == OHMB200_MODE_NDT || m->mode == OHMB200_MODE_NDT_TM)
+    {
+      {
+        KernelScope scope(m, kKNdtGauss);
+        ndtGaussianMisses<<<m->sm_count * 8, 128, 0, s>>>(m->dm, m->geom, m->mp, b);
+      }
+      {
+        KernelScope scope(m, kKNdtClamp);
+        ndtClampGaussians<<<m->sm_count * 4, 256, 0, s>>>(m->dm, m->mp, b);
       }
     }
     if (has_samples)
@@ -1296,7 +1320,7 @@ void ohmb200_destroy(ohmb200_map *m)
                       b.last_exit,      m->cub_temp,        m->d_rays[0],       m->d_rays[1],     m->d_intensities[0],
                       m->d_intensities[1], m->d_timestamps[0], m->d_timestamps[1], m->d_gather,    m->d_gather_slots,
                       b.recs,           b.ray_length,       b.record_vid,       b.seg_count,      b.seg_offset,
-                      b.seg_cursor,     b.segments,         b.items,            b.record_keys,    b.record_keys_sorted,
+                      b.seg_cursor,     b.segments,         b.items,            b.record_keys,    b.record_keys_sorted, b.gauss_keys,
                       m->tsdf_flags };
   for (void *p : to_free)
   {

@@ -121,8 +121,9 @@ __global__ void __launch_bounds__(128) prepRays(DeviceMap dm, Geom g, MapParams 
     if (rec.flags & kRecValid)
     {
       // Pass A: count this ray's segments per region (creating regions as they are first entered).
-      enumerateSegments(rec, g, [&](const int r[3], const int st[3], int n) {
+      enumerateSegments(rec, g, [&](const int r[3], const int st[3], const int entry[3], int n) {
         (void)st;
+        (void)entry;
         if (!ownsRegion(dm, r))
         {
           return;
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(128) emitSegments(DeviceMap dm, Geom g, Batch 
   {
     return;
   }
-  enumerateSegments(rec, g, [&](const int r[3], const int st[3], int n) {
+  enumerateSegments(rec, g, [&](const int r[3], const int st[3], const int entry[3], int n) {
     if (!ownsRegion(dm, r))
     {
       return;
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(128) emitSegments(DeviceMap dm, Geom g, Batch 
       raw.x = i;
       raw.y = (uint32_t)st[0] | ((uint32_t)st[1] << 16);
       raw.z = (uint32_t)st[2] | ((uint32_t)n << 16);
-      raw.w = 0;
+      raw.w = (uint32_t)entry[0] | ((uint32_t)entry[1] << 8) | ((uint32_t)entry[2] << 16);
       reinterpret_cast<uint4 *>(b.segments)[at] = raw;
     }
   });
@@ -394,6 +395,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegions(DeviceMap dm, Geo
       const uint32_t ray = raw.x;
       const int st[3] = { (int)(raw.y & 0xffffu), (int)(raw.y >> 16), (int)(raw.z & 0xffffu) };
       const int visits = (int)(raw.z >> 16);
+      const int entry[3] = { (int)(raw.w & 0xffu), (int)((raw.w >> 8) & 0xffu), (int)((raw.w >> 16) & 0xffu) };
       const RayRec *rp = b.recs + ray;
       // tail of the record: region[3] i16 | local[3] u8 | flags u8 | total[3] u16
       const uint4 tail = reinterpret_cast<const uint4 *>(rp)[3];
@@ -455,7 +457,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegions(DeviceMap dm, Geo
       }
       else
       {
-        resumeSegmentFast(init, delta, local0, total, flags, st, visits, g, count_visit);
+        resumeSegmentFast(init, delta, entry, total, flags, st, visits, g, count_visit);
       }
     }
     __syncthreads();
@@ -551,44 +553,74 @@ __global__ void linkRecords(Batch b)
 // NDT (GpuNdtMap, NdtMode::kOccupancy): RayMapperNdt.cpp:84-407
 // ---------------------------------------------------------------------------------------------------------
 
-// NDT miss adjustment of one visit to a voxel with an established Gaussian, added straight to the occupancy slab.
-// Such a voxel receives no sample in this batch (it would be flagged), so its mean/covariance are constant for the
-// whole batch; the adjustments are <= 0, and sum-then-clamp equals the sequential clamp-each-time.
-__device__ __noinline__ void ndtVisit(const DeviceMap &dm, const Geom &g, const MapParams &mp, const Batch &b, uint32_t ray,
-                                uint32_t slot, uint32_t idx)
+// Visits to voxels with an established Gaussian (mean count >= sample threshold, no sample in this batch) are not
+// evaluated inside the walk — a lane doing ~600 fp64 instructions would stall its whole warp — but recorded as
+// (voxel << 32 | ray) and evaluated one thread per record: ndtGaussianMisses adds the NDT term to the occupancy slab,
+// ndtClampGaussians then applies occupancyAdjustDown's clamp.  Such a voxel's mean/covariance are constant for the
+// whole batch, the terms are <= 0, and sum-then-clamp equals the sequential clamp-each-time.
+__global__ void __launch_bounds__(128) ndtGaussianMisses(DeviceMap dm, Geom g, MapParams mp, Batch b)
 {
-  double sensor[3], sample[3];
-  loadRay(b, ray, sensor, sample);
-  unsigned filter_flags = 0;
-  applyRayFilter(mp, sensor, sample, filter_flags);  // the mapper hands calculateMissNdt the filtered points
-  const uint32_t vid = slot * g.vpr + idx;
-  int r[3];
-  unpackRegion(dm.keys[slot], r);
-  const int l[3] = { (int)(idx % (uint32_t)g.dim[0]), (int)((idx / (uint32_t)g.dim[0]) % (uint32_t)g.dim[1]),
-                     (int)(idx / ((uint32_t)g.dim[0] * (uint32_t)g.dim[1])) };
-  const uint2 vm = dm.mean[vid];
-  double mean[3];
-  subVoxelToLocal(vm.x, g.res, mean);
-  float cov[6];
+  const uint32_t count = min(b.counters->gauss_count, b.gauss_capacity);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+  {
+    const unsigned long long key = b.gauss_keys[i];
+    const uint32_t vid = (uint32_t)(key >> 32);
+    if (vid == kInvalidVoxel)
+    {
+      continue;
+    }
+    const uint32_t ray = (uint32_t)key;
+    double sensor[3], sample[3];
+    loadRay(b, ray, sensor, sample);
+    unsigned filter_flags = 0;
+    applyRayFilter(mp, sensor, sample, filter_flags);  // the mapper hands calculateMissNdt the filtered points
+    const uint32_t slot = vid / g.vpr;
+    const uint32_t idx = vid - slot * g.vpr;
+    int r[3];
+    unpackRegion(dm.keys[slot], r);
+    const int l[3] = { (int)(idx % (uint32_t)g.dim[0]), (int)((idx / (uint32_t)g.dim[0]) % (uint32_t)g.dim[1]),
+                       (int)(idx / ((uint32_t)g.dim[0] * (uint32_t)g.dim[1])) };
+    const uint2 vm = dm.mean[vid];
+    double mean[3];
+    subVoxelToLocal(vm.x, g.res, mean);
+    float cov[6];
 #pragma unroll
-  for (int a = 0; a < 3; ++a)
-  {
-    mean[a] += voxelCentreAxis(g, r[a], l[a], a);
-  }
+    for (int a = 0; a < 3; ++a)
+    {
+      mean[a] += voxelCentreAxis(g, r[a], l[a], a);
+    }
 #pragma unroll
-  for (int k = 0; k < 6; ++k)
-  {
-    cov[k] = dm.covariance[(size_t)vid * 6 + k];
+    for (int k = 0; k < 6; ++k)
+    {
+      cov[k] = dm.covariance[(size_t)vid * 6 + k];
+    }
+    bool valid, is_miss;
+    const float adj = ndtMissAdjustment(cov, sensor, sample, mean, mp.adaptation_rate, mp.sensor_noise, valid, is_miss);
+    if (valid && adj != 0.0f)
+    {
+      atomicAdd(&dm.occupancy[vid], adj);
+    }
+    if (dm.hit_miss && is_miss)
+    {
+      atomicAdd(&dm.hit_miss[vid].y, 1u);  // NDT-TM miss count (RayMapperNdt.cpp:203-209)
+    }
   }
-  bool valid, is_miss;
-  const float adj = ndtMissAdjustment(cov, sensor, sample, mean, mp.adaptation_rate, mp.sensor_noise, valid, is_miss);
-  if (valid && adj != 0.0f)
+}
+
+__global__ void __launch_bounds__(256) ndtClampGaussians(DeviceMap dm, MapParams mp, Batch b)
+{
+  const uint32_t count = min(b.counters->gauss_count, b.gauss_capacity);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
   {
-    atomicAdd(&dm.occupancy[vid], adj);
-  }
-  if (dm.hit_miss && is_miss)
-  {
-    atomicAdd(&dm.hit_miss[vid].y, 1u);  // NDT-TM miss count (RayMapperNdt.cpp:203-209)
+    const uint32_t vid = (uint32_t)(b.gauss_keys[i] >> 32);
+    if (vid != kInvalidVoxel)
+    {
+      const float v = dm.occupancy[vid];
+      if (v < mp.min_value)
+      {
+        dm.occupancy[vid] = mp.min_value;  // every writer of this voxel stores the same value
+      }
+    }
   }
 }
 
@@ -601,6 +633,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsNdt(const __grid_c
   __shared__ WorkItem item;
   __shared__ uint32_t sample_range[2];
   __shared__ unsigned long long record_chunk[kWalkThreads / 32];
+  __shared__ unsigned long long gauss_chunk[kWalkThreads / 32];
   const uint32_t words = (g.vpr + 1u) >> 1;
   const uint32_t kind_words = (g.vpr + 31u) >> 5;
   uint32_t *kind = tile + ((words + 3u) & ~3u);
@@ -609,6 +642,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsNdt(const __grid_c
   if ((tid & 31u) == 0)
   {
     record_chunk[warp] = (unsigned long long)kRecordChunk;
+    gauss_chunk[warp] = (unsigned long long)kRecordChunk;
   }
   for (;;)
   {
@@ -665,6 +699,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsNdt(const __grid_c
       const uint32_t ray = raw.x;
       const int st[3] = { (int)(raw.y & 0xffffu), (int)(raw.y >> 16), (int)(raw.z & 0xffffu) };
       const int visits = (int)(raw.z >> 16);
+      const int entry[3] = { (int)(raw.w & 0xffu), (int)((raw.w >> 8) & 0xffu), (int)((raw.w >> 16) & 0xffu) };
       const RayRec *rp = b.recs + ray;
       const uint4 tail = reinterpret_cast<const uint4 *>(rp)[3];
       const uint32_t flags = (tail.z >> 8) & 0xffu;
@@ -709,7 +744,35 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsNdt(const __grid_c
         }
         else if ((kind[idx >> 5] >> (idx & 31u)) & 1u)
         {
-          ndtVisit(dm, g, mp, b, ray, slot, idx);
+          // Established Gaussian: evaluated later, one thread per visit (ndtGaussianMisses).
+          const unsigned group = __activemask();
+          const uint32_t n = (uint32_t)__popc(group);
+          const uint32_t rank = (uint32_t)__popc(group & ((1u << (tid & 31u)) - 1u));
+          uint32_t at = 0;
+          if (rank == 0)
+          {
+            const unsigned long long state = atomicAdd(&gauss_chunk[warp], (unsigned long long)n);
+            const uint32_t used = (uint32_t)state;
+            if (used + n <= kRecordChunk)
+            {
+              at = (uint32_t)(state >> 32) + used;
+            }
+            else
+            {
+              at = atomicAdd(&b.counters->gauss_count, kRecordChunk);
+              atomicExch(&gauss_chunk[warp], ((unsigned long long)at << 32) | n);
+            }
+          }
+          at = __shfl_sync(group, at, __ffs(group) - 1) + rank;
+          if (at < b.gauss_capacity)
+          {
+            b.gauss_keys[at] = ((unsigned long long)(vbase + idx) << 32) | ray;
+          }
+          else
+          {
+            b.counters->record_overflow = 1;
+            b.counters->overflow_seen = 1;
+          }
         }
       };
       if (dm.traversal)
@@ -728,7 +791,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsNdt(const __grid_c
       }
       else
       {
-        resumeSegmentFast(init, delta, local0, total, flags, st, visits, g, count_visit);
+        resumeSegmentFast(init, delta, entry, total, flags, st, visits, g, count_visit);
       }
     }
     __syncthreads();
@@ -743,8 +806,12 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsNdt(const __grid_c
       {
         continue;
       }
-      const bool gaussian = (kind[v >> 5] >> (v & 31u)) & 1u;
-      if (dm.hit_miss && !gaussian)
+      if ((kind[v >> 5] >> (v & 31u)) & 1u)
+      {
+        continue;  // Gaussian voxel: handled by ndtGaussianMisses / ndtClampGaussians
+      }
+      const bool gaussian = false;
+      if (dm.hit_miss)
       {
         atomicAdd(&dm.hit_miss[vbase + v].y, half);  // every plain NDT miss counts as a miss
       }
@@ -756,6 +823,11 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsNdt(const __grid_c
         const float next = gaussian ? fmaxf(mp.min_value, cur) : missRepeat(cur, half, mp, 0u);
         if (__float_as_int(next) == seen)
         {
+          break;
+        }
+        if (!item.shared)
+        {
+          occ[v] = next;  // this CTA is the only writer of the region in this batch
           break;
         }
         const int prev = atomicCAS(addr, seen, __float_as_int(next));
@@ -801,14 +873,17 @@ __global__ void __launch_bounds__(128) applySamplesNdt(DeviceMap dm, Geom g, Map
           hi = mid;
         }
       }
-      b.record_vid[rec] = lo;  // interval of this record (the voxel id is no longer needed)
+      // Re-thread the record onto the chain of its interval (head kept in interval_count[], -1 based; the tail
+      // interval's head in a register).  record_vid[] becomes the per-interval "next" link.
       if (lo < k)
       {
-        ++b.interval_count[head + lo];
+        b.record_vid[rec] = b.interval_count[head + lo];
+        b.interval_count[head + lo] = (uint32_t)rec + 1u;
       }
       else
       {
-        ++tail;
+        b.record_vid[rec] = tail;
+        tail = (uint32_t)rec + 1u;
       }
       ++ordered;
     }
@@ -843,8 +918,8 @@ __global__ void __launch_bounds__(128) applySamplesNdt(DeviceMap dm, Geom g, Map
     float2 im = ndt_tm ? dm.intensity[vid] : make_float2(0, 0);
     for (uint32_t j = 0; j <= k; ++j)
     {
-      const uint32_t misses = (j < k) ? b.interval_count[head + j] : tail;
-      if (misses)
+      const uint32_t chain = (j < k) ? b.interval_count[head + j] : tail;  // 1-based record index, 0 = none
+      if (chain)
       {
         double mean[3];
         subVoxelToLocal(vm.x, g.res, mean);
@@ -853,14 +928,9 @@ __global__ void __launch_bounds__(128) applySamplesNdt(DeviceMap dm, Geom g, Map
         {
           mean[a] += centre[a];
         }
-        uint32_t found = 0;
-        for (int32_t rec = b.run_head[head]; rec >= 0 && found < misses; rec = b.record_next[rec])
+        for (uint32_t link = chain; link != 0; link = b.record_vid[link - 1u])
         {
-          if (b.record_vid[rec] != j)
-          {
-            continue;
-          }
-          ++found;
+          const uint32_t rec = link - 1u;
           double sensor[3], sample[3];
           loadRay(b, b.record_ray[rec], sensor, sample);
           unsigned filter_flags = 0;

@@ -38,7 +38,7 @@ struct Segment
   uint32_t ray;
   uint16_t stepped[3];  // per-axis steps already taken when the segment starts
   uint16_t visits;      // voxels to visit
-  uint32_t pad;
+  uint32_t entry;       // local voxel coordinates of the first voxel: x | y << 8 | z << 16
 };
 static_assert(sizeof(Segment) == 16, "Segment must be 16 bytes");
 
@@ -94,7 +94,7 @@ OHMB200_HD inline bool makeRayRec(RayRec &rec, const Geom &g, const double start
   return ok;
 }
 
-// Enumerate the per-region segments of a ray in walk order.  emit(region[3], stepped[3], visits).
+// Enumerate the per-region segments of a ray in walk order.  emit(region[3], stepped[3], entry_local[3], visits).
 template <typename Emit>
 OHMB200_HD inline void enumerateSegments(const RayRec &rec, const Geom &g, Emit &&emit)
 {
@@ -118,7 +118,7 @@ OHMB200_HD inline void enumerateSegments(const RayRec &rec, const Geom &g, Emit 
     // start and end share a voxel: only the end-voxel visit can happen (LineWalkCompute.h:392-410)
     if (!exclude_end)
     {
-      emit(r, st, 1);
+      emit(r, st, l, 1);
     }
     return;
   }
@@ -179,7 +179,7 @@ OHMB200_HD inline void enumerateSegments(const RayRec &rec, const Geom &g, Emit 
     }
     if (ca < 0)
     {
-      emit(r, st, q_last - q + 1);  // the ray ends inside this region
+      emit(r, st, l, q_last - q + 1);  // the ray ends inside this region
       return;
     }
     // Steps of the other axes that precede the crossing step.
@@ -226,7 +226,7 @@ OHMB200_HD inline void enumerateSegments(const RayRec &rec, const Geom &g, Emit 
     const int n = min(q_exit - 1, q_last) - q + 1;
     if (n > 0)
     {
-      emit(r, st, n);
+      emit(r, st, l, n);
     }
     if (q_exit > q_last)
     {
@@ -311,20 +311,15 @@ OHMB200_HD inline void resumeSegment(const double init[3], const double delta[3]
 // counters (no int->double conversion in the loop) and a branch per stepped axis instead of predicating all three.
 // visit(idx) receives the voxel index inside the region.  Same arithmetic, same order of comparisons.
 template <typename Visit>
-OHMB200_HD __forceinline__ void resumeSegmentFast(const double init[3], const double delta[3], const int local0[3],
+OHMB200_HD __forceinline__ void resumeSegmentFast(const double init[3], const double delta[3], const int entry[3],
                                                   const int total[3], uint32_t flags, const int st_in[3], int visits,
                                                   const Geom &g, Visit &&visit)
 {
+  // entry = local voxel coordinates at which the segment starts (the producer stores them with the segment)
   int s0 = st_in[0], s1 = st_in[1], s2 = st_in[2];
   const int d0 = (flags & 1u) ? -1 : 1, d1 = (flags & 2u) ? -1 : 1, d2 = (flags & 4u) ? -1 : 1;
-  int p0 = (local0[0] + d0 * s0) % g.dim[0];
-  int p1 = (local0[1] + d1 * s1) % g.dim[1];
-  int p2 = (local0[2] + d2 * s2) % g.dim[2];
-  p0 += (p0 < 0) ? g.dim[0] : 0;
-  p1 += (p1 < 0) ? g.dim[1] : 0;
-  p2 += (p2 < 0) ? g.dim[2] : 0;
   const int stride1 = g.dim[0], stride2 = g.dim[0] * g.dim[1];
-  int idx = p0 + p1 * stride1 + p2 * stride2;
+  int idx = entry[0] + entry[1] * stride1 + entry[2] * stride2;
   const int step0 = d0, step1 = d1 * stride1, step2 = d2 * stride2;
   double m0 = (double)s0, m1 = (double)s1, m2 = (double)s2;
   double t0 = (s0 < total[0]) ? (s0 == 0 ? init[0] : init[0] + delta[0] * m0) : (double)INFINITY;

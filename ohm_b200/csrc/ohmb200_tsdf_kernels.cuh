@@ -44,6 +44,17 @@ __device__ __forceinline__ float tsdfFarThreshold(const MapParams &p)
   return p.tsdf_trunc * (1.0f + 8.0f * 5.9604645e-8f * (p.tsdf_max_weight + 2.0f));
 }
 
+// A voxel `k` steps before the end of a walk has sdf >= res * sqrt((k/sqrt3 - sqrt3/2)^2 - 3/4): its key is k
+// axis-steps from the end key (L2 >= L1/sqrt3), the end voxel's centre is within a half diagonal of the (filtered) end
+// point, the ray passes through the voxel (perpendicular offset <= half diagonal), and the unfiltered sample lies on
+// the ray at or beyond the filtered end.  Voxels further than this many steps from the end are far for certain, so the
+// mark pass never has to look at them (+2 steps of slack for the float evaluation of sdf).
+__device__ __forceinline__ int tsdfNearSteps(const MapParams &p, const Geom &g)
+{
+  const double ratio = (double)tsdfFarThreshold(p) / g.res;
+  return (int)ceil(1.7320508075688772 * (sqrt(ratio * ratio + 0.75) + 0.8660254037844386)) + 2;
+}
+
 // Stored state for which far visits commute.
 __device__ __forceinline__ bool tsdfOrderFree(float2 v, const MapParams &p)
 {
@@ -81,6 +92,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsTsdf(const __grid_
   const uint32_t warp = tid >> 5;
   const float far_threshold = tsdfFarThreshold(mp);
   const bool all_ordered = mp.tsdf_dropoff > 0;  // weights depend on sdf: nothing commutes
+  const int near_steps = tsdfNearSteps(mp, g);
   if ((tid & 31u) == 0)
   {
     record_chunk[warp] = (unsigned long long)kRecordChunk;
@@ -153,57 +165,74 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsTsdf(const __grid_
       const double init[3] = { rp->initial[0], rp->initial[1], rp->initial[2] };
       const double delta[3] = { rp->delta[0], rp->delta[1], rp->delta[2] };
       const int dx = g.dim[0], dxy = g.dim[0] * g.dim[1];
-      TsdfRayGeometry geo;
-      tsdfLoadRay(b, ray, geo);
-      resumeSegment<false>(init, delta, local0, total, rflags, st, visits, 0.0, g,
-                           [&](const int l[3], double, double, bool) {
-                             const uint32_t idx = (uint32_t)(l[0] + l[1] * dx + l[2] * dxy);
-                             if (!kCount)
-                             {
-                               const double centre[3] = { voxelCentreAxis(g, region[0], l[0], 0),
-                                                          voxelCentreAxis(g, region[1], l[1], 1),
-                                                          voxelCentreAxis(g, region[2], l[2], 2) };
-                               const float sdf = tsdfDistance(geo.sensor, geo.sample, centre, geo.distance_g);
-                               if (!(sdf >= far_threshold))
-                               {
-                                 atomicOr(&region_flags[idx >> 5], 1u << (idx & 31u));
-                               }
-                               return;
-                             }
-                             const uint32_t shift = (idx & 1u) * 16u;
-                             const uint32_t old = atomicAdd(&tile[idx >> 1], 1u << shift);
-                             if ((old >> shift) & kTileFlag)
-                             {
-                               const unsigned group = __activemask();
-                               const uint32_t n = (uint32_t)__popc(group);
-                               const uint32_t rank = (uint32_t)__popc(group & ((1u << (tid & 31u)) - 1u));
-                               uint32_t at = 0;
-                               if (rank == 0)
-                               {
-                                 const unsigned long long state = atomicAdd(&record_chunk[warp], (unsigned long long)n);
-                                 const uint32_t used = (uint32_t)state;
-                                 if (used + n <= kRecordChunk)
+      if (kCount)
+      {
+        const int entry[3] = { (int)(raw.w & 0xffu), (int)((raw.w >> 8) & 0xffu), (int)((raw.w >> 16) & 0xffu) };
+        resumeSegmentFast(init, delta, entry, total, rflags, st, visits, g, [&](uint32_t idx) {
+          const uint32_t shift = (idx & 1u) * 16u;
+          const uint32_t old = atomicAdd(&tile[idx >> 1], 1u << shift);
+          if ((old >> shift) & kTileFlag)
+          {
+            const unsigned group = __activemask();
+            const uint32_t n = (uint32_t)__popc(group);
+            const uint32_t rank = (uint32_t)__popc(group & ((1u << (tid & 31u)) - 1u));
+            uint32_t at = 0;
+            if (rank == 0)
+            {
+              const unsigned long long state = atomicAdd(&record_chunk[warp], (unsigned long long)n);
+              const uint32_t used = (uint32_t)state;
+              if (used + n <= kRecordChunk)
+              {
+                at = (uint32_t)(state >> 32) + used;
+              }
+              else
+              {
+                at = atomicAdd(&b.counters->record_count, kRecordChunk);
+                atomicExch(&record_chunk[warp], ((unsigned long long)at << 32) | n);
+              }
+            }
+            at = __shfl_sync(group, at, __ffs(group) - 1) + rank;
+            if (at < b.record_capacity)
+            {
+              b.record_keys[at] = ((unsigned long long)(vbase + idx) << 32) | ray;
+            }
+            else
+            {
+              b.counters->record_overflow = 1;
+              b.counters->overflow_seen = 1;
+            }
+          }
+        });
+      }
+      else if (!all_ordered)
+      {
+        // Only the last `near_steps` voxels of a walk can be near the sample: skip segments that end earlier.
+        const int steps_total = total[0] + total[1] + total[2];
+        const int q_entry = st[0] + st[1] + st[2];
+        if (steps_total - (q_entry + visits - 1) <= near_steps)
+        {
+          const int dx = g.dim[0], dxy = g.dim[0] * g.dim[1];
+          TsdfRayGeometry geo;
+          tsdfLoadRay(b, ray, geo);
+          int q = q_entry;
+          resumeSegment<false>(init, delta, local0, total, rflags, st, visits, 0.0, g,
+                               [&](const int l[3], double, double, bool) {
+                                 if (steps_total - q <= near_steps)
                                  {
-                                   at = (uint32_t)(state >> 32) + used;
+                                   const double centre[3] = { voxelCentreAxis(g, region[0], l[0], 0),
+                                                              voxelCentreAxis(g, region[1], l[1], 1),
+                                                              voxelCentreAxis(g, region[2], l[2], 2) };
+                                   const float sdf = tsdfDistance(geo.sensor, geo.sample, centre, geo.distance_g);
+                                   if (!(sdf >= far_threshold))
+                                   {
+                                     const uint32_t idx = (uint32_t)(l[0] + l[1] * dx + l[2] * dxy);
+                                     atomicOr(&region_flags[idx >> 5], 1u << (idx & 31u));
+                                   }
                                  }
-                                 else
-                                 {
-                                   at = atomicAdd(&b.counters->record_count, kRecordChunk);
-                                   atomicExch(&record_chunk[warp], ((unsigned long long)at << 32) | n);
-                                 }
-                               }
-                               at = __shfl_sync(group, at, __ffs(group) - 1) + rank;
-                               if (at < b.record_capacity)
-                               {
-                                 b.record_keys[at] = ((unsigned long long)(vbase + idx) << 32) | ray;
-                               }
-                               else
-                               {
-                                 b.counters->record_overflow = 1;
-                                 b.counters->overflow_seen = 1;
-                               }
-                             }
-                           });
+                                 ++q;
+                               });
+        }
+      }
     }
     if (!kCount)
     {

@@ -254,8 +254,8 @@ class GpuMap:
         self._check(self.L.ohmb200_set_profiling(self.h, int(bool(enabled))))
 
     def kernel_times(self, reset=True):
-        arr = (KernelTime * 16)()
-        n = self._check(self.L.ohmb200_kernel_times(self.h, arr, 16, int(reset)))
+        arr = (KernelTime * 24)()
+        n = self._check(self.L.ohmb200_kernel_times(self.h, arr, 24, int(reset)))
         return {arr[i].name.decode(): {"ms": arr[i].ms, "launches": int(arr[i].launches)} for i in range(n)}
 
 

@@ -63,7 +63,7 @@ static bool checkRay(const Geom &g, const double start[3], const double end[3], 
   std::vector<Visit> seg;
   std::vector<uint32_t> fast_idx;
   int last_flags = 0;
-  enumerateSegments(rec, g, [&](const int r[3], const int st[3], int n) {
+  enumerateSegments(rec, g, [&](const int r[3], const int st[3], const int entry[3], int n) {
     ++g_segments;
     const int total[3] = { rec.total[0], rec.total[1], rec.total[2] };
     const int local0[3] = { rec.local[0], rec.local[1], rec.local[2] };
@@ -78,7 +78,7 @@ static bool checkRay(const Geom &g, const double start[3], const double end[3], 
                           last_flags += last_of_ray ? 1 : 0;
                         });
     // the hot-path variant must visit the same voxels (as linear indices inside the region)
-    resumeSegmentFast(rec.initial, rec.delta, local0, total, rec.flags, st, n, g,
+    resumeSegmentFast(rec.initial, rec.delta, entry, total, rec.flags, st, n, g,
                       [&](uint32_t idx) { fast_idx.push_back(idx); });
   });
   ++g_rays;
