@@ -113,6 +113,9 @@ struct Batch
   uint32_t *seg_cursor;    // [capacity] fill cursors
   Segment *segments;       // [seg_capacity] binned by region slot
   uint32_t seg_capacity;
+  uint4 *stage;            // [kStageSegments][stage_stride] segments found by pass A, plane k = k-th segment of each ray
+  uint32_t *stage_count;   // [n] segments pass A found for the ray (> kStageSegments: pass B enumerates again)
+  uint32_t stage_stride;
   WorkItem *items;         // (region, segment range) work list
   uint32_t item_capacity;
   unsigned long long *gauss_keys;          // NDT: (voxel id << 32 | ray) of visits to voxels with an established Gaussian
@@ -761,6 +764,8 @@ int ensureScratch(ohmb200_map *m, size_t n)
     cudaFree(b.record_vid);
     cudaFree(b.segments);
     cudaFree(b.items);
+    cudaFree(b.stage);
+    cudaFree(b.stage_count);
     b.ray_length = nullptr;
     rc |= deviceAlloc(b.recs, cap);
     if (m->dm.traversal)
@@ -770,6 +775,9 @@ int ensureScratch(ohmb200_map *m, size_t n)
     rc |= deviceAlloc(b.record_vid, b.record_capacity);
     b.seg_capacity = (uint32_t)std::min<size_t>(cap * 96, 0xFFFFFFF0u);
     rc |= deviceAlloc(b.segments, b.seg_capacity);
+    b.stage_stride = (uint32_t)cap;
+    rc |= deviceAlloc(b.stage, (size_t)kStageSegments * cap);
+    rc |= deviceAlloc(b.stage_count, cap);
     b.item_capacity = m->dm.capacity + b.seg_capacity / kMaxSegmentsPerItem + 16;
     rc |= deviceAlloc(b.items, b.item_capacity);
     if (m->mode == OHMB200_MODE_NDT || m->mode == OHMB200_MODE_NDT_TM)
@@ -1321,7 +1329,7 @@ void ohmb200_destroy(ohmb200_map *m)
                       m->d_intensities[1], m->d_timestamps[0], m->d_timestamps[1], m->d_gather,    m->d_gather_slots,
                       b.recs,           b.ray_length,       b.record_vid,       b.seg_count,      b.seg_offset,
                       b.seg_cursor,     b.segments,         b.items,            b.record_keys,    b.record_keys_sorted, b.gauss_keys,
-                      m->tsdf_flags };
+                      b.stage,          b.stage_count,      m->tsdf_flags };
   for (void *p : to_free)
   {
     if (p)

@@ -118,12 +118,11 @@ __global__ void __launch_bounds__(128) prepRays(DeviceMap dm, Geom g, MapParams 
     {
       b.last_exit[i] = 0;
     }
+    uint32_t staged = 0;
     if (rec.flags & kRecValid)
     {
-      // Pass A: count this ray's segments per region (creating regions as they are first entered).
+      // Pass A: count this ray's segments per region (creating regions as they are first entered) and stage them.
       enumerateSegments(rec, g, [&](const int r[3], const int st[3], const int entry[3], int n) {
-        (void)st;
-        (void)entry;
         if (!ownsRegion(dm, r))
         {
           return;
@@ -142,9 +141,20 @@ __global__ void __launch_bounds__(128) prepRays(DeviceMap dm, Geom g, MapParams 
             }
             atomicAdd(&b.seg_count[slot], (uint32_t)__popc(peers));
           }
+          if (staged < kStageSegments)
+          {
+            uint4 raw;
+            raw.x = (uint32_t)slot;
+            raw.y = (uint32_t)st[0] | ((uint32_t)st[1] << 16);
+            raw.z = (uint32_t)st[2] | ((uint32_t)n << 16);
+            raw.w = (uint32_t)entry[0] | ((uint32_t)entry[1] << 8) | ((uint32_t)entry[2] << 16);
+            b.stage[(size_t)staged * b.stage_stride + i] = raw;
+          }
+          ++staged;
         }
       });
     }
+    b.stage_count[i] = staged;
   }
   __syncwarp();
   const unsigned n_acc = __reduce_add_sync(0xffffffffu, accepted ? 1u : 0u);
@@ -240,12 +250,25 @@ __global__ void __launch_bounds__(128) emitSegments(DeviceMap dm, Geom g, Batch 
   {
     return;
   }
-  RayRec rec;
-  loadRec(rec, b.recs + i);
-  if (!(rec.flags & kRecValid))
+  const uint32_t staged = b.stage_count[i];
+  if (staged <= kStageSegments)
   {
+    // Pass B, common case: scatter the segments pass A staged (plane k holds the k-th segment of every ray).
+    for (uint32_t k = 0; k < staged; ++k)
+    {
+      uint4 raw = b.stage[(size_t)k * b.stage_stride + i];
+      const uint32_t slot = raw.x;
+      const uint32_t at = b.seg_offset[slot] + slotAggregatedInc(b.seg_cursor, slot);
+      if (at < b.seg_capacity)
+      {
+        raw.x = i;
+        reinterpret_cast<uint4 *>(b.segments)[at] = raw;
+      }
+    }
     return;
   }
+  RayRec rec;
+  loadRec(rec, b.recs + i);
   enumerateSegments(rec, g, [&](const int r[3], const int st[3], const int entry[3], int n) {
     if (!ownsRegion(dm, r))
     {

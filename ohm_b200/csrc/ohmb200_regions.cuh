@@ -17,7 +17,8 @@ namespace ohmb200
 {
 constexpr unsigned kRecValid = 1u << 3, kRecExcludeStart = 1u << 4, kRecExcludeEnd = 1u << 5;
 constexpr uint32_t kMaxSegmentsPerItem = 2048;  // < 32768: tile counters are 15 bit + flag
-constexpr uint32_t kRecordChunk = 256;         // ordered-miss records are reserved per warp in chunks
+constexpr uint32_t kRecordChunk = 256;
+constexpr uint32_t kStageSegments = 32;  // segments per ray that pass A hands to pass B without a second enumeration         // ordered-miss records are reserved per warp in chunks
 constexpr uint32_t kTileFlag = 0x8000u;
 
 // Walk constants of one ray (64 bytes).
