@@ -506,11 +506,13 @@ enum KernelId
   kKGather,
   kKFill,
   kKPrepRays,
+  kKPrepSegments,
   kKPlan,
   kKEmit,
   kKWalkRegions,
   kKLink,
   kKTsdfMark,
+  kKTsdfClear,
   kKTsdfReplay,
   kKNdtGauss,
   kKNdtClamp,
@@ -518,8 +520,8 @@ enum KernelId
 };
 static const char *kKernelNames[kKernelCount] = { "prepSamples",  "radixSort",     "markRuns",      "walkRays",
                                                   "applySamples", "resolveMisses", "gatherRegions", "fillFloat",
-                                                  "prepRays",     "planRegions",   "emitSegments",  "walkRegions",
-                                                  "linkRecords",  "walkRegionsTsdf<mark>", "replayTsdf",
+                                                  "prepRays",     "prepSegments",  "planRegions",   "emitSegments",  "walkRegions",
+                                                  "linkRecords",  "markTsdfNear",  "clearTouchedBits", "replayTsdf",
                                                   "ndtGaussianMisses", "ndtClampGaussians" };
 static_assert(kKernelCount <= OHMB200_KERNEL_SLOTS, "raise OHMB200_KERNEL_SLOTS");
 
@@ -531,8 +533,8 @@ struct ohmb200_map
   int algo = 1;           // 1 = region-binned walk (shared-memory tiles), 0 = one thread per ray (global counters)
   size_t tile_bytes = 0;  // dynamic shared memory of walkRegions
   int walk_ctas_per_sm = 1;
-  uint32_t *tsdf_flags = nullptr;  // TSDF: one bit per voxel, "replay this voxel's visits in order"
-  size_t tsdf_flag_bytes = 0;
+  uint32_t *tsdf_near = nullptr;  // TSDF: per-batch bit per voxel, "visited near a sample in this batch"
+  size_t voxel_bit_bytes = 0;     // size of dm.voxel_bits (and of tsdf_near)
   ohmb200_params params{};
   Geom geom{};
   MapParams mp{};
@@ -705,6 +707,14 @@ int initialiseSlabs(ohmb200_map *m)
       CUDA_TRY(cudaMemsetAsync(m->layer_slab[l], 0, kLayerBytes[l] * voxels, m->stream));
     }
   }
+  if (m->dm.voxel_bits)
+  {
+    CUDA_TRY(cudaMemsetAsync(m->dm.voxel_bits, 0, m->voxel_bit_bytes, m->stream));
+  }
+  if (m->tsdf_near)
+  {
+    CUDA_TRY(cudaMemsetAsync(m->tsdf_near, 0, m->voxel_bit_bytes, m->stream));
+  }
   CUDA_TRY(cudaMemsetAsync(m->d_counters, 0, sizeof(Counters), m->stream));
   CUDA_TRY(cudaGetLastError());
   return OHMB200_OK;
@@ -778,7 +788,7 @@ int ensureScratch(ohmb200_map *m, size_t n)
     b.stage_stride = (uint32_t)cap;
     rc |= deviceAlloc(b.stage, (size_t)kStageSegments * cap);
     rc |= deviceAlloc(b.stage_count, cap);
-    b.item_capacity = m->dm.capacity + b.seg_capacity / kMaxSegmentsPerItem + 16;
+    b.item_capacity = m->dm.capacity + b.seg_capacity / 512 + 16;
     rc |= deviceAlloc(b.items, b.item_capacity);
     if (m->mode == OHMB200_MODE_NDT || m->mode == OHMB200_MODE_NDT_TM)
     {
@@ -880,8 +890,12 @@ int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_i
       }
     }
     {
+      KernelScope scope(m, kKPrepSegments);
+      prepSegments<<<blocks, threads, 0, s>>>(m->dm, m->geom, b);
+    }
+    {
       KernelScope scope(m, kKPlan);
-      planRegions<<<1, 1024, 0, s>>>(m->dm, b);
+      planRegions<<<1, 1024, 0, s>>>(m->dm, b, (uint32_t)(m->sm_count * m->walk_ctas_per_sm));
     }
     {
       KernelScope scope(m, kKEmit);
@@ -895,15 +909,18 @@ int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_i
     if (m->mode == OHMB200_MODE_TSDF)
     {
       const unsigned grid = m->sm_count * m->walk_ctas_per_sm;
-      CUDA_TRY(cudaMemsetAsync(m->tsdf_flags, 0, m->tsdf_flag_bytes, s));
       CUDA_TRY(cudaMemsetAsync(b.record_keys, 0xFF, sizeof(unsigned long long) * b.record_capacity, s));
       {
         KernelScope scope(m, kKTsdfMark);
-        walkRegionsTsdf<false><<<grid, kWalkThreads, m->tile_bytes, s>>>(m->dm, m->geom, m->mp, b, m->tsdf_flags);
+        markTsdfNear<<<blocks, threads, 0, s>>>(m->dm, m->geom, m->mp, b, m->tsdf_near);
       }
       {
         KernelScope scope(m, kKWalkRegions);
-        walkRegionsTsdf<true><<<grid, kWalkThreads, m->tile_bytes, s>>>(m->dm, m->geom, m->mp, b, m->tsdf_flags);
+        walkRegionsTsdf<<<grid, kWalkThreads, m->tile_bytes, s>>>(m->dm, m->geom, m->mp, b, m->tsdf_near);
+      }
+      {
+        KernelScope scope(m, kKTsdfClear);
+        clearTouchedBits<<<m->sm_count * 4, 256, 0, s>>>(b, m->tsdf_near, (m->geom.vpr + 31u) / 32u);
       }
       // The ordered records are sorted by (voxel, ray) with a host-known count: the one host wait of the TSDF path.
       CUDA_TRY(cudaMemcpyAsync(m->h_counters, m->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, s));
@@ -1181,7 +1198,7 @@ ohmb200_map *ohmb200_create(const ohmb200_params *params, int mode, size_t devic
   refreshParams(m);
 
   // Walk algorithm: the region-binned path needs the u16 counter tile of a region to fit in shared memory.
-  m->tile_bytes = sizeof(uint32_t) * ((m->geom.vpr + 1u) / 2u);
+  m->tile_bytes = sizeof(uint32_t) * tileWords(m->geom.vpr);
   m->algo = 1;
   if (const char *env = getenv("OHMB200_ALGO"))
   {
@@ -1212,8 +1229,7 @@ ohmb200_map *ohmb200_create(const ohmb200_params *params, int mode, size_t devic
   {
     if (cudaFuncSetAttribute(walkRegions, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->tile_bytes) != cudaSuccess ||
         cudaFuncSetAttribute(walkRegionsNdt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->tile_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(walkRegionsTsdf<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->tile_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(walkRegionsTsdf<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->tile_bytes) != cudaSuccess)
+        cudaFuncSetAttribute(walkRegionsTsdf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->tile_bytes) != cudaSuccess)
     {
       cudaGetLastError();
       m->algo = 0;
@@ -1280,10 +1296,14 @@ ohmb200_map *ohmb200_create(const ohmb200_params *params, int mode, size_t devic
       ok = ok && cudaMalloc(&m->layer_slab[l], kLayerBytes[l] * voxels) == cudaSuccess;
     }
   }
-  if (tsdf)
+  if (tsdf || ndt)
   {
-    m->tsdf_flag_bytes = sizeof(uint32_t) * ((m->geom.vpr + 31u) / 32u) * capacity;
-    ok = ok && cudaMalloc(&m->tsdf_flags, m->tsdf_flag_bytes) == cudaSuccess;
+    m->voxel_bit_bytes = sizeof(uint32_t) * ((m->geom.vpr + 31u) / 32u) * capacity;
+    ok = ok && cudaMalloc(&m->dm.voxel_bits, m->voxel_bit_bytes) == cudaSuccess;
+    if (tsdf)
+    {
+      ok = ok && cudaMalloc(&m->tsdf_near, m->voxel_bit_bytes) == cudaSuccess;
+    }
   }
   if (!ok)
   {
@@ -1329,7 +1349,7 @@ void ohmb200_destroy(ohmb200_map *m)
                       m->d_intensities[1], m->d_timestamps[0], m->d_timestamps[1], m->d_gather,    m->d_gather_slots,
                       b.recs,           b.ray_length,       b.record_vid,       b.seg_count,      b.seg_offset,
                       b.seg_cursor,     b.segments,         b.items,            b.record_keys,    b.record_keys_sorted, b.gauss_keys,
-                      b.stage,          b.stage_count,      m->tsdf_flags };
+                      b.stage,          b.stage_count,      m->tsdf_near,       m->dm.voxel_bits };
   for (void *p : to_free)
   {
     if (p)
@@ -1399,10 +1419,19 @@ int ohmb200_set_params(ohmb200_map *m, const ohmb200_params *p)
   }
   const uint32_t layers = m->params.layers;
   const int ndt_tm = m->params.ndt_tm;
+  const bool bits_stale = m->dm.voxel_bits && (p->sample_threshold != m->params.sample_threshold ||
+                                               p->tsdf_trunc != m->params.tsdf_trunc);
   m->params = *p;
   m->params.layers = layers;
   m->params.ndt_tm = ndt_tm;
   refreshParams(m);
+  if (bits_stale)
+  {
+    // the persistent per-voxel bits are a function of the stored layers AND these parameters
+    cudaSetDevice(m->device);
+    recomputeVoxelBits<<<m->dm.capacity, 256, 0, m->stream>>>(m->dm, m->geom, m->mp, m->mode == OHMB200_MODE_TSDF, 0u);
+    CUDA_TRY(cudaGetLastError());
+  }
   return OHMB200_OK;
 }
 
@@ -1696,6 +1725,10 @@ int ohmb200_write_region(ohmb200_map *m, const int16_t key_xyz[3], int layer, co
   }
   CUDA_TRY(cudaMemcpyAsync((char *)m->layer_slab[layer] + (size_t)slot * chunk, src, chunk, cudaMemcpyHostToDevice,
                            m->stream));
+  if (m->dm.voxel_bits && (layer == OHMB200_LAYER_TSDF || layer == OHMB200_LAYER_MEAN))
+  {
+    recomputeVoxelBits<<<1, 256, 0, m->stream>>>(m->dm, m->geom, m->mp, m->mode == OHMB200_MODE_TSDF, (uint32_t)slot);
+  }
   CUDA_TRY(cudaStreamSynchronize(m->stream));
   return OHMB200_OK;
 }

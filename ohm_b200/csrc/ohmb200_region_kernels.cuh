@@ -59,11 +59,12 @@ __device__ __forceinline__ void loadRec(RayRec &rec, const RayRec *src)
 }
 }  // namespace ohmb200
 
+// Filter, sample voxel and walk constants of every ray.  The sample pairs it writes are all the sort needs, so the
+// sample path (radix sort -> run heads) starts right after this kernel, beside prepSegments.
 __global__ void __launch_bounds__(128) prepRays(DeviceMap dm, Geom g, MapParams mp, Batch b, int mode)
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   bool accepted = false;
-  unsigned visits = 0;
   if (i < b.n)
   {
     double start[3], end[3];
@@ -118,6 +119,25 @@ __global__ void __launch_bounds__(128) prepRays(DeviceMap dm, Geom g, MapParams 
     {
       b.last_exit[i] = 0;
     }
+  }
+  __syncwarp();
+  const unsigned n_acc = __reduce_add_sync(0xffffffffu, accepted ? 1u : 0u);
+  if ((threadIdx.x & 31) == 0 && n_acc)
+  {
+    atomicAdd(&b.counters->rays_accepted, (unsigned long long)n_acc);
+  }
+}
+
+// Pass A of enumerateSegments, one thread per ray: region find-or-insert, per-region segment histogram, touched list,
+// and the segments themselves staged for pass B.
+__global__ void __launch_bounds__(128) prepSegments(DeviceMap dm, Geom g, Batch b)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned visits = 0;
+  if (i < b.n)
+  {
+    RayRec rec;
+    loadRec(rec, b.recs + i);
     uint32_t staged = 0;
     if (rec.flags & kRecValid)
     {
@@ -157,23 +177,15 @@ __global__ void __launch_bounds__(128) prepRays(DeviceMap dm, Geom g, MapParams 
     b.stage_count[i] = staged;
   }
   __syncwarp();
-  const unsigned n_acc = __reduce_add_sync(0xffffffffu, accepted ? 1u : 0u);
   const unsigned n_vis = __reduce_add_sync(0xffffffffu, visits);
-  if ((threadIdx.x & 31) == 0)
+  if ((threadIdx.x & 31) == 0 && n_vis)
   {
-    if (n_acc)
-    {
-      atomicAdd(&b.counters->rays_accepted, (unsigned long long)n_acc);
-    }
-    if (n_vis)
-    {
-      atomicAdd(&b.counters->voxel_visits, (unsigned long long)n_vis);
-    }
+    atomicAdd(&b.counters->voxel_visits, (unsigned long long)n_vis);
   }
 }
 
 // Single CTA over the touched regions only: segment offsets and the work-item list (largest regions first).
-__global__ void __launch_bounds__(1024) planRegions(DeviceMap dm, Batch b)
+__global__ void __launch_bounds__(1024) planRegions(DeviceMap dm, Batch b, uint32_t walk_ctas)
 {
   typedef cub::BlockScan<uint32_t, 1024> Scan;
   __shared__ typename Scan::TempStorage scan_storage;
@@ -212,11 +224,15 @@ __global__ void __launch_bounds__(1024) planRegions(DeviceMap dm, Batch b)
     }
   }
   // Work items in decreasing size classes so that the long items start first and the tail is made of small ones.
+  // Item size: about three items per persistent CTA (a batch that touches few regions — a small batch, or one GPU's
+  // share of a sharded map — is cut finer so that every SM still gets work), at most kMaxSegmentsPerItem.
   __syncthreads();
+  const uint32_t item_max =
+    min(kMaxSegmentsPerItem, max(512u, ((carry / max(3u * walk_ctas, 1u)) + 63u) & ~63u));
   for (int pass = 0; pass < 5; ++pass)
   {
-    const uint32_t hi = (pass == 0) ? 0xFFFFFFFFu : (kMaxSegmentsPerItem >> (pass == 1 ? 0 : (pass == 2 ? 1 : (pass == 3 ? 3 : 5))));
-    const uint32_t lo = (pass == 4) ? 1u : (kMaxSegmentsPerItem >> (pass == 0 ? 0 : (pass == 1 ? 1 : (pass == 2 ? 3 : 5))));
+    const uint32_t hi = (pass == 0) ? 0xFFFFFFFFu : (item_max >> (pass == 1 ? 0 : (pass == 2 ? 1 : (pass == 3 ? 3 : 5))));
+    const uint32_t lo = (pass == 4) ? 1u : (item_max >> (pass == 0 ? 0 : (pass == 1 ? 1 : (pass == 2 ? 3 : 5))));
     for (uint32_t t = threadIdx.x; t < touched; t += blockDim.x)
     {
       const uint32_t slot = b.touched_list[t];
@@ -225,15 +241,15 @@ __global__ void __launch_bounds__(1024) planRegions(DeviceMap dm, Batch b)
       {
         continue;
       }
-      const uint32_t pieces = (count + kMaxSegmentsPerItem - 1) / kMaxSegmentsPerItem;
+      const uint32_t pieces = (count + item_max - 1) / item_max;
       const uint32_t at = atomicAdd(&b.counters->item_count, pieces);
       const uint32_t begin = b.seg_offset[slot];
       for (uint32_t p = 0; p < pieces && at + p < b.item_capacity; ++p)
       {
         WorkItem w;
         w.slot = slot;
-        w.begin = begin + p * kMaxSegmentsPerItem;
-        w.end = min(begin + count, w.begin + kMaxSegmentsPerItem);
+        w.begin = begin + p * item_max;
+        w.end = min(begin + count, w.begin + item_max);
         w.shared = pieces > 1;
         b.items[at + p] = w;
       }
@@ -295,6 +311,175 @@ __global__ void __launch_bounds__(128) emitSegments(DeviceMap dm, Geom g, Batch 
 constexpr int kWalkThreads = 512;
 constexpr uint32_t kLengthBins = 128;  // visits per segment <= 3 * 255; 127+ share a bin
 
+// dm.voxel_bits: one persistent bit per voxel, [capacity][(vpr + 31) / 32] words (NDT: the voxel has an established
+// Gaussian; TSDF: the stored state is not order-free).
+__device__ __forceinline__ void setVoxelBit(const DeviceMap &dm, const Geom &g, uint32_t vid, bool value)
+{
+  const uint32_t slot = vid / g.vpr;
+  const uint32_t local = vid - slot * g.vpr;
+  uint32_t *word = dm.voxel_bits + (size_t)slot * ((g.vpr + 31u) >> 5) + (local >> 5);
+  const uint32_t bit = 1u << (local & 31u);
+  if (value)
+  {
+    if (!(*word & bit))
+    {
+      atomicOr(word, bit);
+    }
+  }
+  else if (*word & bit)
+  {
+    atomicAnd(word, ~bit);
+  }
+}
+
+// Slot for one ordered record, for every lane that calls this together.  Slots come from a per-warp chunk
+// ((base << 32) | used, in shared memory): one global atomic per kRecordChunk records.
+__device__ __forceinline__ uint32_t reserveRecord(unsigned long long *warp_chunk, uint32_t *global_count)
+{
+  const unsigned group = __activemask();
+  const uint32_t n = (uint32_t)__popc(group);
+  const uint32_t rank = (uint32_t)__popc(group & ((1u << (threadIdx.x & 31u)) - 1u));
+  uint32_t at = 0;
+  if (rank == 0)
+  {
+    const unsigned long long state = atomicAdd(warp_chunk, (unsigned long long)n);
+    const uint32_t used = (uint32_t)state;
+    if (used + n <= kRecordChunk)
+    {
+      at = (uint32_t)(state >> 32) + used;
+    }
+    else
+    {
+      at = atomicAdd(global_count, kRecordChunk);
+      atomicExch(warp_chunk, ((unsigned long long)at << 32) | n);
+    }
+  }
+  return __shfl_sync(group, at, __ffs(group) - 1) + rank;
+}
+
+// The segments of a work item, ordered by decreasing visit count and handed to warps 32 at a time: the lanes of a warp
+// walk segments of (nearly) equal length, long segments start first, and a warp that finishes early takes more.
+struct SegmentQueue
+{
+  uint16_t order[kMaxSegmentsPerItem];
+  uint32_t length_bins[kLengthBins];
+  uint32_t next_chunk;
+};
+
+// Every thread of the CTA calls this (it synchronises); the previous item's pops must be behind a barrier already.
+__device__ __forceinline__ void queueBuild(SegmentQueue &q, const Batch &b, const WorkItem &item)
+{
+  const uint32_t tid = threadIdx.x;
+  if (tid < kLengthBins)
+  {
+    q.length_bins[tid] = 0;
+  }
+  if (tid == 0)
+  {
+    q.next_chunk = 0;
+  }
+  __syncthreads();
+  const uint32_t n_segments = item.end - item.begin;
+  const uint32_t *segment_words = reinterpret_cast<const uint32_t *>(b.segments + item.begin);
+  for (uint32_t k = tid; k < n_segments; k += blockDim.x)
+  {
+    const uint32_t visits = segment_words[4 * k + 2] >> 16;
+    atomicAdd(&q.length_bins[kLengthBins - 1u - min(visits, kLengthBins - 1u)], 1u);
+  }
+  __syncthreads();
+  if (tid < 32)
+  {
+    // exclusive scan of the 128 bins by one warp (4 bins per lane)
+    uint32_t c[4], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+      c[k] = q.length_bins[tid * 4 + k];
+      sum += c[k];
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+      incl += (tid >= (uint32_t)d) ? up : 0u;
+    }
+    uint32_t base = incl - sum;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+      q.length_bins[tid * 4 + k] = base;
+      base += c[k];
+    }
+  }
+  __syncthreads();
+  for (uint32_t k = tid; k < n_segments; k += blockDim.x)
+  {
+    const uint32_t visits = segment_words[4 * k + 2] >> 16;
+    q.order[atomicAdd(&q.length_bins[kLengthBins - 1u - min(visits, kLengthBins - 1u)], 1u)] = (uint16_t)k;
+  }
+  __syncthreads();
+}
+
+// Warp-collective.  0: the queue is empty; 1: `raw` holds this lane's segment; 2: this lane has none this round.
+__device__ __forceinline__ int queuePop(SegmentQueue &q, const Batch &b, const WorkItem &item, uint4 &raw)
+{
+  uint32_t k = 0;
+  if ((threadIdx.x & 31u) == 0)
+  {
+    k = atomicAdd(&q.next_chunk, 32u);
+  }
+  k = __shfl_sync(0xffffffffu, k, 0);
+  const uint32_t n_segments = item.end - item.begin;
+  if (k >= n_segments)
+  {
+    return 0;
+  }
+  k += threadIdx.x & 31u;
+  if (k >= n_segments)
+  {
+    return 2;
+  }
+  raw = reinterpret_cast<const uint4 *>(b.segments)[item.begin + q.order[k]];
+  return 1;
+}
+
+// What a lane needs to resume a segment: the segment itself and the walk constants of its ray.
+struct SegmentWalk
+{
+  uint32_t ray, flags;
+  int st[3], visits, entry[3], total[3], local0[3];
+  double init[3], delta[3];
+};
+
+__device__ __forceinline__ void loadSegmentWalk(const Batch &b, const uint4 &raw, SegmentWalk &w)
+{
+  w.ray = raw.x;
+  w.st[0] = (int)(raw.y & 0xffffu);
+  w.st[1] = (int)(raw.y >> 16);
+  w.st[2] = (int)(raw.z & 0xffffu);
+  w.visits = (int)(raw.z >> 16);
+  w.entry[0] = (int)(raw.w & 0xffu);
+  w.entry[1] = (int)((raw.w >> 8) & 0xffu);
+  w.entry[2] = (int)((raw.w >> 16) & 0xffu);
+  const RayRec *rp = b.recs + w.ray;
+  // tail of the record: region[3] i16 | local[3] u8 | flags u8 | total[3] u16
+  const uint4 tail = reinterpret_cast<const uint4 *>(rp)[3];
+  w.flags = (tail.z >> 8) & 0xffu;
+  w.total[0] = (int)(tail.z >> 16);
+  w.total[1] = (int)(tail.w & 0xffffu);
+  w.total[2] = (int)(tail.w >> 16);
+  w.local0[0] = (int)((tail.y >> 16) & 0xffu);
+  w.local0[1] = (int)(tail.y >> 24);
+  w.local0[2] = (int)(tail.z & 0xffu);
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+  {
+    w.init[a] = rp->initial[a];
+    w.delta[a] = rp->delta[a];
+  }
+}
+
 // Persistent CTAs: one (region, segment range) work item at a time against a shared-memory counter tile.
 __global__ void __launch_bounds__(kWalkThreads, 2) walkRegions(DeviceMap dm, Geom g, MapParams mp, Batch b, int has_samples)
 {
@@ -303,11 +488,8 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegions(DeviceMap dm, Geo
   __shared__ uint32_t sample_range[2];
   // per-warp reservation of ordered-miss record slots: (base << 32) | used
   __shared__ unsigned long long record_chunk[kWalkThreads / 32];
-  // segments of the item ordered by decreasing visit count: lanes of a warp then walk segments of (nearly) equal
-  // length, and a thread's strided share mixes long and short ones
-  __shared__ uint16_t order[kMaxSegmentsPerItem];
-  __shared__ uint32_t length_bins[kLengthBins];
-  const uint32_t words = (g.vpr + 1u) >> 1;
+  __shared__ SegmentQueue queue;
+  const uint32_t words = tileWords(g.vpr);
   const uint32_t tid = threadIdx.x;
   const uint32_t warp = tid >> 5;
   if ((tid & 31u) == 0)
@@ -356,102 +538,39 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegions(DeviceMap dm, Geo
     {
       sample_range[tid] = lowerBound(b.keys_out, b.n, vbase + tid * g.vpr);
     }
-    if (tid < kLengthBins)
-    {
-      length_bins[tid] = 0;
-    }
     __syncthreads();
-    const uint32_t n_segments = item.end - item.begin;
-    const uint32_t *segment_words = reinterpret_cast<const uint32_t *>(b.segments + item.begin);
-    for (uint32_t k = tid; k < n_segments; k += blockDim.x)
-    {
-      const uint32_t visits = segment_words[4 * k + 2] >> 16;
-      atomicAdd(&length_bins[kLengthBins - 1u - min(visits, kLengthBins - 1u)], 1u);
-    }
     if (has_samples)
     {
       // Voxels that also receive samples in this batch: their misses must stay ordered against the hits.
       for (uint32_t s = sample_range[0] + tid; s < sample_range[1]; s += blockDim.x)
       {
         const uint32_t v = b.keys_out[s] - vbase;
-        atomicOr(&tile[v >> 1], kTileFlag << ((v & 1u) * 16u));
+        atomicOr(&tile[tileWord(v)], kTileFlag << ((v & 1u) * 16u));
       }
     }
-    __syncthreads();
-    if (warp == 0)
-    {
-      // exclusive scan of the 128 bins by one warp (4 bins per lane)
-      uint32_t c[4], sum = 0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-      {
-        c[k] = length_bins[tid * 4 + k];
-        sum += c[k];
-      }
-      uint32_t incl = sum;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1)
-      {
-        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
-        incl += (tid >= (uint32_t)d) ? up : 0u;
-      }
-      uint32_t base = incl - sum;
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-      {
-        length_bins[tid * 4 + k] = base;
-        base += c[k];
-      }
-    }
-    __syncthreads();
-    for (uint32_t k = tid; k < n_segments; k += blockDim.x)
-    {
-      const uint32_t visits = segment_words[4 * k + 2] >> 16;
-      order[atomicAdd(&length_bins[kLengthBins - 1u - min(visits, kLengthBins - 1u)], 1u)] = (uint16_t)k;
-    }
-    __syncthreads();
+    queueBuild(queue, b, item);
 
-    for (uint32_t k = tid; k < n_segments; k += blockDim.x)
+    for (;;)
     {
-      const uint32_t s = item.begin + order[k];
-      const uint4 raw = reinterpret_cast<const uint4 *>(b.segments)[s];
-      const uint32_t ray = raw.x;
-      const int st[3] = { (int)(raw.y & 0xffffu), (int)(raw.y >> 16), (int)(raw.z & 0xffffu) };
-      const int visits = (int)(raw.z >> 16);
-      const int entry[3] = { (int)(raw.w & 0xffu), (int)((raw.w >> 8) & 0xffu), (int)((raw.w >> 16) & 0xffu) };
-      const RayRec *rp = b.recs + ray;
-      // tail of the record: region[3] i16 | local[3] u8 | flags u8 | total[3] u16
-      const uint4 tail = reinterpret_cast<const uint4 *>(rp)[3];
-      const uint32_t flags = (tail.z >> 8) & 0xffu;
-      const int total[3] = { (int)(tail.z >> 16), (int)(tail.w & 0xffffu), (int)(tail.w >> 16) };
-      const int local0[3] = { (int)((tail.y >> 16) & 0xffu), (int)(tail.y >> 24), (int)(tail.z & 0xffu) };
-      const double init[3] = { rp->initial[0], rp->initial[1], rp->initial[2] };
-      const double delta[3] = { rp->delta[0], rp->delta[1], rp->delta[2] };
+      uint4 raw;
+      const int got = queuePop(queue, b, item, raw);
+      if (got == 0)
+      {
+        break;
+      }
+      if (got == 2)
+      {
+        continue;
+      }
+      SegmentWalk sw;
+      loadSegmentWalk(b, raw, sw);
+      const uint32_t ray = sw.ray;
       auto count_visit = [&](uint32_t idx) {
         const uint32_t shift = (idx & 1u) * 16u;
-        const uint32_t old = atomicAdd(&tile[idx >> 1], 1u << shift);
+        const uint32_t old = atomicAdd(&tile[tileWord(idx)], 1u << shift);
         if ((old >> shift) & kTileFlag)
         {
-          // Ordered-miss record.  Slots come from a per-warp chunk: one global atomic per kRecordChunk records.
-          const unsigned group = __activemask();
-          const uint32_t n = (uint32_t)__popc(group);
-          const uint32_t rank = (uint32_t)__popc(group & ((1u << (tid & 31u)) - 1u));
-          uint32_t at = 0;
-          if (rank == 0)
-          {
-            const unsigned long long state = atomicAdd(&record_chunk[warp], (unsigned long long)n);
-            const uint32_t used = (uint32_t)state;
-            if (used + n <= kRecordChunk)
-            {
-              at = (uint32_t)(state >> 32) + used;
-            }
-            else
-            {
-              at = atomicAdd(&b.counters->record_count, kRecordChunk);
-              atomicExch(&record_chunk[warp], ((unsigned long long)at << 32) | n);
-            }
-          }
-          at = __shfl_sync(group, at, __ffs(group) - 1) + rank;
+          const uint32_t at = reserveRecord(&record_chunk[warp], &b.counters->record_count);
           if (at < b.record_capacity)
           {
             b.record_vid[at] = vbase + idx;
@@ -467,7 +586,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegions(DeviceMap dm, Geo
       if (dm.traversal)
       {
         const int dx = g.dim[0], dxy = g.dim[0] * g.dim[1];
-        resumeSegment<true>(init, delta, local0, total, flags, st, visits, b.ray_length[ray], g,
+        resumeSegment<true>(sw.init, sw.delta, sw.local0, sw.total, sw.flags, sw.st, sw.visits, b.ray_length[ray], g,
                             [&](const int l[3], double t_enter, double t_exit, bool last_of_ray) {
                               const uint32_t idx = (uint32_t)(l[0] + l[1] * dx + l[2] * dxy);
                               count_visit(idx);
@@ -480,7 +599,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegions(DeviceMap dm, Geo
       }
       else
       {
-        resumeSegmentFast(init, delta, entry, total, flags, st, visits, g, count_visit);
+        resumeSegmentFast(sw.init, sw.delta, sw.entry, sw.total, sw.flags, sw.st, sw.visits, g, count_visit);
       }
     }
     __syncthreads();
@@ -493,7 +612,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegions(DeviceMap dm, Geo
       float4 *occ4 = reinterpret_cast<float4 *>(occ);
       for (uint32_t c = tid; c < (g.vpr >> 3); c += blockDim.x)
       {
-        const uint4 t = tile4[c];
+        const uint4 t = tile4[tileGroup(c)];
         const uint32_t w4[4] = { t.x, t.y, t.z, t.w };
         uint32_t cnt[8];
         uint32_t any = 0;
@@ -525,7 +644,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegions(DeviceMap dm, Geo
     {
       for (uint32_t v = tid; v < g.vpr; v += blockDim.x)
       {
-        const uint32_t half = (tile[v >> 1] >> ((v & 1u) * 16u)) & 0xffffu;
+        const uint32_t half = (tile[tileWord(v)] >> ((v & 1u) * 16u)) & 0xffffu;
         if (half == 0 || (half & kTileFlag))
         {
           continue;
@@ -657,7 +776,8 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsNdt(const __grid_c
   __shared__ uint32_t sample_range[2];
   __shared__ unsigned long long record_chunk[kWalkThreads / 32];
   __shared__ unsigned long long gauss_chunk[kWalkThreads / 32];
-  const uint32_t words = (g.vpr + 1u) >> 1;
+  __shared__ SegmentQueue queue;
+  const uint32_t words = tileWords(g.vpr);
   const uint32_t kind_words = (g.vpr + 31u) >> 5;
   uint32_t *kind = tile + ((words + 3u) & ~3u);
   const uint32_t tid = threadIdx.x;
@@ -689,71 +809,54 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsNdt(const __grid_c
     }
     const uint32_t slot = item.slot;
     const uint32_t vbase = slot * g.vpr;
-    for (uint32_t w = tid; w < words; w += blockDim.x)
     {
-      tile[w] = 0;
+      uint4 *tile4 = reinterpret_cast<uint4 *>(tile);
+      for (uint32_t w = tid; w < (words >> 2); w += blockDim.x)
+      {
+        tile4[w] = make_uint4(0, 0, 0, 0);
+      }
     }
-    for (uint32_t w = tid; w < kind_words; w += blockDim.x)
     {
-      kind[w] = 0;
+      // established Gaussians: the persistent bit per voxel (mean count >= sample threshold)
+      const uint32_t *bits = dm.voxel_bits + (size_t)slot * kind_words;
+      for (uint32_t w = tid; w < kind_words; w += blockDim.x)
+      {
+        kind[w] = (mp.sample_threshold == 0) ? 0xFFFFFFFFu : bits[w];
+      }
     }
     if (tid < 2)
     {
       sample_range[tid] = lowerBound(b.keys_out, b.n, vbase + tid * g.vpr);
     }
     __syncthreads();
-    for (uint32_t v = tid; v < g.vpr; v += blockDim.x)
-    {
-      if (dm.mean[vbase + v].y >= mp.sample_threshold)
-      {
-        atomicOr(&kind[v >> 5], 1u << (v & 31u));
-      }
-    }
     for (uint32_t s = sample_range[0] + tid; s < sample_range[1]; s += blockDim.x)
     {
       const uint32_t v = b.keys_out[s] - vbase;
-      atomicOr(&tile[v >> 1], kTileFlag << ((v & 1u) * 16u));
+      atomicOr(&tile[tileWord(v)], kTileFlag << ((v & 1u) * 16u));
     }
-    __syncthreads();
+    queueBuild(queue, b, item);
 
-    for (uint32_t s = item.begin + tid; s < item.end; s += blockDim.x)
+    for (;;)
     {
-      const uint4 raw = reinterpret_cast<const uint4 *>(b.segments)[s];
-      const uint32_t ray = raw.x;
-      const int st[3] = { (int)(raw.y & 0xffffu), (int)(raw.y >> 16), (int)(raw.z & 0xffffu) };
-      const int visits = (int)(raw.z >> 16);
-      const int entry[3] = { (int)(raw.w & 0xffu), (int)((raw.w >> 8) & 0xffu), (int)((raw.w >> 16) & 0xffu) };
-      const RayRec *rp = b.recs + ray;
-      const uint4 tail = reinterpret_cast<const uint4 *>(rp)[3];
-      const uint32_t flags = (tail.z >> 8) & 0xffu;
-      const int total[3] = { (int)(tail.z >> 16), (int)(tail.w & 0xffffu), (int)(tail.w >> 16) };
-      const int local0[3] = { (int)((tail.y >> 16) & 0xffu), (int)(tail.y >> 24), (int)(tail.z & 0xffu) };
-      const double init[3] = { rp->initial[0], rp->initial[1], rp->initial[2] };
-      const double delta[3] = { rp->delta[0], rp->delta[1], rp->delta[2] };
+      uint4 raw;
+      const int got = queuePop(queue, b, item, raw);
+      if (got == 0)
+      {
+        break;
+      }
+      if (got == 2)
+      {
+        continue;
+      }
+      SegmentWalk sw;
+      loadSegmentWalk(b, raw, sw);
+      const uint32_t ray = sw.ray;
       auto count_visit = [&](uint32_t idx) {
         const uint32_t shift = (idx & 1u) * 16u;
-        const uint32_t old = atomicAdd(&tile[idx >> 1], 1u << shift);
+        const uint32_t old = atomicAdd(&tile[tileWord(idx)], 1u << shift);
         if ((old >> shift) & kTileFlag)
         {
-          const unsigned group = __activemask();
-          const uint32_t n = (uint32_t)__popc(group);
-          const uint32_t rank = (uint32_t)__popc(group & ((1u << (tid & 31u)) - 1u));
-          uint32_t at = 0;
-          if (rank == 0)
-          {
-            const unsigned long long state = atomicAdd(&record_chunk[warp], (unsigned long long)n);
-            const uint32_t used = (uint32_t)state;
-            if (used + n <= kRecordChunk)
-            {
-              at = (uint32_t)(state >> 32) + used;
-            }
-            else
-            {
-              at = atomicAdd(&b.counters->record_count, kRecordChunk);
-              atomicExch(&record_chunk[warp], ((unsigned long long)at << 32) | n);
-            }
-          }
-          at = __shfl_sync(group, at, __ffs(group) - 1) + rank;
+          const uint32_t at = reserveRecord(&record_chunk[warp], &b.counters->record_count);
           if (at < b.record_capacity)
           {
             b.record_vid[at] = vbase + idx;
@@ -768,25 +871,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsNdt(const __grid_c
         else if ((kind[idx >> 5] >> (idx & 31u)) & 1u)
         {
           // Established Gaussian: evaluated later, one thread per visit (ndtGaussianMisses).
-          const unsigned group = __activemask();
-          const uint32_t n = (uint32_t)__popc(group);
-          const uint32_t rank = (uint32_t)__popc(group & ((1u << (tid & 31u)) - 1u));
-          uint32_t at = 0;
-          if (rank == 0)
-          {
-            const unsigned long long state = atomicAdd(&gauss_chunk[warp], (unsigned long long)n);
-            const uint32_t used = (uint32_t)state;
-            if (used + n <= kRecordChunk)
-            {
-              at = (uint32_t)(state >> 32) + used;
-            }
-            else
-            {
-              at = atomicAdd(&b.counters->gauss_count, kRecordChunk);
-              atomicExch(&gauss_chunk[warp], ((unsigned long long)at << 32) | n);
-            }
-          }
-          at = __shfl_sync(group, at, __ffs(group) - 1) + rank;
+          const uint32_t at = reserveRecord(&gauss_chunk[warp], &b.counters->gauss_count);
           if (at < b.gauss_capacity)
           {
             b.gauss_keys[at] = ((unsigned long long)(vbase + idx) << 32) | ray;
@@ -801,7 +886,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsNdt(const __grid_c
       if (dm.traversal)
       {
         const int dx = g.dim[0], dxy = g.dim[0] * g.dim[1];
-        resumeSegment<true>(init, delta, local0, total, flags, st, visits, b.ray_length[ray], g,
+        resumeSegment<true>(sw.init, sw.delta, sw.local0, sw.total, sw.flags, sw.st, sw.visits, b.ray_length[ray], g,
                             [&](const int l[3], double t_enter, double t_exit, bool last_of_ray) {
                               const uint32_t idx = (uint32_t)(l[0] + l[1] * dx + l[2] * dxy);
                               count_visit(idx);
@@ -814,7 +899,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsNdt(const __grid_c
       }
       else
       {
-        resumeSegmentFast(init, delta, entry, total, flags, st, visits, g, count_visit);
+        resumeSegmentFast(sw.init, sw.delta, sw.entry, sw.total, sw.flags, sw.st, sw.visits, g, count_visit);
       }
     }
     __syncthreads();
@@ -822,43 +907,50 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsNdt(const __grid_c
     // Fold.  Plain voxels: k identical misses (RayMapperNdt applies no exclusion flags).  Gaussian voxels: the
     // adjustments are already in the slab; apply occupancyAdjustDown's clamp.
     float *occ = dm.occupancy + (size_t)vbase;
-    for (uint32_t v = tid; v < g.vpr; v += blockDim.x)
+    const uint4 *tile4 = reinterpret_cast<const uint4 *>(tile);
+    for (uint32_t c = tid; c < ((g.vpr + 7u) >> 3); c += blockDim.x)
     {
-      const uint32_t half = (tile[v >> 1] >> ((v & 1u) * 16u)) & 0xffffu;
-      if (half == 0 || (half & kTileFlag))
+      const uint4 t = tile4[tileGroup(c)];
+      const uint32_t w4[4] = { t.x, t.y, t.z, t.w };
+      const uint32_t gauss8 = (kind[c >> 2] >> ((c & 3u) * 8u)) & 0xffu;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
       {
-        continue;
-      }
-      if ((kind[v >> 5] >> (v & 31u)) & 1u)
-      {
-        continue;  // Gaussian voxel: handled by ndtGaussianMisses / ndtClampGaussians
-      }
-      const bool gaussian = false;
-      if (dm.hit_miss)
-      {
-        atomicAdd(&dm.hit_miss[vbase + v].y, half);  // every plain NDT miss counts as a miss
-      }
-      int *addr = reinterpret_cast<int *>(occ + v);
-      int seen = *reinterpret_cast<volatile int *>(addr);
-      for (;;)
-      {
-        const float cur = __int_as_float(seen);
-        const float next = gaussian ? fmaxf(mp.min_value, cur) : missRepeat(cur, half, mp, 0u);
-        if (__float_as_int(next) == seen)
+        const uint32_t half = (w4[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+        const uint32_t v = c * 8u + (uint32_t)k;
+        if (half == 0 || (half & kTileFlag) || v >= g.vpr)
         {
-          break;
+          continue;
         }
-        if (!item.shared)
+        if ((gauss8 >> k) & 1u)
         {
-          occ[v] = next;  // this CTA is the only writer of the region in this batch
-          break;
+          continue;  // Gaussian voxel: handled by ndtGaussianMisses / ndtClampGaussians
         }
-        const int prev = atomicCAS(addr, seen, __float_as_int(next));
-        if (prev == seen)
+        if (dm.hit_miss)
         {
-          break;
+          atomicAdd(&dm.hit_miss[vbase + v].y, half);  // every plain NDT miss counts as a miss
         }
-        seen = prev;
+        int *addr = reinterpret_cast<int *>(occ + v);
+        int seen = *reinterpret_cast<volatile int *>(addr);
+        for (;;)
+        {
+          const float next = missRepeat(__int_as_float(seen), half, mp, 0u);
+          if (__float_as_int(next) == seen)
+          {
+            break;
+          }
+          if (!item.shared)
+          {
+            occ[v] = next;  // this CTA is the only writer of the region in this batch
+            break;
+          }
+          const int prev = atomicCAS(addr, seen, __float_as_int(next));
+          if (prev == seen)
+          {
+            break;
+          }
+          seen = prev;
+        }
       }
     }
   }
@@ -1011,6 +1103,7 @@ __global__ void __launch_bounds__(128) applySamplesNdt(DeviceMap dm, Geom g, Map
     }
     dm.occupancy[vid] = value;
     dm.mean[vid] = vm;
+    setVoxelBit(dm, g, vid, vm.y >= mp.sample_threshold);
 #pragma unroll
     for (int c = 0; c < 6; ++c)
     {

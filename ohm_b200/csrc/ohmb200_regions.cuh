@@ -18,7 +18,26 @@ namespace ohmb200
 constexpr unsigned kRecValid = 1u << 3, kRecExcludeStart = 1u << 4, kRecExcludeEnd = 1u << 5;
 constexpr uint32_t kMaxSegmentsPerItem = 2048;  // < 32768: tile counters are 15 bit + flag
 constexpr uint32_t kRecordChunk = 256;
-constexpr uint32_t kStageSegments = 32;  // segments per ray that pass A hands to pass B without a second enumeration         // ordered-miss records are reserved per warp in chunks
+// Counter tile addressing.  Two u16 counters per 32-bit word; the word index is XOR-swizzled in bits 2..4 with a hash of
+// the higher bits (the y and z coordinates of the voxel), so lanes walking the same x/y column at different heights —
+// a lidar's elevation fan — spread over the shared-memory banks instead of queueing on one.  Groups of four words stay
+// together (128-bit accesses of the fold remain valid).  A tile holds tileWords() words (a multiple of 32).
+OHMB200_HD __forceinline__ uint32_t tileWords(uint32_t vpr)
+{
+  return (((vpr + 1u) >> 1) + 31u) & ~31u;
+}
+OHMB200_HD __forceinline__ uint32_t tileWord(uint32_t voxel)
+{
+  const uint32_t w = voxel >> 1;
+  const uint32_t u = w >> 5;
+  return w ^ (((u ^ (u >> 3) ^ (u >> 6)) & 7u) << 2);
+}
+OHMB200_HD __forceinline__ uint32_t tileGroup(uint32_t group)  // group = word index / 4
+{
+  const uint32_t u = group >> 3;
+  return group ^ ((u ^ (u >> 3) ^ (u >> 6)) & 7u);
+}
+constexpr uint32_t kStageSegments = 96;  // segments per ray that pass A hands to pass B without a second enumeration         // ordered-miss records are reserved per warp in chunks
 constexpr uint32_t kTileFlag = 0x8000u;
 
 // Walk constants of one ray (64 bytes).

@@ -75,35 +75,120 @@ __device__ __forceinline__ void tsdfLoadRay(const Batch &b, uint32_t ray, TsdfRa
   geo.distance_g = (float)sqrt((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]);
 }
 
-// Pass 1: flag every voxel whose visits must be replayed in order.  flags: one bit per voxel, [capacity][vpr/32].
-// Pass 2 (kCount): count far visits of unflagged voxels in the tile, record every visit of flagged voxels, fold.
-template <bool kCount>
+// Persistent per-voxel bit (dm.voxel_bits): "the stored state is not order-free".  Rewritten wherever the TSDF layer is:
+// replayTsdf, ohmb200_write_region, a change of the truncation distance.  (The fold only touches order-free voxels and
+// leaves them order-free.)
+// Pass 1, one thread per ray: flag (per-batch `near` bits) the voxels this ray visits at sdf < far threshold.  Only the
+// last tsdfNearSteps() voxels of a walk can qualify, so a lane looks at its last one or two staged segments.
+__global__ void __launch_bounds__(128) markTsdfNear(const __grid_constant__ DeviceMap dm, const __grid_constant__ Geom g,
+                                                    const __grid_constant__ MapParams mp, const __grid_constant__ Batch b,
+                                                    uint32_t *near)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b.n || mp.tsdf_dropoff > 0)  // with a dropoff nothing commutes: the count pass flags every voxel itself
+  {
+    return;
+  }
+  const uint32_t staged = b.stage_count[i];
+  if (staged == 0)
+  {
+    return;
+  }
+  RayRec rec;
+  loadRec(rec, b.recs + i);
+  const float far_threshold = tsdfFarThreshold(mp);
+  const int near_steps = tsdfNearSteps(mp, g);
+  const uint32_t flag_words = (g.vpr + 31u) >> 5;
+  const int total[3] = { rec.total[0], rec.total[1], rec.total[2] };
+  const int local0[3] = { rec.local[0], rec.local[1], rec.local[2] };
+  const int steps_total = total[0] + total[1] + total[2];
+  const int dx = g.dim[0], dxy = g.dim[0] * g.dim[1];
+  TsdfRayGeometry geo;
+  tsdfLoadRay(b, i, geo);
+  // returns false when the segment (and so every earlier one) ends too far from the end of the walk
+  auto mark_segment = [&](uint32_t slot, const int st[3], int visits) -> bool {
+    const int q_entry = st[0] + st[1] + st[2];
+    if (steps_total - (q_entry + visits - 1) > near_steps)
+    {
+      return false;
+    }
+    int region[3];
+    unpackRegion(dm.keys[slot], region);
+    uint32_t *region_flags = near + (size_t)slot * flag_words;
+    int q = q_entry;
+    resumeSegment<false>(rec.initial, rec.delta, local0, total, rec.flags, st, visits, 0.0, g,
+                         [&](const int l[3], double, double, bool) {
+                           if (steps_total - q <= near_steps)
+                           {
+                             const double centre[3] = { voxelCentreAxis(g, region[0], l[0], 0),
+                                                        voxelCentreAxis(g, region[1], l[1], 1),
+                                                        voxelCentreAxis(g, region[2], l[2], 2) };
+                             const float sdf = tsdfDistance(geo.sensor, geo.sample, centre, geo.distance_g);
+                             if (!(sdf >= far_threshold))
+                             {
+                               const uint32_t idx = (uint32_t)(l[0] + l[1] * dx + l[2] * dxy);
+                               atomicOr(&region_flags[idx >> 5], 1u << (idx & 31u));
+                             }
+                           }
+                           ++q;
+                         });
+    return true;
+  };
+  if (staged <= kStageSegments)
+  {
+    for (uint32_t k = staged; k-- > 0;)
+    {
+      const uint4 raw = b.stage[(size_t)k * b.stage_stride + i];
+      const int st[3] = { (int)(raw.y & 0xffffu), (int)(raw.y >> 16), (int)(raw.z & 0xffffu) };
+      if (!mark_segment(raw.x, st, (int)(raw.z >> 16)))
+      {
+        break;
+      }
+    }
+  }
+  else
+  {
+    enumerateSegments(rec, g, [&](const int r[3], const int st[3], const int entry[3], int n) {
+      (void)entry;
+      if (!ownsRegion(dm, r))
+      {
+        return;
+      }
+      const int slot = regionFind(dm, packRegion(r[0], r[1], r[2]));
+      if (slot >= 0)
+      {
+        mark_segment((uint32_t)slot, st, n);
+      }
+    });
+  }
+}
+
+// Pass 2: count far visits of unflagged voxels in the tile, record every visit of flagged voxels (stored state not
+// order-free, or near a sample in this batch), fold the counts.
 __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsTsdf(const __grid_constant__ DeviceMap dm,
                                                                    const __grid_constant__ Geom g,
                                                                    const __grid_constant__ MapParams mp,
-                                                                   const __grid_constant__ Batch b, uint32_t *flags)
+                                                                   const __grid_constant__ Batch b, const uint32_t *near)
 {
   extern __shared__ uint32_t tile[];
   __shared__ WorkItem item;
   __shared__ unsigned long long record_chunk[kWalkThreads / 32];
-  const uint32_t words = (g.vpr + 1u) >> 1;
+  __shared__ SegmentQueue queue;
+  const uint32_t words = tileWords(g.vpr);
   const uint32_t flag_words = (g.vpr + 31u) >> 5;
   const uint32_t tid = threadIdx.x;
   const uint32_t warp = tid >> 5;
-  const float far_threshold = tsdfFarThreshold(mp);
   const bool all_ordered = mp.tsdf_dropoff > 0;  // weights depend on sdf: nothing commutes
-  const int near_steps = tsdfNearSteps(mp, g);
   if ((tid & 31u) == 0)
   {
     record_chunk[warp] = (unsigned long long)kRecordChunk;
   }
-  uint32_t *work_counter = kCount ? &b.counters->work_next : &b.counters->run_count;  // run_count is free in TSDF mode
   for (;;)
   {
     __syncthreads();
     if (tid == 0)
     {
-      const uint32_t w = atomicAdd(work_counter, 1u);
+      const uint32_t w = atomicAdd(&b.counters->work_next, 1u);
       if (w < min(b.counters->item_count, b.item_capacity))
       {
         item = b.items[w];
@@ -120,161 +205,111 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsTsdf(const __grid_
     }
     const uint32_t slot = item.slot;
     const uint32_t vbase = slot * g.vpr;
-    uint32_t *region_flags = flags + (size_t)slot * flag_words;
-    int region[3];
-    unpackRegion(dm.keys[slot], region);
-    if (kCount)
     {
-      for (uint32_t w = tid; w < words; w += blockDim.x)
+      uint4 *tile4 = reinterpret_cast<uint4 *>(tile);
+      const uint32_t fill = all_ordered ? (kTileFlag | (kTileFlag << 16)) : 0u;
+      for (uint32_t w = tid; w < (words >> 2); w += blockDim.x)
       {
-        tile[w] = 0;
+        tile4[w] = make_uint4(fill, fill, fill, fill);
       }
-      __syncthreads();
-      for (uint32_t v = tid; v < g.vpr; v += blockDim.x)
-      {
-        if ((region_flags[v >> 5] >> (v & 31u)) & 1u)
-        {
-          atomicOr(&tile[v >> 1], kTileFlag << ((v & 1u) * 16u));
-        }
-      }
-      __syncthreads();
-    }
-    else
-    {
-      // stored states that are not order-free (only the first item of a region needs to do this; all do, idempotently)
-      for (uint32_t v = tid; v < g.vpr; v += blockDim.x)
-      {
-        if (all_ordered || !tsdfOrderFree(dm.tsdf[vbase + v], mp))
-        {
-          atomicOr(&region_flags[v >> 5], 1u << (v & 31u));
-        }
-      }
-    }
-
-    for (uint32_t s = item.begin + tid; s < item.end; s += blockDim.x)
-    {
-      const uint4 raw = reinterpret_cast<const uint4 *>(b.segments)[s];
-      const uint32_t ray = raw.x;
-      const int st[3] = { (int)(raw.y & 0xffffu), (int)(raw.y >> 16), (int)(raw.z & 0xffffu) };
-      const int visits = (int)(raw.z >> 16);
-      const RayRec *rp = b.recs + ray;
-      const uint4 tail = reinterpret_cast<const uint4 *>(rp)[3];
-      const uint32_t rflags = (tail.z >> 8) & 0xffu;
-      const int total[3] = { (int)(tail.z >> 16), (int)(tail.w & 0xffffu), (int)(tail.w >> 16) };
-      const int local0[3] = { (int)((tail.y >> 16) & 0xffu), (int)(tail.y >> 24), (int)(tail.z & 0xffu) };
-      const double init[3] = { rp->initial[0], rp->initial[1], rp->initial[2] };
-      const double delta[3] = { rp->delta[0], rp->delta[1], rp->delta[2] };
-      const int dx = g.dim[0], dxy = g.dim[0] * g.dim[1];
-      if (kCount)
-      {
-        const int entry[3] = { (int)(raw.w & 0xffu), (int)((raw.w >> 8) & 0xffu), (int)((raw.w >> 16) & 0xffu) };
-        resumeSegmentFast(init, delta, entry, total, rflags, st, visits, g, [&](uint32_t idx) {
-          const uint32_t shift = (idx & 1u) * 16u;
-          const uint32_t old = atomicAdd(&tile[idx >> 1], 1u << shift);
-          if ((old >> shift) & kTileFlag)
-          {
-            const unsigned group = __activemask();
-            const uint32_t n = (uint32_t)__popc(group);
-            const uint32_t rank = (uint32_t)__popc(group & ((1u << (tid & 31u)) - 1u));
-            uint32_t at = 0;
-            if (rank == 0)
-            {
-              const unsigned long long state = atomicAdd(&record_chunk[warp], (unsigned long long)n);
-              const uint32_t used = (uint32_t)state;
-              if (used + n <= kRecordChunk)
-              {
-                at = (uint32_t)(state >> 32) + used;
-              }
-              else
-              {
-                at = atomicAdd(&b.counters->record_count, kRecordChunk);
-                atomicExch(&record_chunk[warp], ((unsigned long long)at << 32) | n);
-              }
-            }
-            at = __shfl_sync(group, at, __ffs(group) - 1) + rank;
-            if (at < b.record_capacity)
-            {
-              b.record_keys[at] = ((unsigned long long)(vbase + idx) << 32) | ray;
-            }
-            else
-            {
-              b.counters->record_overflow = 1;
-              b.counters->overflow_seen = 1;
-            }
-          }
-        });
-      }
-      else if (!all_ordered)
-      {
-        // Only the last `near_steps` voxels of a walk can be near the sample: skip segments that end earlier.
-        const int steps_total = total[0] + total[1] + total[2];
-        const int q_entry = st[0] + st[1] + st[2];
-        if (steps_total - (q_entry + visits - 1) <= near_steps)
-        {
-          const int dx = g.dim[0], dxy = g.dim[0] * g.dim[1];
-          TsdfRayGeometry geo;
-          tsdfLoadRay(b, ray, geo);
-          int q = q_entry;
-          resumeSegment<false>(init, delta, local0, total, rflags, st, visits, 0.0, g,
-                               [&](const int l[3], double, double, bool) {
-                                 if (steps_total - q <= near_steps)
-                                 {
-                                   const double centre[3] = { voxelCentreAxis(g, region[0], l[0], 0),
-                                                              voxelCentreAxis(g, region[1], l[1], 1),
-                                                              voxelCentreAxis(g, region[2], l[2], 2) };
-                                   const float sdf = tsdfDistance(geo.sensor, geo.sample, centre, geo.distance_g);
-                                   if (!(sdf >= far_threshold))
-                                   {
-                                     const uint32_t idx = (uint32_t)(l[0] + l[1] * dx + l[2] * dxy);
-                                     atomicOr(&region_flags[idx >> 5], 1u << (idx & 31u));
-                                   }
-                                 }
-                                 ++q;
-                               });
-        }
-      }
-    }
-    if (!kCount)
-    {
-      continue;
     }
     __syncthreads();
-    // Fold: k commuting far visits -> (trunc, min(w + 1, max) k times).
-    float2 *slab = dm.tsdf + (size_t)vbase;
-    for (uint32_t v = tid; v < g.vpr; v += blockDim.x)
+    if (!all_ordered)
     {
-      const uint32_t half = (tile[v >> 1] >> ((v & 1u) * 16u)) & 0xffffu;
-      if (half == 0 || (half & kTileFlag))
+      const uint32_t *ordered_bits = dm.voxel_bits + (size_t)slot * flag_words;
+      const uint32_t *near_bits = near + (size_t)slot * flag_words;
+      for (uint32_t w = tid; w < flag_words; w += blockDim.x)
+      {
+        uint32_t bits = ordered_bits[w] | near_bits[w];
+        while (bits)
+        {
+          const uint32_t v = (w << 5) + (uint32_t)__ffs(bits) - 1u;
+          bits &= bits - 1u;
+          atomicOr(&tile[tileWord(v)], kTileFlag << ((v & 1u) * 16u));
+        }
+      }
+    }
+    queueBuild(queue, b, item);
+
+    for (;;)
+    {
+      uint4 raw;
+      const int got = queuePop(queue, b, item, raw);
+      if (got == 0)
+      {
+        break;
+      }
+      if (got == 2)
       {
         continue;
       }
-      unsigned long long *addr = reinterpret_cast<unsigned long long *>(slab + v);
-      unsigned long long seen = *reinterpret_cast<volatile unsigned long long *>(addr);
-      for (;;)
-      {
-        float w = __uint_as_float((uint32_t)seen);
-        for (uint32_t k = 0; k < half; ++k)
+      SegmentWalk sw;
+      loadSegmentWalk(b, raw, sw);
+      const uint32_t ray = sw.ray;
+      resumeSegmentFast(sw.init, sw.delta, sw.entry, sw.total, sw.flags, sw.st, sw.visits, g, [&](uint32_t idx) {
+        const uint32_t shift = (idx & 1u) * 16u;
+        const uint32_t old = atomicAdd(&tile[tileWord(idx)], 1u << shift);
+        if ((old >> shift) & kTileFlag)
         {
-          const float next = fminf(w + 1.0f, mp.tsdf_max_weight);
-          if (next == w)
+          const uint32_t at = reserveRecord(&record_chunk[warp], &b.counters->record_count);
+          if (at < b.record_capacity)
+          {
+            b.record_keys[at] = ((unsigned long long)(vbase + idx) << 32) | ray;
+          }
+          else
+          {
+            b.counters->record_overflow = 1;
+            b.counters->overflow_seen = 1;
+          }
+        }
+      });
+    }
+    __syncthreads();
+
+    // Fold: k commuting far visits -> (trunc, min(w + 1, max) k times).
+    float2 *slab = dm.tsdf + (size_t)vbase;
+    const uint4 *tile4 = reinterpret_cast<const uint4 *>(tile);
+    for (uint32_t c = tid; c < ((g.vpr + 7u) >> 3); c += blockDim.x)
+    {
+      const uint4 t = tile4[tileGroup(c)];
+      const uint32_t w4[4] = { t.x, t.y, t.z, t.w };
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+      {
+        const uint32_t half = (w4[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+        const uint32_t v = c * 8u + (uint32_t)k;
+        if (half == 0 || (half & kTileFlag) || v >= g.vpr)
+        {
+          continue;
+        }
+        unsigned long long *addr = reinterpret_cast<unsigned long long *>(slab + v);
+        unsigned long long seen = *reinterpret_cast<volatile unsigned long long *>(addr);
+        for (;;)
+        {
+          float w = __uint_as_float((uint32_t)seen);
+          for (uint32_t n = 0; n < half; ++n)
+          {
+            const float next = fminf(w + 1.0f, mp.tsdf_max_weight);
+            if (next == w)
+            {
+              break;
+            }
+            w = next;
+          }
+          const unsigned long long want =
+            (unsigned long long)__float_as_uint(w) | ((unsigned long long)__float_as_uint(mp.tsdf_trunc) << 32);
+          if (!item.shared)
+          {
+            *addr = want;
+            break;
+          }
+          const unsigned long long prev = atomicCAS(addr, seen, want);
+          if (prev == seen)
           {
             break;
           }
-          w = next;
+          seen = prev;
         }
-        const unsigned long long want =
-          (unsigned long long)__float_as_uint(w) | ((unsigned long long)__float_as_uint(mp.tsdf_trunc) << 32);
-        if (!item.shared)
-        {
-          *addr = want;
-          break;
-        }
-        const unsigned long long prev = atomicCAS(addr, seen, want);
-        if (prev == seen)
-        {
-          break;
-        }
-        seen = prev;
       }
     }
   }
@@ -315,4 +350,47 @@ __global__ void __launch_bounds__(128) replayTsdf(DeviceMap dm, Geom g, MapParam
     tsdfUpdate(tsdfDistance(geo.sensor, geo.sample, centre, geo.distance_g), mp, state.x, state.y);
   }
   dm.tsdf[vid] = state;
+  setVoxelBit(dm, g, vid, !tsdfOrderFree(state, mp));
+}
+
+// Clears the per-batch near bits of the regions this batch walked.
+__global__ void clearTouchedBits(Batch b, uint32_t *bits, uint32_t words_per_region)
+{
+  const uint32_t touched = b.counters->touched_count;
+  for (uint32_t t = blockIdx.x; t < touched; t += gridDim.x)
+  {
+    uint32_t *region = bits + (size_t)b.touched_list[t] * words_per_region;
+    for (uint32_t w = threadIdx.x; w < words_per_region; w += blockDim.x)
+    {
+      region[w] = 0;
+    }
+  }
+}
+
+// dm.voxel_bits of the regions in slots [first, first + gridDim.x), from the stored layers.
+//   NDT:  bit = voxel mean count >= sample threshold ("established Gaussian")
+//   TSDF: bit = stored (weight, distance) is not order-free
+__global__ void recomputeVoxelBits(DeviceMap dm, Geom g, MapParams mp, int tsdf_mode, uint32_t first)
+{
+  const uint32_t slot = first + blockIdx.x;
+  if (slot >= dm.capacity || dm.keys[slot] == kEmptyKey)
+  {
+    return;
+  }
+  const uint32_t flag_words = (g.vpr + 31u) >> 5;
+  const uint32_t vbase = slot * g.vpr;
+  for (uint32_t base = (threadIdx.x >> 5) << 5; base < g.vpr; base += blockDim.x)
+  {
+    const uint32_t v = base + (threadIdx.x & 31u);
+    bool bit = false;
+    if (v < g.vpr)
+    {
+      bit = tsdf_mode ? !tsdfOrderFree(dm.tsdf[vbase + v], mp) : dm.mean[vbase + v].y >= mp.sample_threshold;
+    }
+    const uint32_t word = __ballot_sync(0xffffffffu, bit);
+    if ((threadIdx.x & 31u) == 0)
+    {
+      dm.voxel_bits[(size_t)slot * flag_words + (base >> 5)] = word;
+    }
+  }
 }

@@ -89,6 +89,16 @@ def run(mode, resolution, sweeps, cpu_sweeps, device_gib):
     out["regions"] = int(len(keys))
     g.close()
 
+    # per-kernel times (event pairs around every launch; serialises the side stream, so the sum exceeds ms_per_sweep)
+    g = cls(resolution, device_bytes=int(device_gib * (1 << 30)))
+    g.set_stream(stream.cuda_stream)
+    g.set_profiling(True)
+    for t in d_rays:
+        g.integrate_rays_device(t.data_ptr(), t.shape[0])
+    g.sync_voxels()
+    out["kernels_ms_per_sweep"] = {k: v["ms"] / sweeps for k, v in g.kernel_times().items() if v["launches"]}
+    g.close()
+
     # end to end: host rays through the reference-facing call + download of every layer
     g = cls(resolution, device_bytes=int(device_gib * (1 << 30)))
     t0 = time.perf_counter()
