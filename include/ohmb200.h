@@ -187,6 +187,16 @@ OHMB200_API int ohmb200_read_region(ohmb200_map *map, const int16_t key_xyz[3], 
 OHMB200_API int ohmb200_read_regions(ohmb200_map *map, int layer, const int16_t *keys_xyz, size_t count, void *dst,
                                      size_t bytes);
 
+/* The asynchronous form of the same (GpuLayerCache::syncToMainMemory queues the downloads and returns; the wait is
+ * GpuLayerCache::updateEvents / GpuMap::syncVoxels, ohmgpu/GpuLayerCache.cpp:229-241,300-321,670-713): the chunks are
+ * snapshotted on the device in stream order — batches integrated after this call do not show in them — and copied to
+ * `dst` on a separate stream while those batches run.  `dst` (pinned memory for a real overlap) must stay valid until
+ * ohmb200_download_wait returns; at most two downloads are in flight, a third call waits for the first.
+ * A key that is not resident is reported by ohmb200_download_wait (OHMB200_E_NOT_FOUND; its chunk is left untouched). */
+OHMB200_API int ohmb200_read_regions_async(ohmb200_map *map, int layer, const int16_t *keys_xyz, size_t count,
+                                           void *dst, size_t bytes);
+OHMB200_API int ohmb200_download_wait(ohmb200_map *map);
+
 /* GpuLayerCache::upload (ohmgpu/GpuLayerCache.cpp:172-182): make the region resident (creating it if absent)
  * and overwrite one layer chunk from host memory. */
 OHMB200_API int ohmb200_write_region(ohmb200_map *map, const int16_t key_xyz[3], int layer, const void *src,

@@ -490,6 +490,84 @@ __global__ void gatherRegions(const uint4 *slab, const uint32_t *slots, uint4 *d
   }
 }
 
+// ohmb200_clear: wipe only the regions that exist (the slabs of free slots are clean already), then free the table.
+struct ClearTable
+{
+  uint32_t *base[OHMB200_LAYER_COUNT + 3];   // layer slabs, then voxel_bits, near bits, pending
+  uint32_t words[OHMB200_LAYER_COUNT + 3];   // 32-bit words per region
+  uint32_t fill[OHMB200_LAYER_COUNT + 3];
+  int count;
+};
+
+__global__ void __launch_bounds__(256) clearLiveRegions(DeviceMap dm, ClearTable table)
+{
+  for (uint32_t slot = blockIdx.x; slot < dm.capacity; slot += gridDim.x)
+  {
+    if (dm.keys[slot] == kEmptyKey)
+    {
+      continue;
+    }
+    for (int l = 0; l < table.count; ++l)
+    {
+      uint32_t *chunk = table.base[l] + (size_t)slot * table.words[l];
+      const uint32_t fill = table.fill[l];
+      if ((table.words[l] & 3u) == 0)
+      {
+        uint4 *chunk4 = reinterpret_cast<uint4 *>(chunk);
+        for (uint32_t w = threadIdx.x; w < (table.words[l] >> 2); w += blockDim.x)
+        {
+          chunk4[w] = make_uint4(fill, fill, fill, fill);
+        }
+      }
+      else
+      {
+        for (uint32_t w = threadIdx.x; w < table.words[l]; w += blockDim.x)
+        {
+          chunk[w] = fill;
+        }
+      }
+    }
+    __syncthreads();  // every thread has read keys[slot] before it is freed
+    if (threadIdx.x == 0)
+    {
+      dm.keys[slot] = kEmptyKey;
+      dm.region_stamp[slot] = 0;
+    }
+  }
+}
+
+// Region key -> slab slot for a list of keys (0xFFFFFFFF and *missing = 1 when a key is not resident).
+__global__ void lookupSlots(DeviceMap dm, const unsigned long long *keys, uint32_t count, uint32_t *slots, int *missing)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count)
+  {
+    return;
+  }
+  const int slot = regionFind(dm, keys[i]);
+  slots[i] = (uint32_t)slot;
+  if (slot < 0)
+  {
+    *missing = 1;
+  }
+}
+
+// gatherRegions for a slot list that may hold 0xFFFFFFFF (left untouched).
+__global__ void gatherRegionsChecked(const uint4 *slab, const uint32_t *slots, uint4 *dst, size_t vec_per_region)
+{
+  const uint32_t slot = slots[blockIdx.x];
+  if (slot == 0xFFFFFFFFu)
+  {
+    return;
+  }
+  const uint4 *src = slab + (size_t)slot * vec_per_region;
+  uint4 *out = dst + (size_t)blockIdx.x * vec_per_region;
+  for (size_t i = threadIdx.x; i < vec_per_region; i += blockDim.x)
+  {
+    out[i] = src[i];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Host-side map
 // ---------------------------------------------------------------------------------------------------------
@@ -572,6 +650,19 @@ struct ohmb200_map
   size_t gather_bytes = 0;
   uint32_t *d_gather_slots = nullptr;
   size_t gather_slots_cap = 0;
+  // asynchronous download (ohmb200_read_regions_async): two staging sets, D2H on its own stream
+  cudaStream_t download_stream = nullptr;
+  void *d_stage[2] = { nullptr, nullptr };
+  size_t stage_bytes[2] = { 0, 0 };
+  unsigned long long *d_stage_keys[2] = { nullptr, nullptr };
+  unsigned long long *h_stage_keys[2] = { nullptr, nullptr };  // pinned
+  uint32_t *d_stage_slots[2] = { nullptr, nullptr };
+  size_t stage_keys_cap[2] = { 0, 0 };
+  cudaEvent_t stage_gathered[2] = { nullptr, nullptr };
+  cudaEvent_t stage_done[2] = { nullptr, nullptr };
+  bool stage_pending[2] = { false, false };
+  int stage_next = 0;
+  int *d_lookup_missing = nullptr;  // device flag: an asynchronous download named a region that is not resident
   // profiling
   bool profiling = false;
   std::vector<cudaEvent_t> event_pool;
@@ -971,7 +1062,7 @@ int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_i
     {
       {
         KernelScope scope(m, kKLink);
-        linkRecords<<<m->sm_count * 4, 256, 0, s>>>(b);
+        linkRecords<<<m->sm_count * 4, 256, 0, s>>>(b, (m->mode == OHMB200_MODE_NDT || m->mode == OHMB200_MODE_NDT_TM) ? 1 : 0);
       }
       {
         KernelScope scope(m, kKSamples);
@@ -1387,6 +1478,23 @@ void ohmb200_destroy(ohmb200_map *m)
   {
     cudaStreamDestroy(m->own_stream);
   }
+  for (int i = 0; i < 2; ++i)
+  {
+    cudaFree(m->d_stage[i]);
+    cudaFree(m->d_stage_keys[i]);
+    cudaFree(m->d_stage_slots[i]);
+    cudaFreeHost(m->h_stage_keys[i]);
+    if (m->stage_gathered[i])
+    {
+      cudaEventDestroy(m->stage_gathered[i]);
+      cudaEventDestroy(m->stage_done[i]);
+    }
+  }
+  cudaFree(m->d_lookup_missing);
+  if (m->download_stream)
+  {
+    cudaStreamDestroy(m->download_stream);
+  }
   if (m->copy_stream)
   {
     cudaStreamDestroy(m->copy_stream);
@@ -1695,6 +1803,112 @@ int ohmb200_read_region(ohmb200_map *m, const int16_t key_xyz[3], int layer, voi
   return ohmb200_read_regions(m, layer, key_xyz, 1, dst, bytes);
 }
 
+int ohmb200_read_regions_async(ohmb200_map *m, int layer, const int16_t *keys_xyz, size_t count, void *dst, size_t bytes)
+{
+  if (!m || layer < 0 || layer >= OHMB200_LAYER_COUNT || !m->layer_slab[layer] || (!keys_xyz && count) || !dst)
+  {
+    return setError(OHMB200_E_INVALID, "ohmb200_read_regions_async: bad arguments or layer %d absent", layer);
+  }
+  const size_t chunk = m->region_layer_bytes[layer];
+  if (bytes < chunk * count)
+  {
+    return setError(OHMB200_E_INVALID, "destination too small: %zu < %zu", bytes, chunk * count);
+  }
+  if (chunk % 16 != 0)
+  {
+    return setError(OHMB200_E_INVALID, "asynchronous download needs 16-byte multiple chunks");
+  }
+  if (count == 0)
+  {
+    return OHMB200_OK;
+  }
+  cudaSetDevice(m->device);
+  if (!m->download_stream)
+  {
+    CUDA_TRY(cudaStreamCreateWithFlags(&m->download_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i)
+    {
+      CUDA_TRY(cudaEventCreateWithFlags(&m->stage_gathered[i], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&m->stage_done[i], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaMalloc(&m->d_lookup_missing, sizeof(int)));
+    CUDA_TRY(cudaMemsetAsync(m->d_lookup_missing, 0, sizeof(int), m->stream));
+  }
+  const int buf = m->stage_next;
+  m->stage_next ^= 1;
+  if (m->stage_pending[buf])
+  {
+    CUDA_TRY(cudaEventSynchronize(m->stage_done[buf]));  // the staging set is reused every second call
+    m->stage_pending[buf] = false;
+  }
+  if (chunk * count > m->stage_bytes[buf])
+  {
+    cudaFree(m->d_stage[buf]);
+    m->stage_bytes[buf] = 0;
+    CUDA_TRY(cudaMalloc(&m->d_stage[buf], chunk * count));
+    m->stage_bytes[buf] = chunk * count;
+  }
+  if (count > m->stage_keys_cap[buf])
+  {
+    cudaFree(m->d_stage_keys[buf]);
+    cudaFree(m->d_stage_slots[buf]);
+    cudaFreeHost(m->h_stage_keys[buf]);
+    m->stage_keys_cap[buf] = 0;
+    CUDA_TRY(cudaMalloc(&m->d_stage_keys[buf], sizeof(unsigned long long) * count));
+    CUDA_TRY(cudaMalloc(&m->d_stage_slots[buf], sizeof(uint32_t) * count));
+    CUDA_TRY(cudaMallocHost(&m->h_stage_keys[buf], sizeof(unsigned long long) * count));
+    m->stage_keys_cap[buf] = count;
+  }
+  for (size_t i = 0; i < count; ++i)
+  {
+    m->h_stage_keys[buf][i] = (unsigned long long)(uint16_t)keys_xyz[3 * i] |
+                              ((unsigned long long)(uint16_t)keys_xyz[3 * i + 1] << 16) |
+                              ((unsigned long long)(uint16_t)keys_xyz[3 * i + 2] << 32);
+  }
+  cudaStream_t s = m->stream;
+  CUDA_TRY(cudaMemcpyAsync(m->d_stage_keys[buf], m->h_stage_keys[buf], sizeof(unsigned long long) * count,
+                           cudaMemcpyHostToDevice, s));
+  lookupSlots<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(m->dm, m->d_stage_keys[buf], (uint32_t)count,
+                                                               m->d_stage_slots[buf], m->d_lookup_missing);
+  {
+    KernelScope scope(m, kKGather);
+    gatherRegionsChecked<<<(unsigned)count, 256, 0, s>>>((const uint4 *)m->layer_slab[layer], m->d_stage_slots[buf],
+                                                         (uint4 *)m->d_stage[buf], chunk / 16);
+  }
+  CUDA_TRY(cudaGetLastError());
+  // The snapshot is taken in stream order (later batches do not disturb it); the D2H runs beside them.
+  CUDA_TRY(cudaEventRecord(m->stage_gathered[buf], s));
+  CUDA_TRY(cudaStreamWaitEvent(m->download_stream, m->stage_gathered[buf], 0));
+  CUDA_TRY(cudaMemcpyAsync(dst, m->d_stage[buf], chunk * count, cudaMemcpyDeviceToHost, m->download_stream));
+  CUDA_TRY(cudaEventRecord(m->stage_done[buf], m->download_stream));
+  m->stage_pending[buf] = true;
+  return OHMB200_OK;
+}
+
+int ohmb200_download_wait(ohmb200_map *m)
+{
+  if (!m)
+  {
+    return setError(OHMB200_E_INVALID, "null map");
+  }
+  if (!m->download_stream)
+  {
+    return OHMB200_OK;
+  }
+  cudaSetDevice(m->device);
+  CUDA_TRY(cudaStreamSynchronize(m->download_stream));
+  m->stage_pending[0] = m->stage_pending[1] = false;
+  int missing = 0;
+  CUDA_TRY(cudaMemcpyAsync(&missing, m->d_lookup_missing, sizeof(int), cudaMemcpyDeviceToHost, m->download_stream));
+  CUDA_TRY(cudaMemsetAsync(m->d_lookup_missing, 0, sizeof(int), m->download_stream));
+  CUDA_TRY(cudaStreamSynchronize(m->download_stream));
+  if (missing)
+  {
+    return setError(OHMB200_E_NOT_FOUND, "an asynchronous download named a region that is not resident");
+  }
+  return OHMB200_OK;
+}
+
 __global__ void insertRegion(DeviceMap dm, unsigned long long key, int *slot_out)
 {
   *slot_out = regionSlot(dm, key);
@@ -1741,11 +1955,27 @@ int ohmb200_clear(ohmb200_map *m)
   }
   cudaSetDevice(m->device);
   CUDA_TRY(cudaStreamSynchronize(m->copy_stream));
-  int rc = initialiseSlabs(m);
-  if (rc)
+  ClearTable table{};
+  auto add = [&](void *base, size_t bytes_per_region, uint32_t fill) {
+    if (base)
+    {
+      table.base[table.count] = (uint32_t *)base;
+      table.words[table.count] = (uint32_t)(bytes_per_region / 4);
+      table.fill[table.count] = fill;
+      ++table.count;
+    }
+  };
+  for (int l = 0; l < OHMB200_LAYER_COUNT; ++l)
   {
-    return rc;
+    add(m->layer_slab[l], m->region_layer_bytes[l], l == OHMB200_LAYER_OCCUPANCY ? 0x7f800000u : 0u);  // +inf
   }
+  const size_t bit_bytes = sizeof(uint32_t) * ((m->geom.vpr + 31u) / 32u);
+  add(m->dm.voxel_bits, bit_bytes, 0u);
+  add(m->tsdf_near, bit_bytes, 0u);
+  add(m->dm.pending, sizeof(uint32_t) * m->geom.vpr, 0u);
+  clearLiveRegions<<<std::min<unsigned>(m->dm.capacity, (unsigned)m->sm_count * 16u), 256, 0, m->stream>>>(m->dm, table);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemsetAsync(m->d_counters, 0, sizeof(Counters), m->stream));
   CUDA_TRY(cudaStreamSynchronize(m->stream));
   return OHMB200_OK;
 }

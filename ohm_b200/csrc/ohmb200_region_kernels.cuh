@@ -224,11 +224,14 @@ __global__ void __launch_bounds__(1024) planRegions(DeviceMap dm, Batch b, uint3
     }
   }
   // Work items in decreasing size classes so that the long items start first and the tail is made of small ones.
-  // Item size: about three items per persistent CTA (a batch that touches few regions — a small batch, or one GPU's
-  // share of a sharded map — is cut finer so that every SM still gets work), at most kMaxSegmentsPerItem.
+  // Item size: kMaxSegmentsPerItem, unless that leaves fewer than two items per persistent CTA (a small batch, or one
+  // GPU's share of a sharded map): then the regions are cut finer so that every SM still gets work.
   __syncthreads();
-  const uint32_t item_max =
-    min(kMaxSegmentsPerItem, max(512u, ((carry / max(3u * walk_ctas, 1u)) + 63u) & ~63u));
+  uint32_t item_max = kMaxSegmentsPerItem;
+  if (touched + carry / kMaxSegmentsPerItem < 2u * walk_ctas)
+  {
+    item_max = min(kMaxSegmentsPerItem, max(512u, ((carry / max(2u * walk_ctas, 1u)) + 63u) & ~63u));
+  }
   for (int pass = 0; pass < 5; ++pass)
   {
     const uint32_t hi = (pass == 0) ? 0xFFFFFFFFu : (item_max >> (pass == 1 ? 0 : (pass == 2 ? 1 : (pass == 3 ? 3 : 5))));
@@ -674,11 +677,16 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegions(DeviceMap dm, Geo
   }
 }
 
-// Attach every ordered-miss record to the run (sorted sample pairs) of its voxel.  Slots reserved by a warp but
-// never written keep the kInvalidVoxel fill and are skipped.
-__global__ void linkRecords(Batch b)
+// Attach every ordered-miss record to the interval between two hits of its voxel: the run of the voxel in the sorted
+// sample pairs (binary search by voxel), then the first hit of the run with a larger ray index (binary search by ray).
+// Occupancy (chains == 0): misses of an interval commute, so only their number is kept (interval_count[], and
+// tail_overflow[] for the misses after the last hit).  NDT (chains != 0): the same two arrays hold 1-based heads of
+// per-interval record chains, linked through record_vid[].  Slots reserved by a warp but never written keep the
+// kInvalidVoxel fill and are skipped.
+__global__ void linkRecords(Batch b, int chains)
 {
   const uint32_t count = min(b.counters->record_count, b.record_capacity);
+  unsigned linked = 0;
   for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < count; r += gridDim.x * blockDim.x)
   {
     const uint32_t vid = b.record_vid[r];
@@ -687,7 +695,36 @@ __global__ void linkRecords(Batch b)
       continue;
     }
     const uint32_t head = lowerBound(b.keys_out, b.n, vid);
-    b.record_next[r] = atomicExch(&b.run_head[head], (int32_t)r);
+    const uint32_t k = lowerBound(b.keys_out, b.n, vid + 1u) - head;
+    const uint32_t ray = b.record_ray[r];
+    uint32_t lo = 0, hi = k;  // first hit whose ray index is greater than `ray`
+    while (lo < hi)
+    {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (b.vals_out[head + mid] < ray)
+      {
+        lo = mid + 1;
+      }
+      else
+      {
+        hi = mid;
+      }
+    }
+    uint32_t *cell = (lo < k) ? &b.interval_count[head + lo] : &b.tail_overflow[head];
+    if (chains)
+    {
+      b.record_vid[r] = atomicExch(cell, r + 1u);
+    }
+    else
+    {
+      atomicAdd(cell, 1u);
+    }
+    ++linked;
+  }
+  linked = __reduce_add_sync(0xffffffffu, linked);
+  if ((threadIdx.x & 31u) == 0 && linked)
+  {
+    atomicAdd(&b.counters->ordered_records, (unsigned long long)linked);
   }
 }
 
@@ -913,35 +950,68 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsNdt(const __grid_c
       const uint4 t = tile4[tileGroup(c)];
       const uint32_t w4[4] = { t.x, t.y, t.z, t.w };
       const uint32_t gauss8 = (kind[c >> 2] >> ((c & 3u) * 8u)) & 0xffu;
+      // counts of the plain voxels of the group (flagged voxels are replayed by applySamplesNdt, Gaussian voxels are
+      // handled by ndtGaussianMisses / ndtClampGaussians)
+      uint32_t cnt[8], any = 0;
 #pragma unroll
       for (int k = 0; k < 8; ++k)
       {
         const uint32_t half = (w4[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
-        const uint32_t v = c * 8u + (uint32_t)k;
-        if (half == 0 || (half & kTileFlag) || v >= g.vpr)
+        cnt[k] = ((half & kTileFlag) || ((gauss8 >> k) & 1u) || c * 8u + (uint32_t)k >= g.vpr) ? 0u : half;
+        any |= cnt[k];
+      }
+      if (!any)
+      {
+        continue;
+      }
+      if (dm.hit_miss)
+      {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+        {
+          if (cnt[k])
+          {
+            atomicAdd(&dm.hit_miss[vbase + c * 8u + (uint32_t)k].y, cnt[k]);  // every plain NDT miss counts as a miss
+          }
+        }
+      }
+      if (!item.shared && (g.vpr & 7u) == 0)
+      {
+        // sole writer of the region's log-odds until this kernel ends: 2 x 128-bit read-modify-write
+        float4 *occ4 = reinterpret_cast<float4 *>(occ);
+        float4 a = occ4[2 * c], d = occ4[2 * c + 1];
+        a.x = missRepeat(a.x, cnt[0], mp, 0u);
+        a.y = missRepeat(a.y, cnt[1], mp, 0u);
+        a.z = missRepeat(a.z, cnt[2], mp, 0u);
+        a.w = missRepeat(a.w, cnt[3], mp, 0u);
+        d.x = missRepeat(d.x, cnt[4], mp, 0u);
+        d.y = missRepeat(d.y, cnt[5], mp, 0u);
+        d.z = missRepeat(d.z, cnt[6], mp, 0u);
+        d.w = missRepeat(d.w, cnt[7], mp, 0u);
+        occ4[2 * c] = a;
+        occ4[2 * c + 1] = d;
+        continue;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+      {
+        if (cnt[k] == 0)
         {
           continue;
         }
-        if ((gauss8 >> k) & 1u)
-        {
-          continue;  // Gaussian voxel: handled by ndtGaussianMisses / ndtClampGaussians
-        }
-        if (dm.hit_miss)
-        {
-          atomicAdd(&dm.hit_miss[vbase + v].y, half);  // every plain NDT miss counts as a miss
-        }
+        const uint32_t v = c * 8u + (uint32_t)k;
         int *addr = reinterpret_cast<int *>(occ + v);
         int seen = *reinterpret_cast<volatile int *>(addr);
         for (;;)
         {
-          const float next = missRepeat(__int_as_float(seen), half, mp, 0u);
+          const float next = missRepeat(__int_as_float(seen), cnt[k], mp, 0u);
           if (__float_as_int(next) == seen)
           {
             break;
           }
           if (!item.shared)
           {
-            occ[v] = next;  // this CTA is the only writer of the region in this batch
+            occ[v] = next;
             break;
           }
           const int prev = atomicCAS(addr, seen, __float_as_int(next));
@@ -971,37 +1041,7 @@ __global__ void __launch_bounds__(128) applySamplesNdt(DeviceMap dm, Geom g, Map
     {
       ++k;
     }
-    uint32_t tail = 0;
-    for (int32_t rec = b.run_head[head]; rec >= 0; rec = b.record_next[rec])
-    {
-      const uint32_t ray = b.record_ray[rec];
-      uint32_t lo = 0, hi = k;
-      while (lo < hi)
-      {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (b.vals_out[head + mid] < ray)
-        {
-          lo = mid + 1;
-        }
-        else
-        {
-          hi = mid;
-        }
-      }
-      // Re-thread the record onto the chain of its interval (head kept in interval_count[], -1 based; the tail
-      // interval's head in a register).  record_vid[] becomes the per-interval "next" link.
-      if (lo < k)
-      {
-        b.record_vid[rec] = b.interval_count[head + lo];
-        b.interval_count[head + lo] = (uint32_t)rec + 1u;
-      }
-      else
-      {
-        b.record_vid[rec] = tail;
-        tail = (uint32_t)rec + 1u;
-      }
-      ++ordered;
-    }
+    const uint32_t tail = b.tail_overflow[head];  // 1-based head of the chain of misses after the last hit (linkRecords)
 
     const uint32_t slot = vid / g.vpr;
     const uint32_t local = vid - slot * g.vpr;

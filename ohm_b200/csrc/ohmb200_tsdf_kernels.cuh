@@ -269,16 +269,70 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsTsdf(const __grid_
     // Fold: k commuting far visits -> (trunc, min(w + 1, max) k times).
     float2 *slab = dm.tsdf + (size_t)vbase;
     const uint4 *tile4 = reinterpret_cast<const uint4 *>(tile);
-    for (uint32_t c = tid; c < ((g.vpr + 7u) >> 3); c += blockDim.x)
-    {
-      const uint4 t = tile4[tileGroup(c)];
-      const uint32_t w4[4] = { t.x, t.y, t.z, t.w };
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
+    auto far_visits = [&](float w, uint32_t k) {
+      if (w == floorf(w) && w + (float)k <= 16777216.0f)
       {
-        const uint32_t half = (w4[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
-        const uint32_t v = c * 8u + (uint32_t)k;
-        if (half == 0 || (half & kTileFlag) || v >= g.vpr)
+        return fminf(w + (float)k, mp.tsdf_max_weight);  // integer weights: every +1 is exact
+      }
+      for (uint32_t n = 0; n < k; ++n)
+      {
+        const float next = fminf(w + 1.0f, mp.tsdf_max_weight);
+        if (next == w)
+        {
+          break;
+        }
+        w = next;
+      }
+      return w;
+    };
+    if (!item.shared && (g.vpr & 7u) == 0)
+    {
+      // sole writer of the region in this batch: 64-byte read-modify-write of eight voxels at a time
+      float4 *slab4 = reinterpret_cast<float4 *>(slab);
+      for (uint32_t c = tid; c < (g.vpr >> 3); c += blockDim.x)
+      {
+        const uint4 t = tile4[tileGroup(c)];
+        const uint32_t w4[4] = { t.x, t.y, t.z, t.w };
+        uint32_t cnt[8], any = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+        {
+          const uint32_t half = (w4[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+          cnt[k] = (half & kTileFlag) ? 0u : half;
+          any |= cnt[k];
+        }
+        if (any)
+        {
+          float4 v[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+          {
+            v[k] = slab4[4 * c + k];
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+          {
+            if (cnt[2 * k])
+            {
+              v[k].x = far_visits(v[k].x, cnt[2 * k]);
+              v[k].y = mp.tsdf_trunc;
+            }
+            if (cnt[2 * k + 1])
+            {
+              v[k].z = far_visits(v[k].z, cnt[2 * k + 1]);
+              v[k].w = mp.tsdf_trunc;
+            }
+            slab4[4 * c + k] = v[k];
+          }
+        }
+      }
+    }
+    else
+    {
+      for (uint32_t v = tid; v < g.vpr; v += blockDim.x)
+      {
+        const uint32_t half = (tile[tileWord(v)] >> ((v & 1u) * 16u)) & 0xffffu;
+        if (half == 0 || (half & kTileFlag))
         {
           continue;
         }
@@ -286,16 +340,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsTsdf(const __grid_
         unsigned long long seen = *reinterpret_cast<volatile unsigned long long *>(addr);
         for (;;)
         {
-          float w = __uint_as_float((uint32_t)seen);
-          for (uint32_t n = 0; n < half; ++n)
-          {
-            const float next = fminf(w + 1.0f, mp.tsdf_max_weight);
-            if (next == w)
-            {
-              break;
-            }
-            w = next;
-          }
+          const float w = far_visits(__uint_as_float((uint32_t)seen), half);
           const unsigned long long want =
             (unsigned long long)__float_as_uint(w) | ((unsigned long long)__float_as_uint(mp.tsdf_trunc) << 32);
           if (!item.shared)

@@ -210,6 +210,18 @@ class GpuMap:
         nvox = chunk // (np.dtype(dtype).itemsize * width)
         return arr.reshape(keys.shape[0], nvox, width) if width > 1 else arr.reshape(keys.shape[0], nvox)
 
+    def region_layers_async(self, keys, layer, out_ptr, out_bytes):
+        """Queue a snapshot + download of one layer of `keys` into host memory at `out_ptr` (pinned for a real overlap);
+        returns at once.  Batches integrated afterwards run beside the copy and do not show in it.  The memory must
+        stay valid until download_wait()."""
+        keys = np.ascontiguousarray(keys, dtype=np.int16).reshape(-1, 3)
+        self._check(self.L.ohmb200_read_regions_async(self.h, layer, keys.ctypes.data_as(C.POINTER(C.c_int16)),
+                                                      keys.shape[0], C.c_void_p(out_ptr), out_bytes))
+
+    def download_wait(self):
+        """Wait for every queued region_layers_async download (GpuMap::syncVoxels' wait on the cache events)."""
+        self._check(self.L.ohmb200_download_wait(self.h))
+
     def write_region(self, key, layer, data):
         key = np.ascontiguousarray(key, dtype=np.int16)
         data = np.ascontiguousarray(data)

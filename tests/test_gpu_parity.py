@@ -217,6 +217,40 @@ def test_write_region_roundtrip(gpu):
     assert g.region_count() == 1
 
 
+def test_async_download_is_a_snapshot(gpu):
+    """ohmb200_read_regions_async: the chunks are those of the moment of the call (stream order), whatever is
+    integrated while the copy runs; two downloads may be in flight; a key that is not resident is reported by the wait."""
+    import torch
+
+    g, c = make_pair(0.25)
+    first, second = random_rays(3000, 12.0, seed=11), random_rays(3000, 12.0, seed=12)
+    g.integrate_rays(first)
+    g.sync_voxels()
+    keys = g.region_keys()
+    expect = g.region_layers(keys, gm.LAYER_OCCUPANCY)
+    chunk = g.L.ohmb200_region_layer_bytes(g.h, gm.LAYER_OCCUPANCY)
+    a = torch.empty(len(keys) * chunk, dtype=torch.uint8).pin_memory()
+    b = torch.empty(len(keys) * chunk, dtype=torch.uint8).pin_memory()
+    g.region_layers_async(keys, gm.LAYER_OCCUPANCY, a.data_ptr(), a.numel())
+    g.integrate_rays(second)  # runs beside the copy, must not show in it
+    g.region_layers_async(keys, gm.LAYER_OCCUPANCY, b.data_ptr(), b.numel())
+    g.download_wait()
+    got_a = a.numpy().view(np.float32).reshape(len(keys), -1)
+    got_b = b.numpy().view(np.float32).reshape(len(keys), -1)
+    assert np.array_equal(got_a.view(np.uint32), expect.view(np.uint32))
+    after = g.region_layers(keys, gm.LAYER_OCCUPANCY)
+    assert np.array_equal(got_b.view(np.uint32), after.view(np.uint32))
+    assert not np.array_equal(got_a.view(np.uint32), got_b.view(np.uint32))
+    c.integrate_rays(first)
+    c.integrate_rays(second)
+    compare_maps(g, c)
+    missing = np.array([[99, 99, 99]], dtype=np.int16)
+    g.region_layers_async(missing, gm.LAYER_OCCUPANCY, a.data_ptr(), a.numel())
+    with pytest.raises(ohm_b200.OhmB200Error):
+        g.download_wait()
+    g.download_wait()  # the flag is cleared by the failing wait
+
+
 def test_region_partition_union_matches_single_map(gpu):
     """Multi-GPU sharding on one device: two maps owning complementary region sets, fed the same rays, hold
     between them exactly the single-map (= oracle) result — no region on both, every visit applied once."""
