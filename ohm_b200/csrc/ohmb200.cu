@@ -20,6 +20,7 @@
 
 #include <cub/block/block_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <cmath>
@@ -76,11 +77,12 @@ struct Counters
   uint32_t work_next;
   uint32_t segment_overflow;
   uint32_t gauss_count;  // NDT: reserved Gaussian-visit record slots
+  uint32_t heavy_count;  // NDT: runs set aside for the warp-per-run replay
   // sticky
   int table_full;
   int overflow_seen;
 };
-constexpr int kPerBatchCounterWords = 9;  // record_count .. gauss_count
+constexpr int kPerBatchCounterWords = 10;  // record_count .. heavy_count
 
 struct Batch
 {
@@ -96,8 +98,10 @@ struct Batch
   uint32_t *vals_in, *vals_out;  // ray indices
   uint32_t *run_list;            // [n] sorted index of each run head
   int32_t *run_head;             // [n] head of the record chain of the run starting at sorted index i (-1 = none)
-  uint32_t *interval_count;      // [n] misses that precede sorted hit i inside its run
-  uint32_t *tail_overflow;       // [n] unordered (overflowed) misses of run i
+  uint32_t *interval_count;      // [2n + 1] misses that precede sorted hit i inside its run; [n + i]: see tail_overflow
+  uint32_t *tail_overflow;       // = interval_count + n: misses after the last hit of the run starting at sorted index i
+  uint32_t *interval_offset;     // [2n + 1] NDT: exclusive scan of interval_count
+  uint32_t *sorted_rays;         // [record_capacity] NDT: rays of the ordered-miss records, grouped by interval
   // ordered miss records
   uint32_t *record_ray;
   int32_t *record_next;
@@ -111,6 +115,8 @@ struct Batch
   uint32_t *seg_count;     // [capacity] segments per region slot
   uint32_t *seg_offset;    // [capacity] exclusive scan of seg_count
   uint32_t *seg_cursor;    // [capacity] fill cursors
+  uint32_t *sample_begin;  // [capacity] the region's range of the sorted sample pairs (markRuns); begin == end: none
+  uint32_t *sample_end;
   Segment *segments;       // [seg_capacity] binned by region slot
   uint32_t seg_capacity;
   uint4 *stage;            // [kStageSegments][stage_stride] segments found by pass A, plane k = k-th segment of each ray
@@ -198,7 +204,7 @@ __global__ void prepSamples(DeviceMap dm, Geom g, MapParams mp, Batch b, int mod
 }
 
 // Run heads of the sorted (voxel, ray) pairs.
-__global__ void markRuns(DeviceMap dm, Batch b)
+__global__ void markRuns(DeviceMap dm, Batch b, uint32_t vpr)
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= b.n)
@@ -218,6 +224,21 @@ __global__ void markRuns(DeviceMap dm, Batch b)
     }
     const uint32_t r = warpAggregatedInc(&b.counters->run_count);
     b.run_list[r] = i;
+  }
+  if (b.sample_begin)
+  {
+    // region boundaries of the sorted pairs (keys are slot * vpr + voxel, so a region is one contiguous range)
+    const uint32_t slot = vid / vpr;
+    const uint32_t prev = (i > 0) ? b.keys_out[i - 1] : kInvalidVoxel;
+    if (i == 0 || prev / vpr != slot)
+    {
+      b.sample_begin[slot] = i;
+    }
+    const uint32_t next = (i + 1 < b.n) ? b.keys_out[i + 1] : kInvalidVoxel;
+    if (next == kInvalidVoxel || next / vpr != slot)
+    {
+      b.sample_end[slot] = i + 1;
+    }
   }
 }
 
@@ -589,6 +610,7 @@ enum KernelId
   kKEmit,
   kKWalkRegions,
   kKLink,
+  kKScatter,
   kKTsdfMark,
   kKTsdfClear,
   kKTsdfReplay,
@@ -599,7 +621,7 @@ enum KernelId
 static const char *kKernelNames[kKernelCount] = { "prepSamples",  "radixSort",     "markRuns",      "walkRays",
                                                   "applySamples", "resolveMisses", "gatherRegions", "fillFloat",
                                                   "prepRays",     "prepSegments",  "planRegions",   "emitSegments",  "walkRegions",
-                                                  "linkRecords",  "markTsdfNear",  "clearTouchedBits", "replayTsdf",
+                                                  "linkRecords",  "scatterRecords", "markTsdfNear",  "clearTouchedBits", "replayTsdf",
                                                   "ndtGaussianMisses", "ndtClampGaussians" };
 static_assert(kKernelCount <= OHMB200_KERNEL_SLOTS, "raise OHMB200_KERNEL_SLOTS");
 
@@ -835,7 +857,10 @@ int ensureScratch(ohmb200_map *m, size_t n)
   cudaFree(b.run_list);
   cudaFree(b.run_head);
   cudaFree(b.interval_count);
-  cudaFree(b.tail_overflow);
+  cudaFree(b.interval_offset);
+  cudaFree(b.sorted_rays);
+  b.interval_offset = nullptr;
+  b.sorted_rays = nullptr;
   cudaFree(b.record_ray);
   cudaFree(b.record_next);
   cudaFree(b.last_exit);
@@ -849,8 +874,8 @@ int ensureScratch(ohmb200_map *m, size_t n)
   rc |= deviceAlloc(b.vals_out, cap);
   rc |= deviceAlloc(b.run_list, cap);
   rc |= deviceAlloc(b.run_head, cap);
-  rc |= deviceAlloc(b.interval_count, cap);
-  rc |= deviceAlloc(b.tail_overflow, cap);
+  rc |= deviceAlloc(b.interval_count, 2 * cap + 1);
+  b.tail_overflow = b.interval_count + cap;  // re-pointed at interval_count + n by every batch
   b.record_capacity = (uint32_t)std::min<size_t>(std::max<size_t>(cap * 24, 1u << 20), 1u << 28);
   rc |= deviceAlloc(b.record_ray, b.record_capacity);
   rc |= deviceAlloc(b.record_next, b.record_capacity);
@@ -884,6 +909,8 @@ int ensureScratch(ohmb200_map *m, size_t n)
     if (m->mode == OHMB200_MODE_NDT || m->mode == OHMB200_MODE_NDT_TM)
     {
       cudaFree(b.gauss_keys);
+      rc |= deviceAlloc(b.interval_offset, 2 * cap + 1);
+      rc |= deviceAlloc(b.sorted_rays, b.record_capacity);
       b.gauss_capacity = (uint32_t)std::min<size_t>(std::max<size_t>(cap * 16, 1u << 20), 1u << 28);
       rc |= deviceAlloc(b.gauss_keys, b.gauss_capacity);
     }
@@ -902,6 +929,12 @@ int ensureScratch(ohmb200_map *m, size_t n)
   m->cub_temp_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, m->cub_temp_bytes, b.keys_in, b.keys_out, b.vals_in, b.vals_out, (int)cap, 0,
                                   m->sort_bits, m->stream);
+  if (b.interval_offset)
+  {
+    size_t scan_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, b.interval_count, b.interval_offset, (int)(2 * cap + 1), m->stream);
+    m->cub_temp_bytes = std::max(m->cub_temp_bytes, scan_bytes);
+  }
   if (m->mode == OHMB200_MODE_TSDF && m->algo == 1)
   {
     size_t keys_bytes = 0;
@@ -946,14 +979,15 @@ int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_i
   {
     CUDA_TRY(cudaMemsetAsync(b.seg_count, 0, sizeof(uint32_t) * m->dm.capacity, s));
     CUDA_TRY(cudaMemsetAsync(b.seg_cursor, 0, sizeof(uint32_t) * m->dm.capacity, s));
+    CUDA_TRY(cudaMemsetAsync(b.sample_begin, 0, sizeof(uint32_t) * 2 * m->dm.capacity, s));  // begin and end
     if (has_samples)
     {
       // record slots are reserved per warp in chunks; unwritten slots must read as "no record"
       CUDA_TRY(cudaMemsetAsync(b.record_vid, 0xFF, sizeof(uint32_t) * b.record_capacity, s));
     }
     CUDA_TRY(cudaMemsetAsync(b.run_head, 0xFF, sizeof(int32_t) * n, s));
-    CUDA_TRY(cudaMemsetAsync(b.interval_count, 0, sizeof(uint32_t) * n, s));
-    CUDA_TRY(cudaMemsetAsync(b.tail_overflow, 0, sizeof(uint32_t) * n, s));
+    b.tail_overflow = b.interval_count + n;
+    CUDA_TRY(cudaMemsetAsync(b.interval_count, 0, sizeof(uint32_t) * (2 * n + 1), s));
     {
       KernelScope scope(m, kKPrepRays);
       prepRays<<<blocks, threads, 0, s>>>(m->dm, m->geom, m->mp, b, m->mode);
@@ -977,7 +1011,7 @@ int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_i
       }
       {
         KernelScope scope(m, kKMark);
-        markRuns<<<blocks, threads, 0, sample_stream>>>(m->dm, b);
+        markRuns<<<blocks, threads, 0, sample_stream>>>(m->dm, b, m->geom.vpr);
       }
     }
     {
@@ -1060,15 +1094,25 @@ int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_i
     }
     if (has_samples)
     {
+      const bool ndt_mode = m->mode == OHMB200_MODE_NDT || m->mode == OHMB200_MODE_NDT_TM;
       {
         KernelScope scope(m, kKLink);
-        linkRecords<<<m->sm_count * 4, 256, 0, s>>>(b, (m->mode == OHMB200_MODE_NDT || m->mode == OHMB200_MODE_NDT_TM) ? 1 : 0);
+        linkRecords<<<m->sm_count * 4, 256, 0, s>>>(b, ndt_mode ? 1 : 0);
+      }
+      if (ndt_mode)
+      {
+        // group the records by interval: exclusive scan of the interval counts, then one scatter
+        KernelScope scope(m, kKScatter);
+        size_t temp = m->cub_temp_bytes;
+        cub::DeviceScan::ExclusiveSum(m->cub_temp, temp, b.interval_count, b.interval_offset, (int)(2 * n + 1), s);
+        scatterRecords<<<m->sm_count * 4, 256, 0, s>>>(b);
       }
       {
         KernelScope scope(m, kKSamples);
         if ((m->mode == OHMB200_MODE_NDT || m->mode == OHMB200_MODE_NDT_TM))
         {
           applySamplesNdt<<<blocks, threads, 0, s>>>(m->dm, m->geom, m->mp, b);
+          applySamplesNdtHeavy<<<m->sm_count * 8, 128, 0, s>>>(m->dm, m->geom, m->mp, b);
         }
         else
         {
@@ -1084,8 +1128,8 @@ int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_i
   if (has_samples)
   {
     CUDA_TRY(cudaMemsetAsync(b.run_head, 0xFF, sizeof(int32_t) * n, s));
-    CUDA_TRY(cudaMemsetAsync(b.interval_count, 0, sizeof(uint32_t) * n, s));
-    CUDA_TRY(cudaMemsetAsync(b.tail_overflow, 0, sizeof(uint32_t) * n, s));
+    b.tail_overflow = b.interval_count + n;
+    CUDA_TRY(cudaMemsetAsync(b.interval_count, 0, sizeof(uint32_t) * (2 * n + 1), s));
     {
       KernelScope scope(m, kKPrep);
       prepSamples<<<blocks, threads, 0, s>>>(m->dm, m->geom, m->mp, b, m->mode);
@@ -1098,7 +1142,7 @@ int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_i
     }
     {
       KernelScope scope(m, kKMark);
-      markRuns<<<blocks, threads, 0, s>>>(m->dm, b);
+      markRuns<<<blocks, threads, 0, s>>>(m->dm, b, m->geom.vpr);
     }
   }
   {
@@ -1376,6 +1420,8 @@ ohmb200_map *ohmb200_create(const ohmb200_params *params, int mode, size_t devic
     ok = ok && cudaMalloc(&m->batch.seg_count, sizeof(uint32_t) * capacity) == cudaSuccess;
     ok = ok && cudaMalloc(&m->batch.seg_offset, sizeof(uint32_t) * capacity) == cudaSuccess;
     ok = ok && cudaMalloc(&m->batch.seg_cursor, sizeof(uint32_t) * capacity) == cudaSuccess;
+    ok = ok && cudaMalloc(&m->batch.sample_begin, sizeof(uint32_t) * 2 * capacity) == cudaSuccess;
+    m->batch.sample_end = ok ? m->batch.sample_begin + capacity : nullptr;
   }
   ok = ok && cudaMalloc(&m->batch.touched_list, sizeof(uint32_t) * capacity) == cudaSuccess;
   ok = ok && cudaMalloc(&m->d_counters, sizeof(Counters)) == cudaSuccess;
@@ -1435,11 +1481,11 @@ void ohmb200_destroy(ohmb200_map *m)
   Batch &b = m->batch;
   void *to_free[] = { m->dm.keys,       m->dm.region_stamp, m->dm.pending,      b.touched_list,   m->d_counters,
                       b.keys_in,        b.keys_out,         b.vals_in,          b.vals_out,       b.run_list,
-                      b.run_head,       b.interval_count,   b.tail_overflow,    b.record_ray,     b.record_next,
+                      b.run_head,       b.interval_count,   b.interval_offset,  b.sorted_rays,   b.record_ray,     b.record_next,
                       b.last_exit,      m->cub_temp,        m->d_rays[0],       m->d_rays[1],     m->d_intensities[0],
                       m->d_intensities[1], m->d_timestamps[0], m->d_timestamps[1], m->d_gather,    m->d_gather_slots,
                       b.recs,           b.ray_length,       b.record_vid,       b.seg_count,      b.seg_offset,
-                      b.seg_cursor,     b.segments,         b.items,            b.record_keys,    b.record_keys_sorted, b.gauss_keys,
+                      b.seg_cursor,     b.sample_begin,     b.segments,         b.items,            b.record_keys,    b.record_keys_sorted, b.gauss_keys,
                       b.stage,          b.stage_count,      m->tsdf_near,       m->dm.voxel_bits };
   for (void *p : to_free)
   {

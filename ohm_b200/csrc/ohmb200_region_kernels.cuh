@@ -447,6 +447,20 @@ __device__ __forceinline__ int queuePop(SegmentQueue &q, const Batch &b, const W
   return 1;
 }
 
+// Next work item of the persistent CTA into `slot` (one thread calls this); slot.slot == 0xFFFFFFFF when none is left.
+__device__ __forceinline__ void fetchWorkItem(const Batch &b, WorkItem &slot)
+{
+  const uint32_t w = atomicAdd(&b.counters->work_next, 1u);
+  if (w < min(b.counters->item_count, b.item_capacity))
+  {
+    slot = b.items[w];
+  }
+  else
+  {
+    slot.slot = 0xFFFFFFFFu;
+  }
+}
+
 // What a lane needs to resume a segment: the segment itself and the walk constants of its ray.
 struct SegmentWalk
 {
@@ -487,8 +501,7 @@ __device__ __forceinline__ void loadSegmentWalk(const Batch &b, const uint4 &raw
 __global__ void __launch_bounds__(kWalkThreads, 2) walkRegions(DeviceMap dm, Geom g, MapParams mp, Batch b, int has_samples)
 {
   extern __shared__ uint32_t tile[];
-  __shared__ WorkItem item;
-  __shared__ uint32_t sample_range[2];
+  __shared__ WorkItem items[2];  // the current item and the prefetched next one
   // per-warp reservation of ordered-miss record slots: (base << 32) | used
   __shared__ unsigned long long record_chunk[kWalkThreads / 32];
   __shared__ SegmentQueue queue;
@@ -500,22 +513,14 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegions(DeviceMap dm, Geo
     record_chunk[warp] = (unsigned long long)kRecordChunk;  // "full": the first record reserves a chunk
   }
 
-  for (;;)
+  if (tid == 0)
   {
-    __syncthreads();
-    if (tid == 0)
-    {
-      const uint32_t w = atomicAdd(&b.counters->work_next, 1u);
-      if (w < min(b.counters->item_count, b.item_capacity))
-      {
-        item = b.items[w];
-      }
-      else
-      {
-        item.slot = 0xFFFFFFFFu;
-      }
-    }
-    __syncthreads();
+    fetchWorkItem(b, items[0]);
+  }
+  for (uint32_t phase = 0;; phase ^= 1u)
+  {
+    __syncthreads();  // items[phase] is in place (fetched before the loop, or during the previous item's walk)
+    const WorkItem &item = items[phase];
     if (item.slot == 0xFFFFFFFFu)
     {
       return;
@@ -537,21 +542,23 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegions(DeviceMap dm, Geo
         tile[w] = 0;
       }
     }
-    if (has_samples && tid < 2)
-    {
-      sample_range[tid] = lowerBound(b.keys_out, b.n, vbase + tid * g.vpr);
-    }
     __syncthreads();
     if (has_samples)
     {
       // Voxels that also receive samples in this batch: their misses must stay ordered against the hits.
-      for (uint32_t s = sample_range[0] + tid; s < sample_range[1]; s += blockDim.x)
+      // (the region's range of the sorted sample pairs comes from markRuns)
+      const uint32_t sample_end = b.sample_end[slot];
+      for (uint32_t s = b.sample_begin[slot] + tid; s < sample_end; s += blockDim.x)
       {
         const uint32_t v = b.keys_out[s] - vbase;
         atomicOr(&tile[tileWord(v)], kTileFlag << ((v & 1u) * 16u));
       }
     }
     queueBuild(queue, b, item);
+    if (tid == blockDim.x - 1u)
+    {
+      fetchWorkItem(b, items[phase ^ 1u]);  // two dependent global round trips, hidden behind the walk
+    }
 
     for (;;)
     {
@@ -679,11 +686,12 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegions(DeviceMap dm, Geo
 
 // Attach every ordered-miss record to the interval between two hits of its voxel: the run of the voxel in the sorted
 // sample pairs (binary search by voxel), then the first hit of the run with a larger ray index (binary search by ray).
-// Occupancy (chains == 0): misses of an interval commute, so only their number is kept (interval_count[], and
-// tail_overflow[] for the misses after the last hit).  NDT (chains != 0): the same two arrays hold 1-based heads of
-// per-interval record chains, linked through record_vid[].  Slots reserved by a warp but never written keep the
-// kInvalidVoxel fill and are skipped.
-__global__ void linkRecords(Batch b, int chains)
+// Only the NUMBER of misses per interval is kept here: interval_count[head + j] for the misses before hit j of the
+// run, tail_overflow[head] (= interval_count[n + head], the two arrays are contiguous) for the misses after the last hit.
+// Occupancy needs no more (misses of an interval commute).  NDT (keep_keys != 0) also leaves each record's interval
+// index in record_vid[], for scatterRecords to group the records by interval (a counting sort: these counts, one
+// exclusive scan, one scatter).  Slots reserved by a warp but never written keep the kInvalidVoxel fill and are skipped.
+__global__ void linkRecords(Batch b, int keep_keys)
 {
   const uint32_t count = min(b.counters->record_count, b.record_capacity);
   unsigned linked = 0;
@@ -710,14 +718,11 @@ __global__ void linkRecords(Batch b, int chains)
         hi = mid;
       }
     }
-    uint32_t *cell = (lo < k) ? &b.interval_count[head + lo] : &b.tail_overflow[head];
-    if (chains)
+    const uint32_t key = (lo < k) ? head + lo : b.n + head;
+    atomicAdd(&b.interval_count[key], 1u);
+    if (keep_keys)
     {
-      b.record_vid[r] = atomicExch(cell, r + 1u);
-    }
-    else
-    {
-      atomicAdd(cell, 1u);
+      b.record_vid[r] = key;
     }
     ++linked;
   }
@@ -725,6 +730,23 @@ __global__ void linkRecords(Batch b, int chains)
   if ((threadIdx.x & 31u) == 0 && linked)
   {
     atomicAdd(&b.counters->ordered_records, (unsigned long long)linked);
+  }
+}
+
+// NDT: second half of the counting sort.  interval_offset[] is the exclusive scan of the 2n + 1 interval counts;
+// sorted_rays[interval_offset[key] ...] receives the rays of the records of interval `key` (any order inside).
+__global__ void scatterRecords(Batch b)
+{
+  const uint32_t count = min(b.counters->record_count, b.record_capacity);
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < count; r += gridDim.x * blockDim.x)
+  {
+    const uint32_t key = b.record_vid[r];
+    if (key == kInvalidVoxel)
+    {
+      continue;
+    }
+    const uint32_t left = atomicSub(&b.interval_count[key], 1u);  // counts down to 0: no separate cursor array
+    b.sorted_rays[b.interval_offset[key] + left - 1u] = b.record_ray[r];
   }
 }
 
@@ -809,8 +831,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsNdt(const __grid_c
                                                                   const __grid_constant__ MapParams mp, const __grid_constant__ Batch b)
 {
   extern __shared__ uint32_t tile[];
-  __shared__ WorkItem item;
-  __shared__ uint32_t sample_range[2];
+  __shared__ WorkItem items[2];  // the current item and the prefetched next one
   __shared__ unsigned long long record_chunk[kWalkThreads / 32];
   __shared__ unsigned long long gauss_chunk[kWalkThreads / 32];
   __shared__ SegmentQueue queue;
@@ -824,22 +845,14 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsNdt(const __grid_c
     record_chunk[warp] = (unsigned long long)kRecordChunk;
     gauss_chunk[warp] = (unsigned long long)kRecordChunk;
   }
-  for (;;)
+  if (tid == 0)
+  {
+    fetchWorkItem(b, items[0]);
+  }
+  for (uint32_t phase = 0;; phase ^= 1u)
   {
     __syncthreads();
-    if (tid == 0)
-    {
-      const uint32_t w = atomicAdd(&b.counters->work_next, 1u);
-      if (w < min(b.counters->item_count, b.item_capacity))
-      {
-        item = b.items[w];
-      }
-      else
-      {
-        item.slot = 0xFFFFFFFFu;
-      }
-    }
-    __syncthreads();
+    const WorkItem &item = items[phase];
     if (item.slot == 0xFFFFFFFFu)
     {
       return;
@@ -861,17 +874,18 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsNdt(const __grid_c
         kind[w] = (mp.sample_threshold == 0) ? 0xFFFFFFFFu : bits[w];
       }
     }
-    if (tid < 2)
-    {
-      sample_range[tid] = lowerBound(b.keys_out, b.n, vbase + tid * g.vpr);
-    }
     __syncthreads();
-    for (uint32_t s = sample_range[0] + tid; s < sample_range[1]; s += blockDim.x)
+    const uint32_t sample_end = b.sample_end[slot];
+    for (uint32_t s = b.sample_begin[slot] + tid; s < sample_end; s += blockDim.x)
     {
       const uint32_t v = b.keys_out[s] - vbase;
       atomicOr(&tile[tileWord(v)], kTileFlag << ((v & 1u) * 16u));
     }
     queueBuild(queue, b, item);
+    if (tid == blockDim.x - 1u)
+    {
+      fetchWorkItem(b, items[phase ^ 1u]);
+    }
 
     for (;;)
     {
@@ -1026,82 +1040,64 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsNdt(const __grid_c
   }
 }
 
-// Sample-voxel updates of RayMapperNdt (RayMapperNdt.cpp:284-404), one thread per voxel, hits in ray order; the
-// recorded misses of an interval are applied with the voxel state of that moment.
-__global__ void __launch_bounds__(128) applySamplesNdt(DeviceMap dm, Geom g, MapParams mp, Batch b)
+// Sample-voxel updates of RayMapperNdt (RayMapperNdt.cpp:284-404) for the run (voxel) t: hits in ray order; the
+// recorded misses of an interval are applied with the voxel state of that moment.  kWarp = false: one thread does it
+// all.  kWarp = true: a whole warp executes this with the same t — every lane computes the (identical) hits, the
+// recorded misses of an interval are evaluated 32 at a time, lane 0 stores.  Returns the number of samples applied.
+template <bool kWarp>
+__device__ __forceinline__ unsigned replayNdtRun(const DeviceMap &dm, const Geom &g, const MapParams &mp, const Batch &b,
+                                                 uint32_t t)
 {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned samples = 0, ordered = 0;
-  if (t < b.counters->run_count)
+  unsigned samples = 0;
+  const uint32_t head = b.run_list[t];
+  const uint32_t vid = b.keys_out[head];
+  uint32_t k = 1;
+  while (head + k < b.n && b.keys_out[head + k] == vid)
   {
-    const uint32_t head = b.run_list[t];
-    const uint32_t vid = b.keys_out[head];
-    uint32_t k = 1;
-    while (head + k < b.n && b.keys_out[head + k] == vid)
-    {
-      ++k;
-    }
-    const uint32_t tail = b.tail_overflow[head];  // 1-based head of the chain of misses after the last hit (linkRecords)
-
-    const uint32_t slot = vid / g.vpr;
-    const uint32_t local = vid - slot * g.vpr;
-    Key key;
-    unpackRegion(dm.keys[slot], key.r);
-    key.l[0] = (int)(local % (uint32_t)g.dim[0]);
-    key.l[1] = (int)((local / (uint32_t)g.dim[0]) % (uint32_t)g.dim[1]);
-    key.l[2] = (int)(local / ((uint32_t)g.dim[0] * (uint32_t)g.dim[1]));
-    double centre[3];
+    ++k;
+  }
+  const uint32_t slot = vid / g.vpr;
+  const uint32_t local = vid - slot * g.vpr;
+  Key key;
+  unpackRegion(dm.keys[slot], key.r);
+  key.l[0] = (int)(local % (uint32_t)g.dim[0]);
+  key.l[1] = (int)((local / (uint32_t)g.dim[0]) % (uint32_t)g.dim[1]);
+  key.l[2] = (int)(local / ((uint32_t)g.dim[0] * (uint32_t)g.dim[1]));
+  double centre[3];
 #pragma unroll
-    for (int a = 0; a < 3; ++a)
-    {
-      centre[a] = voxelCentreAxis(g, key.r[a], key.l[a], a);
-    }
-    float value = dm.occupancy[vid];
-    uint2 vm = dm.mean[vid];
-    float cov[6];
+  for (int a = 0; a < 3; ++a)
+  {
+    centre[a] = voxelCentreAxis(g, key.r[a], key.l[a], a);
+  }
+  float value = dm.occupancy[vid];
+  uint2 vm = dm.mean[vid];
+  float cov[6];
 #pragma unroll
-    for (int c = 0; c < 6; ++c)
+  for (int c = 0; c < 6; ++c)
+  {
+    cov[c] = dm.covariance[(size_t)vid * 6 + c];
+  }
+  uint32_t incident = dm.incident ? dm.incident[vid] : 0;
+  uint32_t touch = 0;
+  bool touch_set = false;
+  float traversal_add = 0.0f;
+  const bool ndt_tm = mp.ndt_tm && dm.hit_miss && dm.intensity;
+  uint2 hm = ndt_tm ? dm.hit_miss[vid] : make_uint2(0, 0);
+  float2 im = ndt_tm ? dm.intensity[vid] : make_float2(0, 0);
+  uint32_t pre_ray = 0;
+  double pre_start[3] = { 0, 0, 0 }, pre_end[3] = { 0, 0, 0 };
+  if (!kWarp)
+  {
+    pre_ray = b.vals_out[head];
+    loadRay(b, pre_ray, pre_start, pre_end);
+  }
+  for (uint32_t j = 0; j <= k; ++j)
+  {
+    // the recorded misses of this interval, grouped by scatterRecords (j == k: the misses after the last hit)
+    const uint32_t key = (j < k) ? head + j : b.n + head;
+    const uint32_t first = b.interval_offset[key], last = b.interval_offset[key + 1u];
+    if (first != last)
     {
-      cov[c] = dm.covariance[(size_t)vid * 6 + c];
-    }
-    uint32_t incident = dm.incident ? dm.incident[vid] : 0;
-    uint32_t touch = 0;
-    bool touch_set = false;
-    float traversal_add = 0.0f;
-    const bool ndt_tm = mp.ndt_tm && dm.hit_miss && dm.intensity;
-    uint2 hm = ndt_tm ? dm.hit_miss[vid] : make_uint2(0, 0);
-    float2 im = ndt_tm ? dm.intensity[vid] : make_float2(0, 0);
-    for (uint32_t j = 0; j <= k; ++j)
-    {
-      const uint32_t chain = (j < k) ? b.interval_count[head + j] : tail;  // 1-based record index, 0 = none
-      if (chain)
-      {
-        double mean[3];
-        subVoxelToLocal(vm.x, g.res, mean);
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-        {
-          mean[a] += centre[a];
-        }
-        for (uint32_t link = chain; link != 0; link = b.record_vid[link - 1u])
-        {
-          const uint32_t rec = link - 1u;
-          double sensor[3], sample[3];
-          loadRay(b, b.record_ray[rec], sensor, sample);
-          unsigned filter_flags = 0;
-          applyRayFilter(mp, sensor, sample, filter_flags);
-          bool is_miss;
-          value = ndtMissOnce(value, cov, sensor, sample, mean, vm.y, mp, is_miss);
-          hm.y += is_miss ? 1u : 0u;
-        }
-      }
-      if (j == k)
-      {
-        break;
-      }
-      const uint32_t ray = b.vals_out[head + j];
-      double start[3], end[3];
-      loadRay(b, ray, start, end);
       double mean[3];
       subVoxelToLocal(vm.x, g.res, mean);
 #pragma unroll
@@ -1109,42 +1105,154 @@ __global__ void __launch_bounds__(128) applySamplesNdt(DeviceMap dm, Geom g, Map
       {
         mean[a] += centre[a];
       }
-      const float initial = value;
-      float adjusted = initial;
-      if (ndt_tm)
+      if (!kWarp)
       {
-        ndtHitMissOnHit(cov, adjusted, hm, start, end, mean, vm.y, mp);
-        ndtIntensityOnHit(im, adjusted, b.intensities ? b.intensities[ray] : 0.0f, vm.y, mp);
+        for (uint32_t at = first; at != last; ++at)
+        {
+          double sensor[3], sample[3];
+          loadRay(b, b.sorted_rays[at], sensor, sample);
+          unsigned filter_flags = 0;
+          applyRayFilter(mp, sensor, sample, filter_flags);
+          bool is_miss;
+          value = ndtMissOnce(value, cov, sensor, sample, mean, vm.y, mp, is_miss);
+          hm.y += is_miss ? 1u : 0u;
+        }
       }
-      const bool reset = ndtHit(cov, adjusted, end, mean, vm.y, mp.hit_value, (float)g.res, mp.reinit_threshold,
-                                mp.reinit_count);
-      value = adjustUp(initial, adjusted, mp);
-      vm.y = reset ? 0u : vm.y;
-      const double local_pt[3] = { end[0] - centre[0], end[1] - centre[1], end[2] - centre[2] };
-      vm.x = subVoxelUpdate(vm.x, vm.y, local_pt, g.res);
-      ++vm.y;
-      if (dm.traversal)
+      else
       {
-        const double d[3] = { end[0] - start[0], end[1] - start[1], end[2] - start[2] };
-        const double len = sqrt((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]);
-        traversal_add += (float)(len - b.last_exit[ray]);
+        // 32 records at a time: every lane evaluates the NDT term of one record (it depends on the voxel's Gaussian
+        // and the ray only), then all lanes apply the 32 adjustments to the log-odds in the same order.
+        const uint32_t lane = threadIdx.x & 31u;
+        const bool gaussian = vm.y >= mp.sample_threshold;
+        for (uint32_t base = first; base < last; base += 32u)
+        {
+          const uint32_t at = base + lane;
+          float adj = 0.0f;
+          bool valid = false, rec_miss = true;
+          if (gaussian && at < last)
+          {
+            double sensor[3], sample[3];
+            loadRay(b, b.sorted_rays[at], sensor, sample);
+            unsigned filter_flags = 0;
+            applyRayFilter(mp, sensor, sample, filter_flags);
+            adj = ndtMissAdjustment(cov, sensor, sample, mean, mp.adaptation_rate, mp.sensor_noise, valid, rec_miss);
+          }
+          const uint32_t batch = min(32u, last - base);
+          for (uint32_t i = 0; i < batch; ++i)
+          {
+            const float a = __shfl_sync(0xffffffffu, adj, i);
+            const bool v = __shfl_sync(0xffffffffu, valid ? 1 : 0, i) != 0;
+            const bool m = __shfl_sync(0xffffffffu, rec_miss ? 1 : 0, i) != 0;
+            // ndtMissOnce with the NDT term already evaluated
+            const float initial = value;
+            float adjusted;
+            bool is_miss = true;
+            if (initial == INFINITY)
+            {
+              adjusted = mp.miss_value;
+            }
+            else if (!gaussian)
+            {
+              adjusted = initial + mp.miss_value;
+            }
+            else
+            {
+              adjusted = v ? initial + a : initial;
+              is_miss = m;
+            }
+            value = adjustDown(initial, adjusted, mp);
+            hm.y += is_miss ? 1u : 0u;
+          }
+        }
       }
-      if (dm.touch_time && b.timestamps)
-      {
-        touch = encodeTouchTime(b.time_base, b.timestamps[ray]);
-        touch_set = true;
-      }
-      if (dm.incident)
-      {
-        incident = updateIncidentNormal(incident, (float)(start[0] - end[0]), (float)(start[1] - end[1]),
-                                        (float)(start[2] - end[2]), vm.y - 1u);
-      }
-      ++samples;
     }
+    if (j == k)
+    {
+      break;
+    }
+    // The sample ray of hit j.  Its load latency is kept off the (sequential) hit chain: a warp fetches the rays of
+    // 32 hits at once and broadcasts them one by one; a single thread fetches the next ray before working on this one.
+    uint32_t ray;
+    double start[3], end[3];
+    if (kWarp)
+    {
+      const uint32_t lane = threadIdx.x & 31u;
+      if ((j & 31u) == 0)
+      {
+        pre_ray = (j + lane < k) ? b.vals_out[head + j + lane] : 0u;
+        if (j + lane < k)
+        {
+          loadRay(b, pre_ray, pre_start, pre_end);
+        }
+      }
+      ray = __shfl_sync(0xffffffffu, pre_ray, j & 31u);
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+      {
+        start[a] = __shfl_sync(0xffffffffu, pre_start[a], j & 31u);
+        end[a] = __shfl_sync(0xffffffffu, pre_end[a], j & 31u);
+      }
+    }
+    else
+    {
+      ray = pre_ray;
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+      {
+        start[a] = pre_start[a];
+        end[a] = pre_end[a];
+      }
+      if (j + 1 < k)
+      {
+        pre_ray = b.vals_out[head + j + 1];
+        loadRay(b, pre_ray, pre_start, pre_end);
+      }
+    }
+    double mean[3];
+    subVoxelToLocal(vm.x, g.res, mean);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+    {
+      mean[a] += centre[a];
+    }
+    const float initial = value;
+    float adjusted = initial;
+    if (ndt_tm)
+    {
+      ndtHitMissOnHit(cov, adjusted, hm, start, end, mean, vm.y, mp);
+      ndtIntensityOnHit(im, adjusted, b.intensities ? b.intensities[ray] : 0.0f, vm.y, mp);
+    }
+    const bool reset = ndtHit(cov, adjusted, end, mean, vm.y, mp.hit_value, (float)g.res, mp.reinit_threshold,
+                              mp.reinit_count);
+    value = adjustUp(initial, adjusted, mp);
+    vm.y = reset ? 0u : vm.y;
+    const double local_pt[3] = { end[0] - centre[0], end[1] - centre[1], end[2] - centre[2] };
+    vm.x = subVoxelUpdate(vm.x, vm.y, local_pt, g.res);
+    ++vm.y;
+    if (dm.traversal)
+    {
+      const double d[3] = { end[0] - start[0], end[1] - start[1], end[2] - start[2] };
+      const double len = sqrt((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]);
+      traversal_add += (float)(len - b.last_exit[ray]);
+    }
+    if (dm.touch_time && b.timestamps)
+    {
+      touch = encodeTouchTime(b.time_base, b.timestamps[ray]);
+      touch_set = true;
+    }
+    if (dm.incident)
+    {
+      incident = updateIncidentNormal(incident, (float)(start[0] - end[0]), (float)(start[1] - end[1]),
+                                      (float)(start[2] - end[2]), vm.y - 1u);
+    }
+    ++samples;
+  }
+  if (!kWarp || (threadIdx.x & 31u) == 0)
+  {
     dm.occupancy[vid] = value;
     dm.mean[vid] = vm;
     setVoxelBit(dm, g, vid, vm.y >= mp.sample_threshold);
-#pragma unroll
+  #pragma unroll
     for (int c = 0; c < 6; ++c)
     {
       dm.covariance[(size_t)vid * 6 + c] = cov[c];
@@ -1167,18 +1275,52 @@ __global__ void __launch_bounds__(128) applySamplesNdt(DeviceMap dm, Geom g, Map
       dm.intensity[vid] = im;
     }
   }
+  return samples;
+}
+
+// A run is "heavy" when it holds this many hits + recorded misses: it is replayed by a warp instead of a thread.
+constexpr uint32_t kHeavyRun = 16;
+
+__global__ void __launch_bounds__(128) applySamplesNdt(DeviceMap dm, Geom g, MapParams mp, Batch b)
+{
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned samples = 0;
+  if (t < b.counters->run_count)
+  {
+    const uint32_t head = b.run_list[t];
+    const uint32_t vid = b.keys_out[head];
+    const uint32_t k = lowerBound(b.keys_out, b.n, vid + 1u) - head;
+    const uint32_t records = (b.interval_offset[head + k] - b.interval_offset[head]) +
+                             (b.interval_offset[b.n + head + 1u] - b.interval_offset[b.n + head]);
+    if (k + records >= kHeavyRun)
+    {
+      b.run_head[atomicAdd(&b.counters->heavy_count, 1u)] = (int32_t)t;  // run_head[] is free on this path
+    }
+    else
+    {
+      samples = replayNdtRun<false>(dm, g, mp, b, t);
+    }
+  }
   __syncwarp();
   const unsigned s = __reduce_add_sync(0xffffffffu, samples);
-  const unsigned o = __reduce_add_sync(0xffffffffu, ordered);
-  if ((threadIdx.x & 31) == 0)
+  if ((threadIdx.x & 31) == 0 && s)
   {
-    if (s)
-    {
-      atomicAdd(&b.counters->sample_updates, (unsigned long long)s);
-    }
-    if (o)
-    {
-      atomicAdd(&b.counters->ordered_records, (unsigned long long)o);
-    }
+    atomicAdd(&b.counters->sample_updates, (unsigned long long)s);
+  }
+}
+
+// The heavy runs applySamplesNdt set aside, one warp each.
+__global__ void __launch_bounds__(128) applySamplesNdtHeavy(DeviceMap dm, Geom g, MapParams mp, Batch b)
+{
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t count = b.counters->heavy_count;
+  unsigned samples = 0;
+  for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < count; w += warps)
+  {
+    samples += replayNdtRun<true>(dm, g, mp, b, (uint32_t)b.run_head[w]);
+  }
+  if ((threadIdx.x & 31) == 0 && samples)
+  {
+    atomicAdd(&b.counters->sample_updates, (unsigned long long)samples);
   }
 }

@@ -65,6 +65,28 @@ def test_ndt_miss_rays_through_gaussian_voxel(gpu, shape):
     check_counts(g, c)
 
 
+def test_ndt_heavy_run_hits_and_misses_interleaved(gpu):
+    """One voxel takes hundreds of samples AND hundreds of pass-through rays in the same batch, interleaved in ray
+    order (the warp-per-run replay): every miss must see the Gaussian of its moment."""
+    g, c = make_pair(2.0, mode="ndt")
+    rng = np.random.RandomState(42)
+    n = 1200
+    rays = np.empty((2 * n, 3))
+    for i in range(n):
+        sensor = np.array([1.0, 1.0, 7.0]) + rng.uniform(-0.5, 0.5, 3)
+        if i % 3 == 2:
+            # passes through voxel (0,0,0) [0,2)^3 and ends two voxels below it
+            end = np.array([rng.uniform(0.2, 1.8), rng.uniform(0.2, 1.8), -3.0])
+        else:
+            end = np.array([rng.uniform(0.05, 1.95), rng.uniform(0.05, 1.95), 1.0 + 0.05 * rng.normal()])
+        rays[2 * i], rays[2 * i + 1] = sensor, end
+    integrate_both(g, c, rays)           # one batch: ~800 hits + ~400 recorded misses on one voxel
+    compare_maps(g, c, tol_layers=OCC_TOL)
+    integrate_both(g, c, rays[::-1].reshape(-1, 2, 3)[:, ::-1].reshape(-1, 3))  # again, ray order reversed
+    compare_maps(g, c, tol_layers=OCC_TOL)
+    check_counts(g, c)
+
+
 def test_ndt_random_rays_batched(gpu):
     g, c = make_pair(0.25, mode="ndt")
     rng = np.random.RandomState(7)
