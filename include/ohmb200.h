@@ -197,6 +197,21 @@ OHMB200_API int ohmb200_read_regions_async(ohmb200_map *map, int layer, const in
                                            void *dst, size_t bytes);
 OHMB200_API int ohmb200_download_wait(ohmb200_map *map);
 
+/* ohm::RaysQuery / ohm::RaysQueryGpu (ohm/RaysQuery.h:42-139, ohmgpu/RaysQueryGpu.h, kernel ohmgpu/gpu/RaysQuery.cl): for
+ * each ray [origin, end] walk the resident map until the first occupied voxel (value > threshold).  Outputs per ray:
+ * ranges = exit range of the last voxel that is not occupied (a float, widened — Query::ranges() is double),
+ * unobserved_volumes = volume_coefficient * sum over unobserved voxels of (exit^3 - enter^3) (RaysQuery.h:23-40),
+ * terminal_states = ohm::OccupancyType of the last voxel looked at (-2 null, -1 unobserved, 0 free, 1 occupied),
+ * terminal_keys = its key {region x,y,z, local x,y,z}.  Rays the map's filter rejects report 0, 0, null, zeros.
+ * Runs in stream order after every batch queued before it.  The _device form takes and fills device memory and
+ * returns after queueing. */
+OHMB200_API int ohmb200_rays_query(ohmb200_map *map, const double *rays, size_t element_count,
+                                   double volume_coefficient, double *ranges, double *unobserved_volumes,
+                                   int *terminal_states, int32_t *terminal_keys);
+OHMB200_API int ohmb200_rays_query_device(ohmb200_map *map, const double *d_rays, size_t element_count,
+                                          double volume_coefficient, double *d_ranges, double *d_unobserved_volumes,
+                                          int *d_terminal_states, int32_t *d_terminal_keys);
+
 /* GpuLayerCache::upload (ohmgpu/GpuLayerCache.cpp:172-182): make the region resident (creating it if absent)
  * and overwrite one layer chunk from host memory. */
 OHMB200_API int ohmb200_write_region(ohmb200_map *map, const int16_t key_xyz[3], int layer, const void *src,

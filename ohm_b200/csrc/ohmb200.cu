@@ -90,6 +90,7 @@ struct Batch
   const float *intensities;  // [n] or null
   const double *timestamps;  // [n] or null
   uint32_t n;
+  uint32_t heavy_run;  // NDT: a run with this many hits + recorded misses is replayed by a warp (OHMB200_HEAVY_RUN)
   unsigned ray_flags;
   uint32_t stamp;
   double time_base;
@@ -511,6 +512,93 @@ __global__ void gatherRegions(const uint4 *slab, const uint32_t *slots, uint4 *d
   }
 }
 
+// ohm::RaysQuery::onExecute (ohm/RaysQuery.cpp:109-199; the OpenCL form is ohmgpu/gpu/RaysQuery.cl) on the resident map,
+// one thread per ray: walk until the first occupied voxel.  Same fp64 walk as the mappers, so ranges, volumes, the
+// terminal state and the terminal key are those of the CPU query on the same map.  A region that is not resident reads
+// as unobserved.  (The reference never resets terminal state/key between rays: a ray whose keys are out of range
+// repeats the previous ray's answer there; here it reports kNull.)
+__global__ void __launch_bounds__(128) raysQuery(DeviceMap dm, Geom g, MapParams mp, const double *rays, uint32_t n,
+                                                 double volume_coefficient, double *ranges, double *volumes,
+                                                 int *states, int32_t *keys)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+  {
+    return;
+  }
+  double start[3], end[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+  {
+    start[a] = rays[(size_t)i * 6 + a];
+    end[a] = rays[(size_t)i * 6 + 3 + a];
+  }
+  double unobserved_volume = 0.0;
+  float range = 0.0f;
+  int state = -2;  // OccupancyType::kNull
+  Key terminal;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+  {
+    terminal.r[a] = terminal.l[a] = 0;
+  }
+  unsigned filter_flags = 0;
+  Key skey, ekey;
+  if (applyRayFilter(mp, start, end, filter_flags) && voxelKey(g, start, skey) && voxelKey(g, end, ekey))
+  {
+    Walk w;
+    walkInit(w, g, start, end, skey, ekey);
+    unsigned long long last_region = kEmptyKey;
+    int slot = -1;
+    double last_time = 0;
+    bool go_on = true;
+    // the visit lambda of RaysQuery.cpp:129-158
+    auto visit = [&](const Key &key, double enter_range, double exit_range) {
+      const unsigned long long region = packRegion(key.r[0], key.r[1], key.r[2]);
+      if (region != last_region)
+      {
+        slot = regionFind(dm, region);
+        last_region = region;
+      }
+      const float value = (slot >= 0) ? dm.occupancy[(size_t)slot * g.vpr + voxelIndex(g, key)] : INFINITY;
+      const bool is_unobserved = value == INFINITY;
+      const bool is_occupied = !is_unobserved && value > mp.threshold_value;
+      unobserved_volume +=
+        is_unobserved ?
+          (volume_coefficient * (exit_range * exit_range * exit_range - enter_range * enter_range * enter_range)) :
+          0.0;
+      range = (!is_occupied) ? (float)exit_range : range;
+      state = is_unobserved ? -1 : (is_occupied ? 1 : 0);
+      terminal = key;
+      go_on = !is_occupied;
+    };
+    // walkLineVoxels with an aborting visitor (LineWalkCompute.h:392-410)
+    const unsigned max_steps = (unsigned)(abs(w.remaining[0]) + abs(w.remaining[1]) + abs(w.remaining[2]));
+    unsigned count = 0;
+    while (go_on && w.limit < 7u && !walkAtEnd(w) && count <= max_steps)
+    {
+      const double t = walkNextTime(w);
+      visit(w.cur, last_time, t);
+      last_time = t;
+      ++count;
+      walkStep(w, g);
+    }
+    if (go_on)
+    {
+      visit(ekey, last_time, w.length);
+    }
+  }
+  ranges[i] = (double)range;
+  volumes[i] = unobserved_volume;
+  states[i] = state;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+  {
+    keys[(size_t)i * 6 + a] = terminal.r[a];
+    keys[(size_t)i * 6 + 3 + a] = terminal.l[a];
+  }
+}
+
 // ohmb200_clear: wipe only the regions that exist (the slabs of free slots are clean already), then free the table.
 struct ClearTable
 {
@@ -633,6 +721,7 @@ struct ohmb200_map
   int algo = 1;           // 1 = region-binned walk (shared-memory tiles), 0 = one thread per ray (global counters)
   size_t tile_bytes = 0;  // dynamic shared memory of walkRegions
   int walk_ctas_per_sm = 1;
+  uint32_t heavy_run = 16;
   uint32_t *tsdf_near = nullptr;  // TSDF: per-batch bit per voxel, "visited near a sample in this batch"
   size_t voxel_bit_bytes = 0;     // size of dm.voxel_bits (and of tsdf_near)
   ohmb200_params params{};
@@ -684,6 +773,8 @@ struct ohmb200_map
   cudaEvent_t stage_done[2] = { nullptr, nullptr };
   bool stage_pending[2] = { false, false };
   int stage_next = 0;
+  void *d_query = nullptr;  // staging of ohmb200_rays_query
+  size_t query_bytes = 0;
   int *d_lookup_missing = nullptr;  // device flag: an asynchronous download named a region that is not resident
   // profiling
   bool profiling = false;
@@ -866,7 +957,9 @@ int ensureScratch(ohmb200_map *m, size_t n)
   cudaFree(b.last_exit);
   cudaFree(m->cub_temp);
   b.last_exit = nullptr;
-  const size_t cap = std::max<size_t>(n, 4096);
+  // Grow with headroom, in 16 Ki-ray steps: a stream of sweeps whose size creeps up (clipped rays vary from sweep to
+  // sweep) must not pay ~50 cudaFree/cudaMalloc calls — tens of milliseconds — every time it sets a new maximum.
+  const size_t cap = std::max<size_t>(((n + n / 8 + 16383) / 16384) * 16384, 4096);
   int rc = 0;
   rc |= deviceAlloc(b.keys_in, cap);
   rc |= deviceAlloc(b.keys_out, cap);
@@ -964,6 +1057,7 @@ int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_i
   b.intensities = d_intensities;
   b.timestamps = (m->dm.touch_time) ? d_timestamps : nullptr;
   b.n = (uint32_t)n;
+  b.heavy_run = m->heavy_run;
   b.ray_flags = ray_flags;
   b.stamp = ++m->stamp;
   b.time_base = m->first_ray_time;
@@ -1339,6 +1433,10 @@ ohmb200_map *ohmb200_create(const ohmb200_params *params, int mode, size_t devic
   {
     m->algo = atoi(env) ? 1 : 0;
   }
+  if (const char *env = getenv("OHMB200_HEAVY_RUN"))
+  {
+    m->heavy_run = (uint32_t)std::max(1, atoi(env));
+  }
   const bool ndt = mode == OHMB200_MODE_NDT || mode == OHMB200_MODE_NDT_TM;
   if (ndt)
   {
@@ -1537,6 +1635,7 @@ void ohmb200_destroy(ohmb200_map *m)
     }
   }
   cudaFree(m->d_lookup_missing);
+  cudaFree(m->d_query);
   if (m->download_stream)
   {
     cudaStreamDestroy(m->download_stream);
@@ -1658,7 +1757,7 @@ size_t ohmb200_integrate(ohmb200_map *m, const double *rays, size_t element_coun
     cudaFree(m->d_rays[buf]);
     cudaFree(m->d_intensities[buf]);
     cudaFree(m->d_timestamps[buf]);
-    const size_t cap = std::max<size_t>(n, 4096);
+    const size_t cap = std::max<size_t>(((n + n / 8 + 16383) / 16384) * 16384, 4096);
     if (cudaMalloc(&m->d_rays[buf], sizeof(double) * 6 * cap) != cudaSuccess ||
         cudaMalloc(&m->d_intensities[buf], sizeof(float) * cap) != cudaSuccess ||
         cudaMalloc(&m->d_timestamps[buf], sizeof(double) * cap) != cudaSuccess)
@@ -1847,6 +1946,74 @@ int ohmb200_read_regions(ohmb200_map *m, int layer, const int16_t *keys_xyz, siz
 int ohmb200_read_region(ohmb200_map *m, const int16_t key_xyz[3], int layer, void *dst, size_t bytes)
 {
   return ohmb200_read_regions(m, layer, key_xyz, 1, dst, bytes);
+}
+
+int ohmb200_rays_query_device(ohmb200_map *m, const double *d_rays, size_t element_count, double volume_coefficient,
+                              double *d_ranges, double *d_unobserved_volumes, int *d_terminal_states,
+                              int32_t *d_terminal_keys)
+{
+  if (!m || !d_rays || !d_ranges || !d_unobserved_volumes || !d_terminal_states || !d_terminal_keys)
+  {
+    return setError(OHMB200_E_INVALID, "ohmb200_rays_query_device: null argument");
+  }
+  if (!m->dm.occupancy)
+  {
+    return setError(OHMB200_E_INVALID, "the rays query needs the occupancy layer");
+  }
+  const size_t n = element_count / 2;
+  if (n == 0)
+  {
+    return OHMB200_OK;
+  }
+  cudaSetDevice(m->device);
+  // in stream order: the query sees every batch queued before it
+  raysQuery<<<(unsigned)((n + 127) / 128), 128, 0, m->stream>>>(m->dm, m->geom, m->mp, d_rays, (uint32_t)n,
+                                                                volume_coefficient, d_ranges, d_unobserved_volumes,
+                                                                d_terminal_states, d_terminal_keys);
+  CUDA_TRY(cudaGetLastError());
+  return OHMB200_OK;
+}
+
+int ohmb200_rays_query(ohmb200_map *m, const double *rays, size_t element_count, double volume_coefficient,
+                       double *ranges, double *unobserved_volumes, int *terminal_states, int32_t *terminal_keys)
+{
+  if (!m || !rays || !ranges || !unobserved_volumes || !terminal_states || !terminal_keys)
+  {
+    return setError(OHMB200_E_INVALID, "ohmb200_rays_query: null argument");
+  }
+  const size_t n = element_count / 2;
+  if (n == 0)
+  {
+    return OHMB200_OK;
+  }
+  cudaSetDevice(m->device);
+  // one device block: rays | ranges | volumes | keys | states
+  const size_t bytes = n * (6 * sizeof(double) + 2 * sizeof(double) + 6 * sizeof(int32_t) + sizeof(int));
+  if (bytes > m->query_bytes)
+  {
+    cudaFree(m->d_query);
+    m->query_bytes = 0;
+    CUDA_TRY(cudaMalloc(&m->d_query, bytes));
+    m->query_bytes = bytes;
+  }
+  double *d_rays = (double *)m->d_query;
+  double *d_ranges = d_rays + 6 * n;
+  double *d_volumes = d_ranges + n;
+  int32_t *d_keys = (int32_t *)(d_volumes + n);
+  int *d_states = (int *)(d_keys + 6 * n);
+  cudaStream_t s = m->stream;
+  CUDA_TRY(cudaMemcpyAsync(d_rays, rays, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, s));
+  const int rc = ohmb200_rays_query_device(m, d_rays, 2 * n, volume_coefficient, d_ranges, d_volumes, d_states, d_keys);
+  if (rc)
+  {
+    return rc;
+  }
+  CUDA_TRY(cudaMemcpyAsync(ranges, d_ranges, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(unobserved_volumes, d_volumes, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(terminal_keys, d_keys, sizeof(int32_t) * 6 * n, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(terminal_states, d_states, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return OHMB200_OK;
 }
 
 int ohmb200_read_regions_async(ohmb200_map *m, int layer, const int16_t *keys_xyz, size_t count, void *dst, size_t bytes)

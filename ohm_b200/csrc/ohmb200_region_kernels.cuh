@@ -447,20 +447,6 @@ __device__ __forceinline__ int queuePop(SegmentQueue &q, const Batch &b, const W
   return 1;
 }
 
-// Next work item of the persistent CTA into `slot` (one thread calls this); slot.slot == 0xFFFFFFFF when none is left.
-__device__ __forceinline__ void fetchWorkItem(const Batch &b, WorkItem &slot)
-{
-  const uint32_t w = atomicAdd(&b.counters->work_next, 1u);
-  if (w < min(b.counters->item_count, b.item_capacity))
-  {
-    slot = b.items[w];
-  }
-  else
-  {
-    slot.slot = 0xFFFFFFFFu;
-  }
-}
-
 // What a lane needs to resume a segment: the segment itself and the walk constants of its ray.
 struct SegmentWalk
 {
@@ -501,7 +487,7 @@ __device__ __forceinline__ void loadSegmentWalk(const Batch &b, const uint4 &raw
 __global__ void __launch_bounds__(kWalkThreads, 2) walkRegions(DeviceMap dm, Geom g, MapParams mp, Batch b, int has_samples)
 {
   extern __shared__ uint32_t tile[];
-  __shared__ WorkItem items[2];  // the current item and the prefetched next one
+  __shared__ WorkItem item;
   // per-warp reservation of ordered-miss record slots: (base << 32) | used
   __shared__ unsigned long long record_chunk[kWalkThreads / 32];
   __shared__ SegmentQueue queue;
@@ -513,14 +499,22 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegions(DeviceMap dm, Geo
     record_chunk[warp] = (unsigned long long)kRecordChunk;  // "full": the first record reserves a chunk
   }
 
-  if (tid == 0)
+  for (;;)
   {
-    fetchWorkItem(b, items[0]);
-  }
-  for (uint32_t phase = 0;; phase ^= 1u)
-  {
-    __syncthreads();  // items[phase] is in place (fetched before the loop, or during the previous item's walk)
-    const WorkItem &item = items[phase];
+    __syncthreads();
+    if (tid == 0)
+    {
+      const uint32_t w = atomicAdd(&b.counters->work_next, 1u);
+      if (w < min(b.counters->item_count, b.item_capacity))
+      {
+        item = b.items[w];
+      }
+      else
+      {
+        item.slot = 0xFFFFFFFFu;
+      }
+    }
+    __syncthreads();
     if (item.slot == 0xFFFFFFFFu)
     {
       return;
@@ -555,10 +549,6 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegions(DeviceMap dm, Geo
       }
     }
     queueBuild(queue, b, item);
-    if (tid == blockDim.x - 1u)
-    {
-      fetchWorkItem(b, items[phase ^ 1u]);  // two dependent global round trips, hidden behind the walk
-    }
 
     for (;;)
     {
@@ -831,7 +821,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsNdt(const __grid_c
                                                                   const __grid_constant__ MapParams mp, const __grid_constant__ Batch b)
 {
   extern __shared__ uint32_t tile[];
-  __shared__ WorkItem items[2];  // the current item and the prefetched next one
+  __shared__ WorkItem item;
   __shared__ unsigned long long record_chunk[kWalkThreads / 32];
   __shared__ unsigned long long gauss_chunk[kWalkThreads / 32];
   __shared__ SegmentQueue queue;
@@ -845,14 +835,22 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsNdt(const __grid_c
     record_chunk[warp] = (unsigned long long)kRecordChunk;
     gauss_chunk[warp] = (unsigned long long)kRecordChunk;
   }
-  if (tid == 0)
-  {
-    fetchWorkItem(b, items[0]);
-  }
-  for (uint32_t phase = 0;; phase ^= 1u)
+  for (;;)
   {
     __syncthreads();
-    const WorkItem &item = items[phase];
+    if (tid == 0)
+    {
+      const uint32_t w = atomicAdd(&b.counters->work_next, 1u);
+      if (w < min(b.counters->item_count, b.item_capacity))
+      {
+        item = b.items[w];
+      }
+      else
+      {
+        item.slot = 0xFFFFFFFFu;
+      }
+    }
+    __syncthreads();
     if (item.slot == 0xFFFFFFFFu)
     {
       return;
@@ -882,10 +880,6 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsNdt(const __grid_c
       atomicOr(&tile[tileWord(v)], kTileFlag << ((v & 1u) * 16u));
     }
     queueBuild(queue, b, item);
-    if (tid == blockDim.x - 1u)
-    {
-      fetchWorkItem(b, items[phase ^ 1u]);
-    }
 
     for (;;)
     {
@@ -1278,8 +1272,7 @@ __device__ __forceinline__ unsigned replayNdtRun(const DeviceMap &dm, const Geom
   return samples;
 }
 
-// A run is "heavy" when it holds this many hits + recorded misses: it is replayed by a warp instead of a thread.
-constexpr uint32_t kHeavyRun = 16;
+// A run is "heavy" when it holds b.heavy_run hits + recorded misses: it is replayed by a warp instead of a thread.
 
 __global__ void __launch_bounds__(128) applySamplesNdt(DeviceMap dm, Geom g, MapParams mp, Batch b)
 {
@@ -1292,7 +1285,7 @@ __global__ void __launch_bounds__(128) applySamplesNdt(DeviceMap dm, Geom g, Map
     const uint32_t k = lowerBound(b.keys_out, b.n, vid + 1u) - head;
     const uint32_t records = (b.interval_offset[head + k] - b.interval_offset[head]) +
                              (b.interval_offset[b.n + head + 1u] - b.interval_offset[b.n + head]);
-    if (k + records >= kHeavyRun)
+    if (k + records >= b.heavy_run)
     {
       b.run_head[atomicAdd(&b.counters->heavy_count, 1u)] = (int32_t)t;  // run_head[] is free on this path
     }

@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsTsdf(const __grid_
                                                                    const __grid_constant__ Batch b, const uint32_t *near)
 {
   extern __shared__ uint32_t tile[];
-  __shared__ WorkItem items[2];  // the current item and the prefetched next one
+  __shared__ WorkItem item;
   __shared__ unsigned long long record_chunk[kWalkThreads / 32];
   __shared__ SegmentQueue queue;
   const uint32_t words = tileWords(g.vpr);
@@ -183,14 +183,22 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsTsdf(const __grid_
   {
     record_chunk[warp] = (unsigned long long)kRecordChunk;
   }
-  if (tid == 0)
-  {
-    fetchWorkItem(b, items[0]);
-  }
-  for (uint32_t phase = 0;; phase ^= 1u)
+  for (;;)
   {
     __syncthreads();
-    const WorkItem &item = items[phase];
+    if (tid == 0)
+    {
+      const uint32_t w = atomicAdd(&b.counters->work_next, 1u);
+      if (w < min(b.counters->item_count, b.item_capacity))
+      {
+        item = b.items[w];
+      }
+      else
+      {
+        item.slot = 0xFFFFFFFFu;
+      }
+    }
+    __syncthreads();
     if (item.slot == 0xFFFFFFFFu)
     {
       return;
@@ -222,10 +230,6 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsTsdf(const __grid_
       }
     }
     queueBuild(queue, b, item);
-    if (tid == blockDim.x - 1u)
-    {
-      fetchWorkItem(b, items[phase ^ 1u]);
-    }
 
     for (;;)
     {

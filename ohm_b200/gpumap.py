@@ -222,6 +222,19 @@ class GpuMap:
         """Wait for every queued region_layers_async download (GpuMap::syncVoxels' wait on the cache events)."""
         self._check(self.L.ohmb200_download_wait(self.h))
 
+    def rays_query(self, rays, volume_coefficient=1.0):
+        """ohm::RaysQuery on the resident map (ohm/RaysQuery.h:42-139): per ray [origin, end], the range to the first
+        occupied voxel, the unobserved volume, the terminal OccupancyType and the terminal voxel key.  Returns
+        (ranges f64[n], unobserved_volumes f64[n], terminal_states i32[n], terminal_keys i32[n, 6])."""
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 3)
+        n = rays.shape[0] // 2
+        ranges, volumes = np.zeros(n), np.zeros(n)
+        states = np.zeros(n, dtype=np.int32)
+        keys = np.zeros((n, 6), dtype=np.int32)
+        self._check(self.L.ohmb200_rays_query(self.h, _ptr(rays), rays.shape[0], float(volume_coefficient), _ptr(ranges),
+                                              _ptr(volumes), _ptr(states), _ptr(keys)))
+        return ranges, volumes, states, keys
+
     def write_region(self, key, layer, data):
         key = np.ascontiguousarray(key, dtype=np.int16)
         data = np.ascontiguousarray(data)

@@ -1490,3 +1490,87 @@ size_t oracle_integrate_tsdf(oracle_map *m, const double *rays, size_t element_c
   }
   return element_count / 2;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* RaysQuery::onExecute (ohm/RaysQuery.cpp:109-199)                                            */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct rays_query_ctx
+{
+  const oracle_map *m;
+  double volume_coefficient;
+  double unobserved_volume;
+  float range;
+  int terminal_state;
+  int32_t terminal_key[6];
+  chunk *last_chunk;
+  int16_t last_region[3];
+} rays_query_ctx;
+
+/* the visit lambda, RaysQuery.cpp:129-158 */
+static int rays_query_visit(void *vctx, const int32_t key[6], double enter_range, double exit_range)
+{
+  rays_query_ctx *c = (rays_query_ctx *)vctx;
+  const oracle_map *m = c->m;
+  const int16_t region[3] = { (int16_t)key[0], (int16_t)key[1], (int16_t)key[2] };
+  const size_t voxel_index =
+    (size_t)key[3] + (size_t)key[4] * m->p.region_dim[0] + (size_t)key[5] * m->p.region_dim[0] * m->p.region_dim[1];
+  float occupancy_value = INFINITY; /* unobservedOccupancyValue() */
+  chunk *ch = (c->last_chunk && region[0] == c->last_region[0] && region[1] == c->last_region[1] &&
+               region[2] == c->last_region[2]) ?
+                c->last_chunk :
+                map_region((oracle_map *)m, region, 0);
+  if (ch)
+  {
+    occupancy_value = ((const float *)ch->layers[ORC_LAYER_OCCUPANCY])[voxel_index];
+    c->last_region[0] = region[0];
+    c->last_region[1] = region[1];
+    c->last_region[2] = region[2];
+  }
+  c->last_chunk = ch;
+  const int is_unobserved = occupancy_value == INFINITY;
+  const int is_occupied = !is_unobserved && occupancy_value > m->p.threshold_value;
+  c->unobserved_volume +=
+    is_unobserved ?
+      (c->volume_coefficient * (exit_range * exit_range * exit_range - enter_range * enter_range * enter_range)) :
+      0.0f;
+  c->range = (!is_occupied) ? (float)exit_range : c->range;
+  c->terminal_state = is_unobserved ? ORC_OCCUPANCY_UNOBSERVED : (is_occupied ? ORC_OCCUPANCY_OCCUPIED : ORC_OCCUPANCY_FREE);
+  memcpy(c->terminal_key, key, sizeof(c->terminal_key));
+  return !is_occupied;
+}
+
+size_t oracle_rays_query(const oracle_map *m, const double *rays, size_t element_count, double volume_coefficient,
+                         double *ranges, double *unobserved_volumes, int *terminal_states, int32_t *terminal_keys)
+{
+  rays_query_ctx c;
+  memset(&c, 0, sizeof(c));
+  c.m = m;
+  c.volume_coefficient = volume_coefficient;
+  c.terminal_state = ORC_OCCUPANCY_NULL; /* RaysQuery.cpp:119-120: declared outside the ray loop, never reset */
+  size_t n = 0;
+  for (size_t i = 0; i + 1 < element_count; i += 2, ++n)
+  {
+    double start[3] = { rays[3 * i], rays[3 * i + 1], rays[3 * i + 2] };
+    double end[3] = { rays[3 * i + 3], rays[3 * i + 4], rays[3 * i + 5] };
+    unsigned filter_flags = 0;
+    c.unobserved_volume = 0.0;
+    c.range = 0.0f;
+    if (!apply_filter(m, start, end, &filter_flags))
+    {
+      ranges[n] = c.range;
+      unobserved_volumes[n] = c.unobserved_volume;
+      terminal_states[n] = ORC_OCCUPANCY_NULL;
+      for (int k = 0; k < 6; ++k)
+      {
+        terminal_keys[6 * n + k] = 0; /* Key::kNull is reported as all zero with *_states == NULL */
+      }
+      continue;
+    }
+    walk_segment_keys(m, start, end, 0u, rays_query_visit, &c);
+    ranges[n] = c.range;
+    unobserved_volumes[n] = c.unobserved_volume;
+    terminal_states[n] = c.terminal_state;
+    memcpy(terminal_keys + 6 * n, c.terminal_key, sizeof(c.terminal_key));
+  }
+  return n;
+}

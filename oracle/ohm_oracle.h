@@ -118,6 +118,19 @@ size_t oracle_integrate_ndt(oracle_map *m, const double *rays, size_t element_co
 size_t oracle_integrate_tsdf(oracle_map *m, const double *rays, size_t element_count, const float *intensities,
                              const double *timestamps, unsigned ray_flags);
 
+/* ohm::RaysQuery::onExecute (ohm/RaysQuery.cpp:109-199): per ray, walk until the first occupied voxel.  ranges[n] = exit
+ * range of the last voxel that is not occupied (a float, stored as double), unobserved_volumes[n] = volume_coefficient * sum over
+ * unobserved voxels of (exit^3 - enter^3), terminal_states[n] = OccupancyType of the last voxel visited (ohm/OccupancyType.h:
+ * -2 null, -1 unobserved, 0 free, 1 occupied), terminal_keys[6n..] = its key.  A ray the filter rejects reports 0, 0,
+ * null.  (terminal state/key are NOT reset between rays in the reference: a ray that visits nothing repeats the
+ * previous ray's.)  Returns the number of rays. */
+#define ORC_OCCUPANCY_NULL (-2)
+#define ORC_OCCUPANCY_UNOBSERVED (-1)
+#define ORC_OCCUPANCY_FREE 0
+#define ORC_OCCUPANCY_OCCUPIED 1
+size_t oracle_rays_query(const oracle_map *m, const double *rays, size_t element_count, double volume_coefficient,
+                         double *ranges, double *unobserved_volumes, int *terminal_states, int32_t *terminal_keys);
+
 size_t oracle_region_count(const oracle_map *m);
 /* Writes up to cap region keys (3 x int16 each), sorted (z,y,x ascending); returns the total count. */
 size_t oracle_region_keys(const oracle_map *m, int16_t *keys, size_t cap);

@@ -106,6 +106,8 @@ def lib():
         f = getattr(L, name)
         f.argtypes = [vp, dp, C.c_size_t, fp, dp, C.c_uint]
         f.restype = C.c_size_t
+    L.oracle_rays_query.argtypes = [vp, dp, C.c_size_t, C.c_double, dp, dp, C.POINTER(C.c_int), ip]
+    L.oracle_rays_query.restype = C.c_size_t
     L.oracle_count_walk_visits.argtypes = [vp, dp, C.c_size_t, C.c_uint]
     L.oracle_count_walk_visits.restype = C.c_uint64
     L.oracle_region_count.argtypes = [vp]
@@ -210,6 +212,20 @@ class OracleMap:
             "tsdf": self.L.oracle_integrate_tsdf,
         }[self.mode]
         return fn(self.h, _dptr(rays), n, ip, tp, int(ray_flags))
+
+    def rays_query(self, rays, volume_coefficient=1.0):
+        """ohm::RaysQuery (ohm/RaysQuery.cpp:109-199): (ranges f64[n], unobserved_volumes f64[n], terminal_states i32[n],
+        terminal_keys i32[n, 6])."""
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 3)
+        n = rays.shape[0] // 2
+        ranges, volumes = np.zeros(n), np.zeros(n)
+        states = np.zeros(n, dtype=np.int32)
+        keys = np.zeros((n, 6), dtype=np.int32)
+        got = self.L.oracle_rays_query(self.h, _dptr(rays), rays.shape[0], float(volume_coefficient), _dptr(ranges),
+                                       _dptr(volumes), states.ctypes.data_as(C.POINTER(C.c_int)),
+                                       keys.ctypes.data_as(C.POINTER(C.c_int32)))
+        assert got == n
+        return ranges, volumes, states, keys
 
     def count_walk_visits(self, rays, walk_flags=0):
         rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 3)

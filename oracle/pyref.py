@@ -58,6 +58,8 @@ def lib():
     L.ref_region_layer.restype = C.c_size_t
     L.ref_walk_segment.argtypes = [vp, dp, dp, C.c_uint, C.POINTER(C.c_int32), dp, dp, C.c_size_t]
     L.ref_walk_segment.restype = C.c_size_t
+    L.ref_rays_query.argtypes = [vp, dp, C.c_size_t, C.c_double, dp, dp, C.POINTER(C.c_int), C.POINTER(C.c_int32)]
+    L.ref_rays_query.restype = C.c_size_t
     _lib = L
     return L
 
@@ -135,6 +137,20 @@ class ReferenceMap:
         for key in self.region_keys():
             out[tuple(int(k) for k in key)] = {l: self.region_layer(key, l) for l in self.layers()}
         return out
+
+    def rays_query(self, rays, volume_coefficient=1.0):
+        """ohm::RaysQuery on the reference map: (ranges, unobserved_volumes, terminal_states, terminal_keys)."""
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 3)
+        n = rays.shape[0] // 2
+        ranges, volumes = np.zeros(n), np.zeros(n)
+        states = np.zeros(n, dtype=np.int32)
+        keys = np.zeros((n, 6), dtype=np.int32)
+        dp = C.POINTER(C.c_double)
+        got = self.L.ref_rays_query(self.h, rays.ctypes.data_as(dp), rays.shape[0], float(volume_coefficient),
+                                    ranges.ctypes.data_as(dp), volumes.ctypes.data_as(dp),
+                                    states.ctypes.data_as(C.POINTER(C.c_int)), keys.ctypes.data_as(C.POINTER(C.c_int32)))
+        assert got == n
+        return ranges, volumes, states, keys
 
     def walk_segment(self, start, end, walk_flags=0, cap=1 << 16):
         start = np.ascontiguousarray(start, dtype=np.float64)

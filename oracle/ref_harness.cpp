@@ -263,3 +263,39 @@ extern "C" size_t ref_walk_segment(void *h, const double start[3], const double 
                        glm::dvec3(end[0], end[1], end[2]), walk_flags);
   return n;
 }
+
+#include <ohm/RaysQuery.h>
+
+// ohm::RaysQuery on the reference map (ohm/RaysQuery.cpp:109-199).  Null keys are reported as six zeros.
+extern "C" size_t ref_rays_query(void *h, const double *rays, size_t element_count, double volume_coefficient,
+                                 double *ranges, double *unobserved_volumes, int *terminal_states, int32_t *terminal_keys)
+{
+  auto *r = static_cast<RefMap *>(h);
+  ohm::RaysQuery query;
+  query.setMap(r->map.get());
+  query.setVolumeCoefficient(volume_coefficient);
+  query.setRays(reinterpret_cast<const glm::dvec3 *>(rays), element_count);
+  if (!query.execute())
+  {
+    return 0;
+  }
+  const size_t n = query.numberOfResults();
+  const double *q_ranges = query.ranges();  // stored as double, assigned from a float (RaysQuery.cpp:121,151)
+  const double *q_volumes = query.unobservedVolumes();
+  const ohm::OccupancyType *q_states = query.terminalOccupancyTypes();
+  const ohm::Key *q_keys = query.intersectedVoxels();
+  for (size_t i = 0; i < n; ++i)
+  {
+    ranges[i] = q_ranges[i];
+    unobserved_volumes[i] = q_volumes[i];
+    terminal_states[i] = static_cast<int>(q_states[i]);
+    const bool null_key = q_keys[i].isNull();
+    terminal_keys[6 * i + 0] = null_key ? 0 : q_keys[i].regionKey().x;
+    terminal_keys[6 * i + 1] = null_key ? 0 : q_keys[i].regionKey().y;
+    terminal_keys[6 * i + 2] = null_key ? 0 : q_keys[i].regionKey().z;
+    terminal_keys[6 * i + 3] = null_key ? 0 : q_keys[i].localKey().x;
+    terminal_keys[6 * i + 4] = null_key ? 0 : q_keys[i].localKey().y;
+    terminal_keys[6 * i + 5] = null_key ? 0 : q_keys[i].localKey().z;
+  }
+  return n;
+}

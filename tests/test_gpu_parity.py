@@ -217,6 +217,33 @@ def test_write_region_roundtrip(gpu):
     assert g.region_count() == 1
 
 
+@pytest.mark.parametrize("mode", ["occupancy", "ndt", "tsdf"])
+def test_repeatable_bit_for_bit(gpu, mode):
+    """The same rays into a fresh map, six times: every layer of every region must come out bit-identical (a data
+    race between the persistent CTAs that share a region shows up here long before it shows up against the oracle)."""
+    rays = np.concatenate([cube_rays(6000), random_rays(3000, 9.0, seed=3)])
+    cls = {"occupancy": ohm_b200.GpuMap, "ndt": ohm_b200.GpuNdtMap, "tsdf": ohm_b200.GpuTsdfMap}[mode]
+    first = None
+    for rep in range(6):
+        g = cls(0.2, device_bytes=1 << 30)
+        g.integrate_rays(rays[:8000])
+        g.integrate_rays(rays[8000:])
+        d = g.dump()
+        g.close()
+        if first is None:
+            first = d
+            continue
+        assert sorted(d) == sorted(first)
+        for key in d:
+            for layer, arr in d[key].items():
+                a, b = np.ascontiguousarray(arr), np.ascontiguousarray(first[key][layer])
+                if mode == "ndt" and layer == gm.LAYER_OCCUPANCY:
+                    # NDT log-odds: the order of float atomics on Gaussian voxels is not fixed
+                    assert np.allclose(np.nan_to_num(a, posinf=1e30), np.nan_to_num(b, posinf=1e30), rtol=1e-5, atol=1e-5)
+                else:
+                    assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), (rep, key, gm.LAYER_NAMES[layer])
+
+
 def test_async_download_is_a_snapshot(gpu):
     """ohmb200_read_regions_async: the chunks are those of the moment of the call (stream order), whatever is
     integrated while the copy runs; two downloads may be in flight; a key that is not resident is reported by the wait."""

@@ -170,3 +170,29 @@ def test_clip_box_filter():
     o.integrate_rays(rays)
     r.integrate_rays(rays)
     assert_identical(o, r)
+
+
+def query_rays(n, seed, extent=9.0):
+    rng = np.random.RandomState(seed)
+    q = np.empty((2 * n, 3))
+    q[0::2] = rng.uniform(-2, 2, size=(n, 3))
+    q[1::2] = rng.uniform(-extent, extent, size=(n, 3))
+    q[4] = [np.nan, 0, 0]          # rejected by the filter: range 0, volume 0, kNull
+    q[9] = q[8]                    # degenerate: one voxel
+    return q
+
+
+def test_rays_query():
+    # ohm::RaysQuery (ohm/RaysQuery.cpp:109-199) on a populated map: range to the first occupied voxel, unobserved
+    # volume, terminal state and key, for rays through free, occupied and unobserved space
+    o, r = po.OracleMap(0.2), pr.ReferenceMap(0.2)
+    rays = np.concatenate([cube_rays(6000), random_rays(2000, 7.0, 5)])
+    o.integrate_rays(rays)
+    r.integrate_rays(rays)
+    q = query_rays(4000, 21)
+    for coefficient in (1.0, 4.0 / 3.0 * np.pi * 1e-3):
+        a, b = o.rays_query(q, coefficient), r.rays_query(q, coefficient)
+        for name, x, y in zip(("ranges", "unobserved volumes", "terminal states", "terminal keys"), a, b):
+            assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), name
+    states = a[2]
+    assert (states == -2).sum() == 1 and (states == 1).sum() > 100 and (states == -1).sum() > 10 and (states == 0).sum() > 0
