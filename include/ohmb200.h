@@ -212,6 +212,16 @@ OHMB200_API int ohmb200_rays_query_device(ohmb200_map *map, const double *d_rays
                                           double volume_coefficient, double *d_ranges, double *d_unobserved_volumes,
                                           int *d_terminal_states, int32_t *d_terminal_keys);
 
+/* ohm::LineKeysQuery / ohm::LineKeysQueryGpu (ohm/LineKeysQuery.h:20-90, ohmgpu/LineKeysQueryGpu.h, kernel
+ * ohmgpu/gpu/LineKeys.cl): the voxel keys along each line [start, end], both end voxels included
+ * (calculateSegmentKeys, ohm/CalculateSegmentKeys.cpp).  For line i the keys are keys[6 * result_indices[i] ...], six
+ * int32 each {region x,y,z, local x,y,z}, result_counts[i] of them.  *total_keys receives the sum of the counts; keys
+ * are written only when key_capacity (in keys) >= *total_keys — call once with keys = NULL, key_capacity = 0 to size the
+ * buffer.  Uses only the map's geometry (resolution, region dimensions, origin). */
+OHMB200_API int ohmb200_line_keys_query(ohmb200_map *map, const double *rays, size_t element_count,
+                                        uint64_t *result_indices, uint64_t *result_counts, int32_t *keys,
+                                        size_t key_capacity, size_t *total_keys);
+
 /* GpuLayerCache::upload (ohmgpu/GpuLayerCache.cpp:172-182): make the region resident (creating it if absent)
  * and overwrite one layer chunk from host memory. */
 OHMB200_API int ohmb200_write_region(ohmb200_map *map, const int16_t key_xyz[3], int layer, const void *src,

@@ -365,6 +365,101 @@ public:
   }
   float sparsityCompensationFactor() const { return params_.tsdf_sparsity; }
 };
+
+/// ohm::OccupancyType (ohm/OccupancyType.h:14-24).
+enum OccupancyType
+{
+  kNull = -2,
+  kUnobserved = -1,
+  kFree = 0,
+  kOccupied = 1
+};
+
+/// ohm::RaysQuery / ohm::RaysQueryGpu (ohm/RaysQuery.h:42-139, ohmgpu/RaysQueryGpu.h) on a GpuMap: for each ray, the range
+/// to the first occupied voxel, the unobserved volume along it and the state of the voxel it ends in.  The map is
+/// queried where it lives (no syncVoxels needed); execute() runs after every batch already handed to integrateRays().
+class RaysQueryGpu
+{
+public:
+  explicit RaysQueryGpu(GpuMap *map = nullptr) : map_(map) {}
+
+  void setMap(GpuMap *map) { map_ = map; }
+  GpuMap *map() const { return map_; }
+
+  void setVolumeCoefficient(double coefficient) { volume_coefficient_ = coefficient; }
+  double volumeCoefficient() const { return volume_coefficient_; }
+
+  void setRays(const glm::dvec3 *rays, size_t element_count)
+  {
+    rays_.clear();
+    addRays(rays, element_count);
+  }
+  void addRays(const glm::dvec3 *rays, size_t element_count)
+  {
+    rays_.insert(rays_.end(), rays, rays + (element_count & ~size_t(1)));
+  }
+  void addRay(const glm::dvec3 &origin, const glm::dvec3 &end_point)
+  {
+    rays_.push_back(origin);
+    rays_.push_back(end_point);
+  }
+  void clearRays() { rays_.clear(); }
+  const glm::dvec3 *rays(size_t *count = nullptr) const
+  {
+    if (count)
+    {
+      *count = rays_.size();
+    }
+    return rays_.data();
+  }
+  size_t numberOfRays() const { return rays_.size() / 2; }
+
+  /// Query::execute(): false when there is no map or the device call fails.
+  bool execute()
+  {
+    const size_t n = numberOfRays();
+    ranges_.assign(n, 0.0);
+    unobserved_volumes_.assign(n, 0.0);
+    terminal_states_.assign(n, kNull);
+    keys_.assign(6 * n, 0);
+    if (!map_ || !map_->gpuOk())
+    {
+      return false;
+    }
+    static_assert(sizeof(OccupancyType) == sizeof(int), "terminal states are written as int");
+    return n == 0 || ohmb200_rays_query(map_->handle(), &rays_[0].x, rays_.size(), volume_coefficient_, ranges_.data(),
+                                        unobserved_volumes_.data(), reinterpret_cast<int *>(terminal_states_.data()),
+                                        keys_.data()) == OHMB200_OK;
+  }
+
+  size_t numberOfResults() const { return ranges_.size(); }
+  const double *ranges() const { return ranges_.data(); }
+  const double *unobservedVolumes() const { return unobserved_volumes_.data(); }
+  const OccupancyType *terminalOccupancyTypes() const { return terminal_states_.data(); }
+  /// Terminal voxel keys, six int32 per ray: region x, y, z then local x, y, z (Query::intersectedVoxels()).
+  const int32_t *intersectedVoxels() const { return keys_.data(); }
+
+  void reset(bool hard_reset = false)
+  {
+    ranges_.clear();
+    unobserved_volumes_.clear();
+    terminal_states_.clear();
+    keys_.clear();
+    if (hard_reset)
+    {
+      rays_.clear();
+    }
+  }
+
+private:
+  GpuMap *map_;
+  double volume_coefficient_ = 1.0;
+  std::vector<glm::dvec3> rays_;
+  std::vector<double> ranges_;
+  std::vector<double> unobserved_volumes_;
+  std::vector<OccupancyType> terminal_states_;
+  std::vector<int32_t> keys_;
+};
 }  // namespace ohm
 
 #endif  // OHMB200_GPUMAP_HPP

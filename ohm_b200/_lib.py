@@ -76,6 +76,7 @@ SYMBOLS = [
     ("ohmb200_download_wait", C.c_int, [_vp]),
     ("ohmb200_rays_query", C.c_int, [_vp, _vp, C.c_size_t, C.c_double, _vp, _vp, _vp, _vp]),
     ("ohmb200_rays_query_device", C.c_int, [_vp, _vp, C.c_size_t, C.c_double, _vp, _vp, _vp, _vp]),
+    ("ohmb200_line_keys_query", C.c_int, [_vp, _vp, C.c_size_t, _vp, _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     ("ohmb200_write_region", C.c_int, [_vp, _kp, C.c_int, _vp, C.c_size_t]),
     ("ohmb200_clear", C.c_int, [_vp]),
     ("ohmb200_first_ray_time", C.c_double, [_vp]),

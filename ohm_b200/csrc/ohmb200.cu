@@ -599,6 +599,50 @@ __global__ void __launch_bounds__(128) raysQuery(DeviceMap dm, Geom g, MapParams
   }
 }
 
+// ohm::LineKeysQuery::onExecute (ohm/LineKeysQuery.cpp:103-123; OpenCL form ohmgpu/gpu/LineKeys.cl): the voxel keys
+// along each line, calculateSegmentKeys(..., include_end_point = true) = walkSegmentKeys with no flags.  Pure geometry
+// (resolution, region dimensions, origin); no ray filter, no map data.  kFill = false counts the keys of every line,
+// kFill = true writes them at the offsets an exclusive scan of the counts gave.
+template <bool kFill>
+__global__ void __launch_bounds__(128) lineKeys(Geom g, const double *rays, uint32_t n, uint32_t *counts,
+                                                const uint32_t *offsets, int32_t *keys)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+  {
+    return;
+  }
+  double start[3], end[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+  {
+    start[a] = rays[(size_t)i * 6 + a];
+    end[a] = rays[(size_t)i * 6 + 3 + a];
+  }
+  Key skey, ekey;
+  uint32_t count = 0;
+  if (voxelKey(g, start, skey) && voxelKey(g, end, ekey))  // a null key: no voxels (LineWalk.h:119-122)
+  {
+    int32_t *out = kFill ? keys + (size_t)offsets[i] * 6 : nullptr;
+    count = walkLine(g, start, end, skey, ekey, 0u, [&](const Key &key, double, double) {
+      if (kFill)
+      {
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+        {
+          out[a] = key.r[a];
+          out[3 + a] = key.l[a];
+        }
+        out += 6;
+      }
+    });
+  }
+  if (!kFill)
+  {
+    counts[i] = count;
+  }
+}
+
 // ohmb200_clear: wipe only the regions that exist (the slabs of free slots are clean already), then free the table.
 struct ClearTable
 {
@@ -773,8 +817,10 @@ struct ohmb200_map
   cudaEvent_t stage_done[2] = { nullptr, nullptr };
   bool stage_pending[2] = { false, false };
   int stage_next = 0;
-  void *d_query = nullptr;  // staging of ohmb200_rays_query
+  void *d_query = nullptr;  // staging of ohmb200_rays_query / ohmb200_line_keys_query
   size_t query_bytes = 0;
+  void *d_query_keys = nullptr;
+  size_t query_keys_bytes = 0;
   int *d_lookup_missing = nullptr;  // device flag: an asynchronous download named a region that is not resident
   // profiling
   bool profiling = false;
@@ -1636,6 +1682,7 @@ void ohmb200_destroy(ohmb200_map *m)
   }
   cudaFree(m->d_lookup_missing);
   cudaFree(m->d_query);
+  cudaFree(m->d_query_keys);
   if (m->download_stream)
   {
     cudaStreamDestroy(m->download_stream);
@@ -2012,6 +2059,70 @@ int ohmb200_rays_query(ohmb200_map *m, const double *rays, size_t element_count,
   CUDA_TRY(cudaMemcpyAsync(unobserved_volumes, d_volumes, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(terminal_keys, d_keys, sizeof(int32_t) * 6 * n, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(terminal_states, d_states, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return OHMB200_OK;
+}
+
+int ohmb200_line_keys_query(ohmb200_map *m, const double *rays, size_t element_count, uint64_t *result_indices,
+                            uint64_t *result_counts, int32_t *keys, size_t key_capacity, size_t *total_keys)
+{
+  if (!m || !rays || !result_indices || !result_counts || !total_keys || (!keys && key_capacity))
+  {
+    return setError(OHMB200_E_INVALID, "ohmb200_line_keys_query: null argument");
+  }
+  const size_t n = element_count / 2;
+  *total_keys = 0;
+  if (n == 0)
+  {
+    return OHMB200_OK;
+  }
+  cudaSetDevice(m->device);
+  cudaStream_t s = m->stream;
+  // staging: rays | counts[n + 1] | offsets[n + 1] | scan temp; the keys live in a second block
+  size_t scan_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)(n + 1), s);
+  const size_t head_bytes = sizeof(double) * 6 * n + sizeof(uint32_t) * 2 * (n + 1) + scan_bytes + 256;
+  if (head_bytes > m->query_bytes)
+  {
+    cudaFree(m->d_query);
+    m->query_bytes = 0;
+    CUDA_TRY(cudaMalloc(&m->d_query, head_bytes));
+    m->query_bytes = head_bytes;
+  }
+  double *d_rays = (double *)m->d_query;
+  uint32_t *d_counts = (uint32_t *)(d_rays + 6 * n);
+  uint32_t *d_offsets = d_counts + (n + 1);
+  void *d_scan = (void *)(((uintptr_t)(d_offsets + (n + 1)) + 255) & ~(uintptr_t)255);
+  const unsigned blocks = (unsigned)((n + 127) / 128);
+  CUDA_TRY(cudaMemcpyAsync(d_rays, rays, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemsetAsync(d_counts + n, 0, sizeof(uint32_t), s));
+  lineKeys<false><<<blocks, 128, 0, s>>>(m->geom, d_rays, (uint32_t)n, d_counts, nullptr, nullptr);
+  CUDA_TRY(cub::DeviceScan::ExclusiveSum(d_scan, scan_bytes, d_counts, d_offsets, (int)(n + 1), s));
+  std::vector<uint32_t> h_counts(n + 1), h_offsets(n + 1);
+  CUDA_TRY(cudaMemcpyAsync(h_counts.data(), d_counts, sizeof(uint32_t) * (n + 1), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(h_offsets.data(), d_offsets, sizeof(uint32_t) * (n + 1), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  for (size_t i = 0; i < n; ++i)
+  {
+    result_indices[i] = h_offsets[i];
+    result_counts[i] = h_counts[i];
+  }
+  const size_t total = h_offsets[n];
+  *total_keys = total;
+  if (key_capacity < total || total == 0)
+  {
+    return OHMB200_OK;  // sizes only: the caller allocates 6 * total int32 and calls again
+  }
+  if (sizeof(int32_t) * 6 * total > m->query_keys_bytes)
+  {
+    cudaFree(m->d_query_keys);
+    m->query_keys_bytes = 0;
+    CUDA_TRY(cudaMalloc(&m->d_query_keys, sizeof(int32_t) * 6 * total));
+    m->query_keys_bytes = sizeof(int32_t) * 6 * total;
+  }
+  lineKeys<true><<<blocks, 128, 0, s>>>(m->geom, d_rays, (uint32_t)n, nullptr, d_offsets, (int32_t *)m->d_query_keys);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(keys, m->d_query_keys, sizeof(int32_t) * 6 * total, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   return OHMB200_OK;
 }

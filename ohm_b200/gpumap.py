@@ -235,6 +235,21 @@ class GpuMap:
                                               _ptr(volumes), _ptr(states), _ptr(keys)))
         return ranges, volumes, states, keys
 
+    def line_keys_query(self, rays):
+        """ohm::LineKeysQuery (ohm/LineKeysQuery.h:20-90): the voxel keys along each line.  Returns (result_indices
+        u64[n], result_counts u64[n], keys i32[total, 6]); line i owns keys[result_indices[i]:][:result_counts[i]]."""
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 3)
+        n = rays.shape[0] // 2
+        indices, counts = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint64)
+        total = C.c_size_t(0)
+        self._check(self.L.ohmb200_line_keys_query(self.h, _ptr(rays), rays.shape[0], _ptr(indices), _ptr(counts), None,
+                                                   0, C.byref(total)))
+        keys = np.zeros((total.value, 6), dtype=np.int32)
+        if total.value:
+            self._check(self.L.ohmb200_line_keys_query(self.h, _ptr(rays), rays.shape[0], _ptr(indices), _ptr(counts),
+                                                       _ptr(keys), total.value, C.byref(total)))
+        return indices, counts, keys
+
     def write_region(self, key, layer, data):
         key = np.ascontiguousarray(key, dtype=np.int16)
         data = np.ascontiguousarray(data)

@@ -227,6 +227,21 @@ class OracleMap:
         assert got == n
         return ranges, volumes, states, keys
 
+    def line_keys_query(self, rays):
+        """ohm::LineKeysQuery (ohm/LineKeysQuery.cpp:103-123) = calculateSegmentKeys per line, end voxel included:
+        (result_indices u64[n], result_counts u64[n], keys i32[total, 6])."""
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 3)
+        n = rays.shape[0] // 2
+        indices, counts = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint64)
+        chunks = []
+        at = 0
+        for i in range(n):
+            keys, _, _ = self.walk_segment(rays[2 * i], rays[2 * i + 1], 0)
+            indices[i], counts[i] = at, len(keys)
+            at += len(keys)
+            chunks.append(keys.copy())
+        return indices, counts, (np.concatenate(chunks) if chunks else np.zeros((0, 6), dtype=np.int32))
+
     def count_walk_visits(self, rays, walk_flags=0):
         rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 3)
         return int(self.L.oracle_count_walk_visits(self.h, _dptr(rays), rays.shape[0], int(walk_flags)))

@@ -60,6 +60,9 @@ def lib():
     L.ref_walk_segment.restype = C.c_size_t
     L.ref_rays_query.argtypes = [vp, dp, C.c_size_t, C.c_double, dp, dp, C.POINTER(C.c_int), C.POINTER(C.c_int32)]
     L.ref_rays_query.restype = C.c_size_t
+    L.ref_line_keys_query.argtypes = [vp, dp, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                      C.POINTER(C.c_int32), C.c_size_t]
+    L.ref_line_keys_query.restype = C.c_size_t
     _lib = L
     return L
 
@@ -151,6 +154,19 @@ class ReferenceMap:
                                     states.ctypes.data_as(C.POINTER(C.c_int)), keys.ctypes.data_as(C.POINTER(C.c_int32)))
         assert got == n
         return ranges, volumes, states, keys
+
+    def line_keys_query(self, rays, cap=1 << 22):
+        """ohm::LineKeysQuery on the reference map: (result_indices u64[n], result_counts u64[n], keys i32[total, 6])."""
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 3)
+        n = rays.shape[0] // 2
+        indices, counts = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint64)
+        keys = np.zeros((cap, 6), dtype=np.int32)
+        total = self.L.ref_line_keys_query(self.h, rays.ctypes.data_as(C.POINTER(C.c_double)), rays.shape[0],
+                                           indices.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                           counts.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                           keys.ctypes.data_as(C.POINTER(C.c_int32)), cap)
+        assert total <= cap
+        return indices, counts, keys[:total]
 
     def walk_segment(self, start, end, walk_flags=0, cap=1 << 16):
         start = np.ascontiguousarray(start, dtype=np.float64)

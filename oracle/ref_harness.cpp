@@ -299,3 +299,38 @@ extern "C" size_t ref_rays_query(void *h, const double *rays, size_t element_cou
   }
   return n;
 }
+
+#include <ohm/LineKeysQuery.h>
+
+// ohm::LineKeysQuery on the reference map (ohm/LineKeysQuery.cpp:103-123).  keys receives six int32 per key; returns the
+// total number of keys (which may exceed key_capacity: nothing beyond the capacity is written).
+extern "C" size_t ref_line_keys_query(void *h, const double *rays, size_t element_count, uint64_t *result_indices,
+                                      uint64_t *result_counts, int32_t *keys, size_t key_capacity)
+{
+  auto *r = static_cast<RefMap *>(h);
+  ohm::LineKeysQuery query(*r->map);
+  query.setRays(reinterpret_cast<const glm::dvec3 *>(rays), element_count);
+  if (!query.execute())
+  {
+    return 0;
+  }
+  const size_t n = query.numberOfResults();
+  size_t total = 0;
+  for (size_t i = 0; i < n; ++i)
+  {
+    result_indices[i] = query.resultIndices()[i];
+    result_counts[i] = query.resultCounts()[i];
+    total = std::max<size_t>(total, query.resultIndices()[i] + query.resultCounts()[i]);
+  }
+  const ohm::Key *q_keys = query.intersectedVoxels();
+  for (size_t k = 0; k < total && k < key_capacity; ++k)
+  {
+    keys[6 * k + 0] = q_keys[k].regionKey().x;
+    keys[6 * k + 1] = q_keys[k].regionKey().y;
+    keys[6 * k + 2] = q_keys[k].regionKey().z;
+    keys[6 * k + 3] = q_keys[k].localKey().x;
+    keys[6 * k + 4] = q_keys[k].localKey().y;
+    keys[6 * k + 5] = q_keys[k].localKey().z;
+  }
+  return total;
+}

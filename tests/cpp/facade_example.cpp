@@ -3,6 +3,7 @@
 // occupied and the sensor voxel is free.
 #include <ohmb200/GpuMap.hpp>
 
+#include <cmath>
 #include <cstdio>
 #include <random>
 #include <vector>
@@ -50,5 +51,28 @@ int main()
     }
   }
   std::printf("regions %zu occupied %zu free %zu\n", keys.size(), occupied, free_voxels);
-  return (occupied > 1500 && free_voxels > occupied) ? 0 : 1;
+
+  // ohm::RaysQueryGpu: rays from the sensor to every sample stop at the sample's (occupied) voxel, about where the
+  // sample is; rays going twice as far stop there too.
+  ohm::RaysQueryGpu query(&gpu_map);
+  for (size_t i = 0; i < rays.size(); i += 2)
+  {
+    const glm::dvec3 &o = rays[i], &s = rays[i + 1];
+    query.addRay(o, glm::dvec3(o.x + 2 * (s.x - o.x), o.y + 2 * (s.y - o.y), o.z + 2 * (s.z - o.z)));
+  }
+  if (!query.execute() || query.numberOfResults() != rays.size() / 2)
+  {
+    std::fprintf(stderr, "rays query failed: %s\n", ohm::GpuMap::lastError().c_str());
+    return 1;
+  }
+  size_t stopped = 0;
+  for (size_t i = 0; i < query.numberOfResults(); ++i)
+  {
+    const glm::dvec3 &o = rays[2 * i], &s = rays[2 * i + 1];
+    const double to_sample = std::sqrt((s.x - o.x) * (s.x - o.x) + (s.y - o.y) * (s.y - o.y) + (s.z - o.z) * (s.z - o.z));
+    stopped += query.terminalOccupancyTypes()[i] == ohm::kOccupied && query.ranges()[i] <= to_sample + 0.5;
+  }
+  std::printf("rays query: %zu of %zu rays stop at an occupied voxel before or at their sample\n", stopped,
+              query.numberOfResults());
+  return (occupied > 1500 && free_voxels > occupied && stopped == query.numberOfResults()) ? 0 : 1;
 }

@@ -58,3 +58,16 @@ def test_rays_query_on_lidar_map_and_empty_map(gpu):
     got = g.rays_query(q)
     c.integrate_rays(sweep[2 * 40000: 2 * 60000])
     assert_same(got, c.rays_query(q))
+
+
+def test_line_keys_query_matches_cpu(gpu):
+    """ohm::LineKeysQuery / LineKeysQueryGpu: keys along each line, both ends included, for an off-lattice origin and
+    odd region dimensions (pure geometry: no map content involved)."""
+    for kw in (dict(), dict(origin=(0.1, -0.2, 0.3), region_dim=(16, 24, 8))):
+        g, c = make_pair(0.25, **kw)
+        q = query_rays(1500, 33, extent=20.0)
+        q[4] = [3.0, 0, 0]
+        gi, gc, gk = g.line_keys_query(q)
+        ci, cc, ck = c.line_keys_query(q)
+        assert np.array_equal(gi, ci) and np.array_equal(gc, cc) and np.array_equal(gk, ck)
+        assert gc.min() >= 1 and gk.shape[0] == int(gc.sum())

@@ -196,3 +196,14 @@ def test_rays_query():
             assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), name
     states = a[2]
     assert (states == -2).sum() == 1 and (states == 1).sum() > 100 and (states == -1).sum() > 10 and (states == 0).sum() > 0
+
+
+def test_line_keys_query():
+    # ohm::LineKeysQuery (ohm/LineKeysQuery.cpp:103-123): the keys along each line, both end voxels included
+    o, r = po.OracleMap(0.25, origin=(0.1, -0.2, 0.3)), pr.ReferenceMap(0.25, origin=(0.1, -0.2, 0.3))
+    q = query_rays(600, 33, extent=20.0)
+    q[4] = [3.0, 0, 0]  # no filter in this query: keep the inputs finite
+    a, b = o.line_keys_query(q), r.line_keys_query(q)
+    for name, x, y in zip(("result indices", "result counts", "keys"), a, b):
+        assert np.array_equal(x, y), name
+    assert a[1].min() >= 1 and a[1][4] == 1 and a[2].shape[0] == int(a[1].sum())
