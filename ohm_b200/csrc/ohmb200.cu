@@ -783,6 +783,22 @@ struct ohmb200_map
   Counters *h_counters = nullptr;  // pinned
   double first_ray_time = -1.0;
   uint32_t stamp = 0;
+  // CUDA graphs of whole batches (occupancy / NDT, region-binned path): a batch is ~30 stream operations; replaying
+  // it as one graph launch removes the gaps between them and most of the host cost.  Keyed by everything a kernel
+  // argument is built from; dropped whenever parameters, scratch buffers or the partition change.
+  struct BatchGraph
+  {
+    const void *rays, *intensities, *timestamps;
+    size_t n;
+    unsigned ray_flags;
+    double time_base;
+    cudaGraphExec_t exec;
+    uint64_t launches;
+  };
+  std::vector<BatchGraph> graphs;
+  std::vector<BatchGraph> seen;  // shapes met once (exec unused): a shape is recorded the second time it comes
+  bool capturing = false;
+  bool use_graphs = true;
   uint64_t rays_in = 0;
   uint64_t batches = 0;
   uint64_t launches = 0;
@@ -895,8 +911,19 @@ void drainSpans(ohmb200_map *m)
   m->events_used = 0;
 }
 
+void dropBatchGraphs(ohmb200_map *m)
+{
+  for (auto &g : m->graphs)
+  {
+    cudaGraphExecDestroy(g.exec);
+  }
+  m->graphs.clear();
+  m->seen.clear();
+}
+
 void refreshParams(ohmb200_map *m)
 {
+  dropBatchGraphs(m);
   const ohmb200_params &p = m->params;
   Geom &g = m->geom;
   g.res = p.resolution;
@@ -986,6 +1013,7 @@ int ensureScratch(ohmb200_map *m, size_t n)
     return OHMB200_OK;
   }
   CUDA_TRY(cudaStreamSynchronize(m->stream));
+  dropBatchGraphs(m);
   Batch &b = m->batch;
   cudaFree(b.keys_in);
   cudaFree(b.keys_out);
@@ -1112,6 +1140,71 @@ int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_i
   const unsigned threads = 128;
   const unsigned blocks = (unsigned)((n + threads - 1) / threads);
   const bool has_samples = m->mode != OHMB200_MODE_TSDF;
+
+  if (m->use_graphs && !m->capturing && m->algo == 1 && has_samples && !m->profiling)
+  {
+    for (auto &g : m->graphs)
+    {
+      if (g.rays == d_rays && g.intensities == d_intensities && g.timestamps == b.timestamps && g.n == n &&
+          g.ray_flags == ray_flags && g.time_base == b.time_base)
+      {
+        CUDA_TRY(cudaGraphLaunch(g.exec, s));
+        m->launches += g.launches;
+        m->rays_in += n;
+        ++m->batches;
+        return OHMB200_OK;
+      }
+    }
+    // A shape is recorded the second time it is met (a stream of sweeps that all differ in size or buffer never
+    // pays for a capture).  The same code below then runs into a capture instead of the stream.
+    bool met_before = false;
+    for (auto &g : m->seen)
+    {
+      met_before = met_before || (g.rays == d_rays && g.intensities == d_intensities && g.timestamps == b.timestamps &&
+                                  g.n == n && g.ray_flags == ray_flags && g.time_base == b.time_base);
+    }
+    if (!met_before)
+    {
+      if (m->seen.size() >= 16)
+      {
+        m->seen.erase(m->seen.begin());
+      }
+      m->seen.push_back({ d_rays, d_intensities, b.timestamps, n, ray_flags, b.time_base, nullptr, 0 });
+    }
+    if (m->graphs.size() >= 8)
+    {
+      dropBatchGraphs(m);
+    }
+    const uint64_t launches_before = m->launches, rays_before = m->rays_in, batches_before = m->batches;
+    cudaGraph_t graph = nullptr;
+    if (met_before && cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess)
+    {
+      m->capturing = true;
+      const int rc_capture = launchBatch(m, d_rays, n, d_intensities, d_timestamps, ray_flags);
+      m->capturing = false;
+      const cudaError_t end = cudaStreamEndCapture(s, &graph);
+      cudaGraphExec_t exec = nullptr;
+      if (rc_capture == OHMB200_OK && end == cudaSuccess && graph &&
+          cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess)
+      {
+        cudaGraphDestroy(graph);
+        m->graphs.push_back({ d_rays, d_intensities, b.timestamps, n, ray_flags, b.time_base, exec,
+                              m->launches - launches_before });
+        CUDA_TRY(cudaGraphLaunch(exec, s));
+        return OHMB200_OK;
+      }
+      // could not be recorded: forget it and run the batch directly
+      if (graph)
+      {
+        cudaGraphDestroy(graph);
+      }
+      cudaGetLastError();
+      m->launches = launches_before;
+      m->rays_in = rays_before;
+      m->batches = batches_before;
+      m->use_graphs = false;
+    }
+  }
 
   // Reset the per-batch counters (record_count .. segment_overflow are contiguous).
   CUDA_TRY(cudaMemsetAsync(&m->d_counters->record_count, 0, sizeof(uint32_t) * kPerBatchCounterWords, s));
@@ -1479,6 +1572,10 @@ ohmb200_map *ohmb200_create(const ohmb200_params *params, int mode, size_t devic
   {
     m->algo = atoi(env) ? 1 : 0;
   }
+  if (const char *env = getenv("OHMB200_GRAPHS"))
+  {
+    m->use_graphs = atoi(env) != 0;
+  }
   if (const char *env = getenv("OHMB200_HEAVY_RUN"))
   {
     m->heavy_run = (uint32_t)std::max(1, atoi(env));
@@ -1622,6 +1719,7 @@ void ohmb200_destroy(ohmb200_map *m)
   }
   cudaSetDevice(m->device);
   cudaDeviceSynchronize();
+  dropBatchGraphs(m);
   Batch &b = m->batch;
   void *to_free[] = { m->dm.keys,       m->dm.region_stamp, m->dm.pending,      b.touched_list,   m->d_counters,
                       b.keys_in,        b.keys_out,         b.vals_in,          b.vals_out,       b.run_list,
@@ -2365,6 +2463,7 @@ int ohmb200_set_partition(ohmb200_map *m, int rank, int world)
   CUDA_TRY(cudaStreamSynchronize(m->stream));
   m->dm.part_rank = rank;
   m->dm.part_world = world;
+  dropBatchGraphs(m);
   return OHMB200_OK;
 }
 

@@ -155,11 +155,11 @@ __global__ void __launch_bounds__(128) prepSegments(DeviceMap dm, Geom g, Batch 
           const unsigned peers = __match_any_sync(__activemask(), slot);
           if ((int)(threadIdx.x & 31) == __ffs(peers) - 1)
           {
-            if (__ldcg(&dm.region_stamp[slot]) != b.stamp && atomicExch(&dm.region_stamp[slot], b.stamp) != b.stamp)
+            // the adder that finds the region's count at zero is the first to enter it in this batch
+            if (atomicAdd(&b.seg_count[slot], (uint32_t)__popc(peers)) == 0u)
             {
               b.touched_list[atomicAdd(&b.counters->touched_count, 1u)] = (uint32_t)slot;
             }
-            atomicAdd(&b.seg_count[slot], (uint32_t)__popc(peers));
           }
           if (staged < kStageSegments)
           {
