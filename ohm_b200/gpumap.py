@@ -180,6 +180,10 @@ class GpuMap:
     def first_ray_time(self):
         return self.L.ohmb200_first_ray_time(self.h)
 
+    def set_first_ray_time(self, t):
+        """OccupancyMap::setFirstRayTime: the time base of the touch-time layer (restored when a map is loaded)."""
+        self._check(self.L.ohmb200_set_first_ray_time(self.h, float(t)))
+
     # -- map access ----------------------------------------------------------------------------------------
     def region_count(self):
         return self.L.ohmb200_region_count(self.h)

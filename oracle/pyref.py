@@ -63,6 +63,11 @@ def lib():
     L.ref_line_keys_query.argtypes = [vp, dp, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                       C.POINTER(C.c_int32), C.c_size_t]
     L.ref_line_keys_query.restype = C.c_size_t
+    L.ref_save.argtypes = [vp, C.c_char_p]
+    L.ref_save.restype = C.c_int
+    L.ref_load.argtypes = [C.c_char_p, C.POINTER(C.c_int)]
+    L.ref_load.restype = vp
+    L.ref_map_header.argtypes = [vp, dp, dp, C.POINTER(C.c_int), dp, dp, dp, dp, C.POINTER(C.c_uint)]
     _lib = L
     return L
 
@@ -140,6 +145,29 @@ class ReferenceMap:
         for key in self.region_keys():
             out[tuple(int(k) for k in key)] = {l: self.region_layer(key, l) for l in self.layers()}
         return out
+
+    def save(self, path):
+        """ohm::save(path, map) (ohm/MapSerialise.cpp:595-648)."""
+        rc = self.L.ref_save(self.h, str(path).encode())
+        assert rc == 0, f"ohm::save failed: {rc}"
+
+    @classmethod
+    def load(cls, path, layers):
+        """ohm::load(path, map) into a fresh reference map; `layers` = the layer ids to expose through dump()."""
+        err = C.c_int(0)
+        h = lib().ref_load(str(path).encode(), C.byref(err))
+        if not h:
+            raise RuntimeError(f"ohm::load failed: {err.value}")
+        self = cls.__new__(cls)
+        self.L, self.h, self.mode = lib(), h, "loaded"
+        res, thr, hit, miss, frt = (C.c_double() for _ in range(5))
+        origin, dim, flags = (C.c_double * 3)(), (C.c_int * 3)(), C.c_uint()
+        self.L.ref_map_header(h, C.byref(res), origin, dim, C.byref(frt), C.byref(thr), C.byref(hit), C.byref(miss),
+                              C.byref(flags))
+        self.params = po.default_params(res.value, origin=tuple(origin), region_dim=tuple(dim), layers=list(layers))
+        self.header = dict(resolution=res.value, origin=tuple(origin), region_dim=tuple(dim), first_ray_time=frt.value,
+                           threshold_value=thr.value, hit_value=hit.value, miss_value=miss.value, flags=flags.value)
+        return self
 
     def rays_query(self, rays, volume_coefficient=1.0):
         """ohm::RaysQuery on the reference map: (ranges, unobserved_volumes, terminal_states, terminal_keys)."""

@@ -334,3 +334,50 @@ extern "C" size_t ref_line_keys_query(void *h, const double *rays, size_t elemen
   }
   return total;
 }
+
+#include <ohm/MapSerialise.h>
+
+// ohm::save / ohm::load (ohm/MapSerialise.cpp:595-705) on the reference map.  ref_load returns a new handle holding
+// the loaded map (no mapper: for inspection with ref_region_keys / ref_region_layer only), or null.
+extern "C" int ref_save(void *h, const char *path)
+{
+  auto *r = static_cast<RefMap *>(h);
+  return ohm::save(path, *r->map);
+}
+
+extern "C" void *ref_load(const char *path, int *error)
+{
+  auto *r = new RefMap;
+  r->map.reset(new ohm::OccupancyMap(1.0));
+  const int err = ohm::load(path, *r->map);
+  if (error)
+  {
+    *error = err;
+  }
+  if (err)
+  {
+    delete r;
+    return nullptr;
+  }
+  return r;
+}
+
+extern "C" void ref_map_header(void *h, double *resolution, double origin[3], int region_dim[3], double *first_ray_time,
+                               double *threshold, double *hit, double *miss, unsigned *flags)
+{
+  auto *r = static_cast<RefMap *>(h);
+  *resolution = r->map->resolution();
+  const glm::dvec3 o = r->map->origin();
+  origin[0] = o.x;
+  origin[1] = o.y;
+  origin[2] = o.z;
+  const glm::u8vec3 d = r->map->regionVoxelDimensions();
+  region_dim[0] = d.x;
+  region_dim[1] = d.y;
+  region_dim[2] = d.z;
+  *first_ray_time = r->map->firstRayTime();
+  *threshold = r->map->occupancyThresholdValue();
+  *hit = r->map->hitValue();
+  *miss = r->map->missValue();
+  *flags = unsigned(r->map->flags());
+}
