@@ -38,7 +38,8 @@ enum ohmb200_layer
   OHMB200_LAYER_INTENSITY = 6,  /* {f32 mean, f32 cov}               (CovarianceVoxelCompute.h:67-73) */
   OHMB200_LAYER_HIT_MISS = 7,   /* {u32 hit, u32 miss}               (CovarianceVoxelCompute.h:76-82) */
   OHMB200_LAYER_TSDF = 8,       /* {f32 weight, f32 distance}        (VoxelTsdfCompute.h:20-24) */
-  OHMB200_LAYER_COUNT = 9
+  OHMB200_LAYER_SECONDARY = 9,  /* {f32 m2, u16 range_mean, u16 count} (VoxelSecondarySample.h:29-38) */
+  OHMB200_LAYER_COUNT = 10
 };
 
 /* Which mapper the map runs — the classes OhmAppGpu::prepareForRun picks between (ohmapp/OhmAppGpu.cpp:164-259). */
@@ -196,6 +197,14 @@ OHMB200_API int ohmb200_read_regions(ohmb200_map *map, int layer, const int16_t 
 OHMB200_API int ohmb200_read_regions_async(ohmb200_map *map, int layer, const int16_t *keys_xyz, size_t count,
                                            void *dst, size_t bytes);
 OHMB200_API int ohmb200_download_wait(ohmb200_map *map);
+
+/* ohm::RayMapperSecondarySample::integrateRays (ohm/RayMapperSecondarySample.cpp:37-74), the dual-return mapper ohmpop
+ * runs beside the main one: for every ray [primary sample, secondary sample] a Welford update (addSecondarySample,
+ * ohm/VoxelSecondarySample.h:87-99) of the voxel holding the SECOND point with range = |second - first|; samples of one
+ * voxel are applied in ray order.  No ray filter, no walk.  The map must have been created with
+ * OHMB200_LAYER_SECONDARY in params.layers (MapFlag::kSecondarySample).  Returns the number of elements consumed. */
+OHMB200_API size_t ohmb200_integrate_secondary(ohmb200_map *map, const double *rays, size_t element_count);
+OHMB200_API size_t ohmb200_integrate_secondary_device(ohmb200_map *map, const double *d_rays, size_t element_count);
 
 /* ohm::RaysQuery / ohm::RaysQueryGpu (ohm/RaysQuery.h:42-139, ohmgpu/RaysQueryGpu.h, kernel ohmgpu/gpu/RaysQuery.cl): for
  * each ray [origin, end] walk the resident map until the first occupied voxel (value > threshold).  Outputs per ray:

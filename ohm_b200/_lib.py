@@ -74,6 +74,8 @@ SYMBOLS = [
     ("ohmb200_read_regions", C.c_int, [_vp, C.c_int, _kp, C.c_size_t, _vp, C.c_size_t]),
     ("ohmb200_read_regions_async", C.c_int, [_vp, C.c_int, _kp, C.c_size_t, _vp, C.c_size_t]),
     ("ohmb200_download_wait", C.c_int, [_vp]),
+    ("ohmb200_integrate_secondary", C.c_size_t, [_vp, _vp, C.c_size_t]),
+    ("ohmb200_integrate_secondary_device", C.c_size_t, [_vp, _vp, C.c_size_t]),
     ("ohmb200_rays_query", C.c_int, [_vp, _vp, C.c_size_t, C.c_double, _vp, _vp, _vp, _vp]),
     ("ohmb200_rays_query_device", C.c_int, [_vp, _vp, C.c_size_t, C.c_double, _vp, _vp, _vp, _vp]),
     ("ohmb200_line_keys_query", C.c_int, [_vp, _vp, C.c_size_t, _vp, _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),

@@ -512,6 +512,69 @@ __global__ void gatherRegions(const uint4 *slab, const uint32_t *slots, uint4 *d
   }
 }
 
+// RayMapperSecondarySample::integrateRays (ohm/RayMapperSecondarySample.cpp:37-74), step 1: the voxel of every ray's END
+// point (region find-or-insert) as a sort key, the range |end - start| (glm::length) beside it.
+__global__ void __launch_bounds__(128) prepSecondary(DeviceMap dm, Geom g, Batch b, double *ranges)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b.n)
+  {
+    return;
+  }
+  double start[3], end[3];
+  loadRay(b, i, start, end);
+  const double d[3] = { end[0] - start[0], end[1] - start[1], end[2] - start[2] };
+  ranges[i] = sqrt((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]);
+  uint32_t vid = kInvalidVoxel;
+  Key key;
+  if (voxelKey(g, end, key) && ownsRegion(dm, key.r))
+  {
+    const int slot = regionSlot(dm, packRegion(key.r[0], key.r[1], key.r[2]));
+    if (slot >= 0)
+    {
+      vid = (uint32_t)slot * g.vpr + voxelIndex(g, key);
+    }
+  }
+  b.keys_in[i] = vid;
+  b.vals_in[i] = i;
+}
+
+// Step 2, one thread per voxel run of the sorted pairs: addSecondarySample (VoxelSecondarySample.h:87-99) in ray order.
+__global__ void __launch_bounds__(128) applySecondary(DeviceMap dm, Batch b, const double *ranges)
+{
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned samples = 0;
+  if (t < b.counters->run_count)
+  {
+    const uint32_t head = b.run_list[t];
+    const uint32_t vid = b.keys_out[head];
+    const uint2 raw = dm.secondary[vid];
+    float m2 = __uint_as_float(raw.x);
+    uint32_t range_mean_q = raw.y & 0xffffu, count = raw.y >> 16;
+    const double quantisation = 1000.0;
+    const double max_range = (65535 - 1u) / quantisation;
+    for (uint32_t j = head; j < b.n && b.keys_out[j] == vid; ++j)
+    {
+      double range = ranges[b.vals_out[j]];
+      range = (range < max_range) ? range : max_range;
+      double range_mean = range_mean_q / quantisation;
+      count = (count + 1u) & 0xffffu;  // uint16_t ++
+      const double delta = range - range_mean;
+      range_mean += delta / count;
+      range_mean_q = (uint32_t)(uint16_t)(range_mean * quantisation);
+      const double delta2 = range - range_mean;
+      m2 += (float)(delta * delta2);
+      ++samples;
+    }
+    dm.secondary[vid] = make_uint2(__float_as_uint(m2), range_mean_q | (count << 16));
+  }
+  samples = __reduce_add_sync(0xffffffffu, samples);
+  if ((threadIdx.x & 31u) == 0 && samples)
+  {
+    atomicAdd(&b.counters->sample_updates, (unsigned long long)samples);
+  }
+}
+
 // ohm::RaysQuery::onExecute (ohm/RaysQuery.cpp:109-199; the OpenCL form is ohmgpu/gpu/RaysQuery.cl) on the resident map,
 // one thread per ray: walk until the first occupied voxel.  Same fp64 walk as the mappers, so ranges, volumes, the
 // terminal state and the terminal key are those of the CPU query on the same map.  A region that is not resident reads
@@ -724,7 +787,7 @@ __global__ void gatherRegionsChecked(const uint4 *slab, const uint32_t *slots, u
 // ---------------------------------------------------------------------------------------------------------
 // Host-side map
 // ---------------------------------------------------------------------------------------------------------
-static const size_t kLayerBytes[OHMB200_LAYER_COUNT] = { 4, 8, 4, 4, 4, 24, 8, 8, 8 };
+static const size_t kLayerBytes[OHMB200_LAYER_COUNT] = { 4, 8, 4, 4, 4, 24, 8, 8, 8, 8 };
 
 enum KernelId
 {
@@ -837,6 +900,10 @@ struct ohmb200_map
   size_t query_bytes = 0;
   void *d_query_keys = nullptr;
   size_t query_keys_bytes = 0;
+  double *d_secondary_ranges = nullptr;  // ohmb200_integrate_secondary scratch
+  size_t secondary_bytes = 0;
+  void *d_secondary_rays = nullptr;
+  size_t secondary_rays_bytes = 0;
   int *d_lookup_missing = nullptr;  // device flag: an asynchronous download named a region that is not resident
   // profiling
   bool profiling = false;
@@ -1699,6 +1766,7 @@ ohmb200_map *ohmb200_create(const ohmb200_params *params, int mode, size_t devic
   m->dm.intensity = (float2 *)m->layer_slab[OHMB200_LAYER_INTENSITY];
   m->dm.hit_miss = (uint2 *)m->layer_slab[OHMB200_LAYER_HIT_MISS];
   m->dm.tsdf = (float2 *)m->layer_slab[OHMB200_LAYER_TSDF];
+  m->dm.secondary = (uint2 *)m->layer_slab[OHMB200_LAYER_SECONDARY];
   m->dm.region_count = &m->d_counters->region_count;
   m->dm.table_full = &m->d_counters->table_full;
   m->dm.part_rank = 0;
@@ -1781,6 +1849,8 @@ void ohmb200_destroy(ohmb200_map *m)
   cudaFree(m->d_lookup_missing);
   cudaFree(m->d_query);
   cudaFree(m->d_query_keys);
+  cudaFree(m->d_secondary_ranges);
+  cudaFree(m->d_secondary_rays);
   if (m->download_stream)
   {
     cudaStreamDestroy(m->download_stream);
@@ -2091,6 +2161,108 @@ int ohmb200_read_regions(ohmb200_map *m, int layer, const int16_t *keys_xyz, siz
 int ohmb200_read_region(ohmb200_map *m, const int16_t key_xyz[3], int layer, void *dst, size_t bytes)
 {
   return ohmb200_read_regions(m, layer, key_xyz, 1, dst, bytes);
+}
+
+size_t ohmb200_integrate_secondary_device(ohmb200_map *m, const double *d_rays, size_t element_count)
+{
+  if (!m || !d_rays || element_count < 2)
+  {
+    setError(OHMB200_E_INVALID, "ohmb200_integrate_secondary_device: bad arguments");
+    return 0;
+  }
+  if (!m->dm.secondary)
+  {
+    setError(OHMB200_E_INVALID, "the map has no secondary-sample layer (OHMB200_LAYER_SECONDARY)");
+    return 0;
+  }
+  cudaSetDevice(m->device);
+  const size_t n = element_count / 2;
+  if (ensureScratch(m, n) != OHMB200_OK)
+  {
+    return 0;
+  }
+  if (sizeof(double) * n > m->secondary_bytes)
+  {
+    cudaFree(m->d_secondary_ranges);
+    m->secondary_bytes = 0;
+    if (cudaMalloc(&m->d_secondary_ranges, sizeof(double) * m->scratch_rays) != cudaSuccess)
+    {
+      setError(OHMB200_E_CUDA, "scratch allocation failed");
+      return 0;
+    }
+    m->secondary_bytes = sizeof(double) * m->scratch_rays;
+  }
+  Batch &b = m->batch;
+  b.rays = d_rays;
+  b.intensities = nullptr;
+  b.timestamps = nullptr;
+  b.n = (uint32_t)n;
+  b.counters = m->d_counters;
+  cudaStream_t s = m->stream;
+  const unsigned blocks = (unsigned)((n + 127) / 128);
+  bool ok = cudaMemsetAsync(&m->d_counters->record_count, 0, sizeof(uint32_t) * kPerBatchCounterWords, s) == cudaSuccess;
+  {
+    KernelScope scope(m, kKPrepRays);
+    prepSecondary<<<blocks, 128, 0, s>>>(m->dm, m->geom, b, m->d_secondary_ranges);
+  }
+  {
+    KernelScope scope(m, kKSort);
+    size_t temp = m->cub_temp_bytes;
+    ok = ok && cub::DeviceRadixSort::SortPairs(m->cub_temp, temp, b.keys_in, b.keys_out, b.vals_in, b.vals_out, (int)n, 0,
+                                               m->sort_bits, s) == cudaSuccess;
+  }
+  {
+    // run heads only (no per-region sample ranges: those belong to the main mapper's batch)
+    Batch runs = b;
+    runs.sample_begin = nullptr;
+    KernelScope scope(m, kKMark);
+    markRuns<<<blocks, 128, 0, s>>>(m->dm, runs, m->geom.vpr);
+  }
+  {
+    KernelScope scope(m, kKSamples);
+    applySecondary<<<blocks, 128, 0, s>>>(m->dm, b, m->d_secondary_ranges);
+  }
+  if (!ok || cudaGetLastError() != cudaSuccess)
+  {
+    setError(OHMB200_E_CUDA, "secondary-sample batch failed to launch");
+    return 0;
+  }
+  m->rays_in += n;
+  ++m->batches;
+  return element_count;
+}
+
+size_t ohmb200_integrate_secondary(ohmb200_map *m, const double *rays, size_t element_count)
+{
+  if (!m || !rays || element_count < 2)
+  {
+    setError(OHMB200_E_INVALID, "ohmb200_integrate_secondary: bad arguments");
+    return 0;
+  }
+  cudaSetDevice(m->device);
+  const size_t n = element_count / 2;
+  if (cudaStreamSynchronize(m->stream) != cudaSuccess)  // the staging buffer may still feed the previous call
+  {
+    setError(OHMB200_E_CUDA, "device error before the secondary-sample batch");
+    return 0;
+  }
+  if (sizeof(double) * 6 * n > m->secondary_rays_bytes)
+  {
+    cudaFree(m->d_secondary_rays);
+    m->secondary_rays_bytes = 0;
+    if (cudaMalloc(&m->d_secondary_rays, sizeof(double) * 6 * n) != cudaSuccess)
+    {
+      setError(OHMB200_E_CUDA, "input staging allocation failed");
+      return 0;
+    }
+    m->secondary_rays_bytes = sizeof(double) * 6 * n;
+  }
+  if (cudaMemcpyAsync(m->d_secondary_rays, rays, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, m->stream) != cudaSuccess)
+  {
+    setError(OHMB200_E_CUDA, "ray upload failed");
+    return 0;
+  }
+  return ohmb200_integrate_secondary_device(m, (const double *)m->d_secondary_rays, 2 * n) ? element_count : 0;
 }
 
 int ohmb200_rays_query_device(ohmb200_map *m, const double *d_rays, size_t element_count, double volume_coefficient,

@@ -68,6 +68,7 @@ struct DeviceMap
   float2 *intensity;
   uint2 *hit_miss;
   float2 *tsdf;
+  uint2 *secondary;          // {f32 m2, u16 range_mean | u16 count << 16}
   uint32_t *voxel_bits;      // [capacity][(vpr + 31) / 32] persistent bit per voxel (NDT / TSDF maps), else nullptr
   unsigned long long *region_count;  // device counter of occupied slots
   int *table_full;                   // set when an insert found no free slot

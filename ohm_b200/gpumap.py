@@ -15,9 +15,9 @@ from . import _lib
 from ._lib import Params, Stats, KernelTime
 
 LAYER_OCCUPANCY, LAYER_MEAN, LAYER_TRAVERSAL, LAYER_TOUCH_TIME, LAYER_INCIDENT = 0, 1, 2, 3, 4
-LAYER_COVARIANCE, LAYER_INTENSITY, LAYER_HIT_MISS, LAYER_TSDF = 5, 6, 7, 8
+LAYER_COVARIANCE, LAYER_INTENSITY, LAYER_HIT_MISS, LAYER_TSDF, LAYER_SECONDARY = 5, 6, 7, 8, 9
 LAYER_NAMES = ["occupancy", "mean", "traversal", "touch_time", "incident_normal", "covariance", "intensity",
-               "hit_miss_count", "tsdf"]
+               "hit_miss_count", "tsdf", "secondary_samples"]
 LAYER_DTYPES = {
     LAYER_OCCUPANCY: (np.float32, 1),
     LAYER_MEAN: (np.uint32, 2),
@@ -28,6 +28,7 @@ LAYER_DTYPES = {
     LAYER_INTENSITY: (np.float32, 2),
     LAYER_HIT_MISS: (np.uint32, 2),
     LAYER_TSDF: (np.float32, 2),
+    LAYER_SECONDARY: (np.uint32, 2),  # {f32 m2 | u16 range_mean, u16 count}: raw words
 }
 MODE_OCCUPANCY, MODE_NDT, MODE_NDT_TM, MODE_TSDF = 0, 1, 2, 3
 MODES = {"occupancy": MODE_OCCUPANCY, "ndt": MODE_NDT, "ndt_tm": MODE_NDT_TM, "tsdf": MODE_TSDF}
@@ -153,6 +154,18 @@ class GpuMap:
             raise OhmB200Error(_lib.last_error())
         return n
 
+    def integrate_secondary(self, rays):
+        """ohm::RayMapperSecondarySample::integrateRays on this map (needs LAYER_SECONDARY): ``rays`` = [primary sample,
+        secondary sample]* ; returns the number of elements consumed."""
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 3)
+        n = rays.shape[0] - (rays.shape[0] & 1)
+        if n == 0:
+            return 0
+        done = self.L.ohmb200_integrate_secondary(self.h, _ptr(rays), n)
+        if done == 0:
+            raise OhmB200Error(_lib.last_error())
+        return done
+
     def sync_voxels(self):
         self._check(self.L.ohmb200_sync(self.h))
 
@@ -195,7 +208,7 @@ class GpuMap:
         return keys[:min(n, n2)]
 
     def layers(self):
-        return [l for l in range(9) if self.params.layers & (1 << l)]
+        return [l for l in range(10) if self.params.layers & (1 << l)]
 
     def region_layer(self, key, layer):
         return self.region_layers(np.asarray([key], dtype=np.int16), layer)[0]

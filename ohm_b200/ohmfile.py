@@ -33,9 +33,9 @@ VERSION = (0, 5, 0)
 _HEADER = "<IIHH3d3d3i4dIdQI"
 
 # ohm/DataType.h:17-34
-DT_UINT32, DT_FLOAT = 6, 9
+DT_UINT16, DT_UINT32, DT_FLOAT = 4, 6, 9
 # ohm/MapFlag.h:16-38
-FLAG_VOXEL_MEAN, FLAG_TRAVERSAL, FLAG_TOUCH_TIME, FLAG_INCIDENT, FLAG_TSDF = 1, 1 << 2, 1 << 3, 1 << 4, 1 << 5
+FLAG_VOXEL_MEAN, FLAG_TRAVERSAL, FLAG_TOUCH_TIME, FLAG_INCIDENT, FLAG_TSDF, FLAG_SECONDARY = 1, 1 << 2, 1 << 3, 1 << 4, 1 << 5, 1 << 6
 _POS_INF_BITS = 0x7F800000  # unobservedOccupancyValue() as the occupancy member's clear value (DefaultLayer.cpp:87-91)
 
 # layer -> (name, [(member, type, offset, clear value)])   ohm/DefaultLayer.cpp:29-330
@@ -50,10 +50,12 @@ LAYER_LAYOUT = {
     gm.LAYER_INTENSITY: ("intensity", [("mean", DT_FLOAT, 0, 0), ("cov", DT_FLOAT, 4, 0)]),
     gm.LAYER_HIT_MISS: ("hit_miss_count", [("hit_count", DT_UINT32, 0, 0), ("miss_count", DT_UINT32, 4, 0)]),
     gm.LAYER_TSDF: ("tsdf", [("weight", DT_FLOAT, 0, 0), ("distance", DT_FLOAT, 4, 0)]),
+    gm.LAYER_SECONDARY: ("secondary_samples", [("m2", DT_FLOAT, 0, 0), ("range_mean", DT_UINT16, 4, 0),
+                                               ("count", DT_UINT16, 6, 0)]),
 }
 LAYER_BY_NAME = {v[0]: k for k, v in LAYER_LAYOUT.items()}
 _VOXEL_BYTES = {gm.LAYER_OCCUPANCY: 4, gm.LAYER_MEAN: 8, gm.LAYER_TRAVERSAL: 4, gm.LAYER_TOUCH_TIME: 4, gm.LAYER_INCIDENT: 4,
-                gm.LAYER_COVARIANCE: 24, gm.LAYER_INTENSITY: 8, gm.LAYER_HIT_MISS: 8, gm.LAYER_TSDF: 8}
+                gm.LAYER_COVARIANCE: 24, gm.LAYER_INTENSITY: 8, gm.LAYER_HIT_MISS: 8, gm.LAYER_TSDF: 8, gm.LAYER_SECONDARY: 8}
 _TYPE_BYTES = {1: 1, 2: 1, 3: 2, 4: 2, 5: 4, 6: 4, 7: 8, 8: 8, 9: 4, 10: 8}
 
 # MapValue types, ohm/MapInfo.h:38-53
@@ -68,7 +70,8 @@ class OhmFileError(Exception):
 def map_flags(layers):
     flags = 0
     for layer, flag in ((gm.LAYER_MEAN, FLAG_VOXEL_MEAN), (gm.LAYER_TRAVERSAL, FLAG_TRAVERSAL),
-                        (gm.LAYER_TOUCH_TIME, FLAG_TOUCH_TIME), (gm.LAYER_INCIDENT, FLAG_INCIDENT)):
+                        (gm.LAYER_TOUCH_TIME, FLAG_TOUCH_TIME), (gm.LAYER_INCIDENT, FLAG_INCIDENT),
+                        (gm.LAYER_SECONDARY, FLAG_SECONDARY)):
         flags |= flag if layer in layers else 0
     return flags
 

@@ -26,7 +26,7 @@
 /* ------------------------------------------------------------------------------------------ */
 /* Map container                                                                               */
 /* ------------------------------------------------------------------------------------------ */
-static const size_t k_layer_bytes[ORC_LAYER_COUNT] = { 4, 8, 4, 4, 4, 24, 8, 8, 8 };
+static const size_t k_layer_bytes[ORC_LAYER_COUNT] = { 4, 8, 4, 4, 4, 24, 8, 8, 8, 8 };
 
 typedef struct chunk
 {
@@ -1573,4 +1573,55 @@ size_t oracle_rays_query(const oracle_map *m, const double *rays, size_t element
     memcpy(terminal_keys + 6 * n, c.terminal_key, sizeof(c.terminal_key));
   }
   return n;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* RayMapperSecondarySample (ohm/RayMapperSecondarySample.cpp:37-74)                           */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct voxel_secondary_sample /* VoxelSecondarySample.h:29-38 */
+{
+  float m2;
+  uint16_t range_mean;
+  uint16_t count;
+} voxel_secondary_sample;
+
+/* addSecondarySample, VoxelSecondarySample.h:87-99 (Welford) */
+static void add_secondary_sample(voxel_secondary_sample *voxel, double range)
+{
+  const double quantisation = 1000.0;                  /* secondarySampleQuantisationFactor() */
+  const double max_range = (65535 - 1u) / quantisation; /* secondarySampleMaxRange() */
+  range = (range < max_range) ? range : max_range;     /* std::min(range, max) */
+  double range_mean = voxel->range_mean / quantisation;
+  ++voxel->count;
+  const double delta = range - range_mean;
+  range_mean += delta / voxel->count;
+  voxel->range_mean = (uint16_t)(range_mean * quantisation);
+  const double delta2 = range - range_mean;
+  voxel->m2 += (float)(delta * delta2);
+}
+
+size_t oracle_integrate_secondary(oracle_map *m, const double *rays, size_t element_count)
+{
+  if (!(m->p.layers & (1u << ORC_LAYER_SECONDARY)))
+  {
+    return 0;
+  }
+  for (size_t i = 0; i + 1 < element_count; i += 2)
+  {
+    const double *start = rays + 3 * i, *end = rays + 3 * i + 3;
+    const double d[3] = { end[0] - start[0], end[1] - start[1], end[2] - start[2] };
+    const double range = sqrt(dot3(d, d)); /* glm::length */
+    int32_t key[6];
+    if (!oracle_voxel_key(m, end, key))
+    {
+      continue;
+    }
+    const int16_t region[3] = { (int16_t)key[0], (int16_t)key[1], (int16_t)key[2] };
+    chunk *ch = map_region(m, region, 1);
+    const size_t voxel_index =
+      (size_t)key[3] + (size_t)key[4] * m->p.region_dim[0] + (size_t)key[5] * m->p.region_dim[0] * m->p.region_dim[1];
+    add_secondary_sample((voxel_secondary_sample *)ch->layers[ORC_LAYER_SECONDARY] + voxel_index, range);
+    ++m->stats.sample_updates;
+  }
+  return element_count / 2;
 }

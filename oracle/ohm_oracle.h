@@ -35,7 +35,8 @@ enum
   ORC_LAYER_INTENSITY = 6,  /* 2 x f32 */
   ORC_LAYER_HIT_MISS = 7,   /* 2 x u32 */
   ORC_LAYER_TSDF = 8,       /* {f32 weight,f32 distance} (VoxelTsdfCompute.h:20-24) */
-  ORC_LAYER_COUNT = 9
+  ORC_LAYER_SECONDARY = 9,  /* {f32 m2, u16 range_mean, u16 count} (VoxelSecondarySample.h:29-38) */
+  ORC_LAYER_COUNT = 10
 };
 
 /* Ray filter kinds: ohm/RayFilter.cpp:15-87 */
@@ -130,6 +131,11 @@ size_t oracle_integrate_tsdf(oracle_map *m, const double *rays, size_t element_c
 #define ORC_OCCUPANCY_OCCUPIED 1
 size_t oracle_rays_query(const oracle_map *m, const double *rays, size_t element_count, double volume_coefficient,
                          double *ranges, double *unobserved_volumes, int *terminal_states, int32_t *terminal_keys);
+
+/* RayMapperSecondarySample::integrateRays (ohm/RayMapperSecondarySample.cpp:37-74): for every ray, Welford update of
+ * the secondary-sample voxel at the END point with range = |end - start| (VoxelSecondarySample.h:87-99).  No ray
+ * filter, no walk.  The map must hold ORC_LAYER_SECONDARY. */
+size_t oracle_integrate_secondary(oracle_map *m, const double *rays, size_t element_count);
 
 size_t oracle_region_count(const oracle_map *m);
 /* Writes up to cap region keys (3 x int16 each), sorted (z,y,x ascending); returns the total count. */

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libohm_oracle.so")
 
 LAYER_OCCUPANCY, LAYER_MEAN, LAYER_TRAVERSAL, LAYER_TOUCH_TIME, LAYER_INCIDENT = 0, 1, 2, 3, 4
-LAYER_COVARIANCE, LAYER_INTENSITY, LAYER_HIT_MISS, LAYER_TSDF = 5, 6, 7, 8
+LAYER_COVARIANCE, LAYER_INTENSITY, LAYER_HIT_MISS, LAYER_TSDF, LAYER_SECONDARY = 5, 6, 7, 8, 9
 LAYER_DTYPES = {
     LAYER_OCCUPANCY: (np.float32, 1),
     LAYER_MEAN: (np.uint32, 2),
@@ -24,6 +24,7 @@ LAYER_DTYPES = {
     LAYER_INTENSITY: (np.float32, 2),
     LAYER_HIT_MISS: (np.uint32, 2),
     LAYER_TSDF: (np.float32, 2),
+    LAYER_SECONDARY: (np.uint32, 2),  # {f32 m2 | u16 range_mean, u16 count}, compared as raw words
 }
 FILTER_NONE, FILTER_GOOD_RAY, FILTER_CLIP_RANGE, FILTER_CLIP_BOX = 0, 1, 2, 3
 
@@ -108,6 +109,8 @@ def lib():
         f.restype = C.c_size_t
     L.oracle_rays_query.argtypes = [vp, dp, C.c_size_t, C.c_double, dp, dp, C.POINTER(C.c_int), ip]
     L.oracle_rays_query.restype = C.c_size_t
+    L.oracle_integrate_secondary.argtypes = [vp, dp, C.c_size_t]
+    L.oracle_integrate_secondary.restype = C.c_size_t
     L.oracle_count_walk_visits.argtypes = [vp, dp, C.c_size_t, C.c_uint]
     L.oracle_count_walk_visits.restype = C.c_uint64
     L.oracle_region_count.argtypes = [vp]
@@ -242,6 +245,11 @@ class OracleMap:
             chunks.append(keys.copy())
         return indices, counts, (np.concatenate(chunks) if chunks else np.zeros((0, 6), dtype=np.int32))
 
+    def integrate_secondary(self, rays):
+        """RayMapperSecondarySample::integrateRays (ohm/RayMapperSecondarySample.cpp:37-74)."""
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 3)
+        return self.L.oracle_integrate_secondary(self.h, _dptr(rays), rays.shape[0] - (rays.shape[0] & 1))
+
     def count_walk_visits(self, rays, walk_flags=0):
         rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 3)
         return int(self.L.oracle_count_walk_visits(self.h, _dptr(rays), rays.shape[0], int(walk_flags)))
@@ -297,7 +305,7 @@ class OracleMap:
         return arr.reshape(nvox, width) if width > 1 else arr
 
     def layers(self):
-        return [l for l in range(9) if self.params.layers & (1 << l)]
+        return [l for l in range(10) if self.params.layers & (1 << l)]
 
     def dump(self):
         """{(rx,ry,rz): {layer: ndarray}} for every region."""

@@ -63,6 +63,8 @@ def lib():
     L.ref_line_keys_query.argtypes = [vp, dp, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                       C.POINTER(C.c_int32), C.c_size_t]
     L.ref_line_keys_query.restype = C.c_size_t
+    L.ref_integrate_secondary.argtypes = [vp, dp, C.c_size_t]
+    L.ref_integrate_secondary.restype = C.c_size_t
     L.ref_save.argtypes = [vp, C.c_char_p]
     L.ref_save.restype = C.c_int
     L.ref_load.argtypes = [C.c_char_p, C.POINTER(C.c_int)]
@@ -119,7 +121,7 @@ class ReferenceMap:
         return self.L.ref_first_ray_time(self.h)
 
     def layers(self):
-        return [l for l in range(9) if self.params.layers & (1 << l)]
+        return [l for l in range(10) if self.params.layers & (1 << l)]
 
     def region_keys(self):
         n = self.L.ref_region_count(self.h)
@@ -145,6 +147,12 @@ class ReferenceMap:
         for key in self.region_keys():
             out[tuple(int(k) for k in key)] = {l: self.region_layer(key, l) for l in self.layers()}
         return out
+
+    def integrate_secondary(self, rays):
+        """ohm::RayMapperSecondarySample::integrateRays on this map."""
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 3)
+        n = rays.shape[0] - (rays.shape[0] & 1)
+        return self.L.ref_integrate_secondary(self.h, rays.ctypes.data_as(C.POINTER(C.c_double)), n)
 
     def save(self, path):
         """ohm::save(path, map) (ohm/MapSerialise.cpp:595-648)."""

@@ -58,6 +58,7 @@ const char *layerName(int layer)
   case ORC_LAYER_TOUCH_TIME: return touchTimeLayerName();
   case ORC_LAYER_INCIDENT: return incidentNormalLayerName();
   case ORC_LAYER_COVARIANCE: return covarianceLayerName();
+  case ORC_LAYER_SECONDARY: return secondarySamplesLayerName();
   case ORC_LAYER_INTENSITY: return intensityLayerName();
   case ORC_LAYER_HIT_MISS: return hitMissCountLayerName();
   case ORC_LAYER_TSDF: return tsdfLayerName();
@@ -118,6 +119,7 @@ void *ref_map_create(const oracle_params *p, int mode)
   if (p->layers & (1u << ORC_LAYER_TRAVERSAL)) flags |= ohm::MapFlag::kTraversal;
   if (p->layers & (1u << ORC_LAYER_TOUCH_TIME)) flags |= ohm::MapFlag::kTouchTime;
   if (p->layers & (1u << ORC_LAYER_INCIDENT)) flags |= ohm::MapFlag::kIncidentNormal;
+  if (p->layers & (1u << ORC_LAYER_SECONDARY)) flags |= ohm::MapFlag::kSecondarySample;
   const glm::u8vec3 dim(uint8_t(p->region_dim[0]), uint8_t(p->region_dim[1]), uint8_t(p->region_dim[2]));
   r->map.reset(new ohm::OccupancyMap(p->resolution, dim, flags));
   if (mode == 3)
@@ -380,4 +382,18 @@ extern "C" void ref_map_header(void *h, double *resolution, double origin[3], in
   *hit = r->map->hitValue();
   *miss = r->map->missValue();
   *flags = unsigned(r->map->flags());
+}
+
+#include <ohm/RayMapperSecondarySample.h>
+
+// ohm::RayMapperSecondarySample on the same reference map (ohm/RayMapperSecondarySample.cpp:37-74).
+extern "C" size_t ref_integrate_secondary(void *h, const double *rays, size_t element_count)
+{
+  auto *r = static_cast<RefMap *>(h);
+  ohm::RayMapperSecondarySample mapper(r->map.get());
+  if (!mapper.valid())
+  {
+    return 0;
+  }
+  return mapper.integrateRays(reinterpret_cast<const glm::dvec3 *>(rays), element_count, nullptr, nullptr, 0u);
 }

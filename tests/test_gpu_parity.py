@@ -322,3 +322,23 @@ def test_clip_box_filter(gpu):
     integrate_both(g, c, rays, batch=1000)
     compare_maps(g, c)
     check_counts(g, c)
+
+
+def test_secondary_sample_mapper(gpu):
+    """ohm::RayMapperSecondarySample on the device map: Welford statistics of |secondary - primary| per voxel, samples of
+    a voxel applied in ray order (many rays per voxel, several batches), beside the occupancy mapper."""
+    layers = [gm.LAYER_OCCUPANCY, gm.LAYER_MEAN, gm.LAYER_SECONDARY]
+    g, c = make_pair(0.25, layers=layers)
+    rng = np.random.RandomState(2)
+    rays = np.empty((2 * 20000, 3))
+    rays[0::2] = rng.uniform(-1.5, 1.5, size=(20000, 3))
+    rays[1::2] = rays[0::2] + rng.normal(scale=0.4, size=(20000, 3))
+    rays[20:40:2] = rays[21:41:2] + [80.0, 0, 0]      # beyond the u16 millimetre clamp
+    for lo, hi in ((0, 14000), (14000, 14002), (14002, 40000)):
+        assert g.integrate_secondary(rays[lo:hi]) == 2 * c.integrate_secondary(rays[lo:hi]) == hi - lo
+    integrate_both(g, c, random_rays(2000, 4.0, seed=3))
+    compare_maps(g, c)
+    assert g.stats()["sample_updates"] == c.stats()["sample_updates"]
+    plain, _ = make_pair(0.25)
+    with pytest.raises(ohm_b200.OhmB200Error):
+        plain.integrate_secondary(rays[:10])

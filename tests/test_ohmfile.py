@@ -43,6 +43,7 @@ def rays_for(seed):
     ("occupancy", [gm.LAYER_OCCUPANCY], {}),
     ("occupancy", [gm.LAYER_OCCUPANCY, gm.LAYER_MEAN, gm.LAYER_TOUCH_TIME, gm.LAYER_INCIDENT], dict(origin=(0.1, -0.2, 0.3))),
     ("occupancy", [gm.LAYER_OCCUPANCY, gm.LAYER_MEAN, gm.LAYER_TRAVERSAL], dict(region_dim=(16, 24, 8))),
+    ("occupancy", [gm.LAYER_OCCUPANCY, gm.LAYER_MEAN, gm.LAYER_SECONDARY], {}),
     ("ndt", None, {}),
     ("ndt_tm", None, {}),
     ("tsdf", None, {}),
@@ -60,6 +61,8 @@ def test_files_we_write_load_in_the_reference(tmp_path, mode, layers, kw):
     rays = rays_for(3)
     ts = np.linspace(10.0, 11.0, rays.shape[0] // 2) if gm.LAYER_TOUCH_TIME in o.layers() else None
     o.integrate_rays(rays, intensities=np.linspace(0, 200, rays.shape[0] // 2).astype(np.float32), timestamps=ts)
+    if gm.LAYER_SECONDARY in o.layers():
+        o.integrate_secondary(rays[:3000])
     path = tmp_path / "ours.ohm"
     first = o.first_ray_time() if ts is not None else -1.0
     ohmfile.write_ohm(path, header_of(o, first_ray_time=first), o.dump())

@@ -207,3 +207,20 @@ def test_line_keys_query():
     for name, x, y in zip(("result indices", "result counts", "keys"), a, b):
         assert np.array_equal(x, y), name
     assert a[1].min() >= 1 and a[1][4] == 1 and a[2].shape[0] == int(a[1].sum())
+
+
+def test_secondary_samples():
+    # ohm::RayMapperSecondarySample (ohm/RayMapperSecondarySample.cpp:37-74): Welford range statistics per voxel, in ray
+    # order, beside the occupancy mapper on the same map; ranges beyond the u16 millimetre clamp included
+    layers = [po.LAYER_OCCUPANCY, po.LAYER_MEAN, po.LAYER_SECONDARY]
+    o, r = po.OracleMap(0.25, layers=layers), pr.ReferenceMap(0.25, layers=layers)
+    rng = np.random.RandomState(2)
+    rays = np.empty((2 * 6000, 3))
+    rays[0::2] = rng.uniform(-1, 1, size=(6000, 3))
+    rays[1::2] = rays[0::2] + rng.normal(scale=0.4, size=(6000, 3))
+    rays[20:40:2] = rays[21:41:2] + [80.0, 0, 0]
+    for chunk in (rays[:4000], rays[4000:]):
+        assert o.integrate_secondary(chunk) == r.integrate_secondary(chunk) == chunk.shape[0] // 2
+    o.integrate_rays(random_rays(500, 4.0, 3))
+    r.integrate_rays(random_rays(500, 4.0, 3))
+    assert_identical(o, r)
