@@ -249,7 +249,7 @@ OHMB200_API int ohmb200_get_stats(ohmb200_map *map, ohmb200_stats *stats);
 OHMB200_API int ohmb200_set_stream(ohmb200_map *map, void *cuda_stream);
 
 /* Multi-GPU sharding (new capability; the reference is single-device).  The map keeps only the regions
- * whose owner is `rank` of `world`: owner = ((rx>>1) + 3(ry>>1) + 5(rz>>1)) mod world.  Every GPU is handed the
+ * whose owner is `rank` of `world`: owner = (rx + 2 ry + 4 rz) mod world.  Every GPU is handed the
  * same rays (one NCCL all-gather per batch, done by the caller) and applies exactly the visits and samples that
  * fall in its own regions, so the union of the per-GPU maps is bit-identical to the single-GPU map. */
 OHMB200_API int ohmb200_set_partition(ohmb200_map *map, int rank, int world);

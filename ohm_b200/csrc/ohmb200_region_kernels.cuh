@@ -558,49 +558,49 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegions(DeviceMap dm, Geo
       {
         break;
       }
-      if (got == 2)
+      if (got == 1)
       {
-        continue;
-      }
-      SegmentWalk sw;
-      loadSegmentWalk(b, raw, sw);
-      const uint32_t ray = sw.ray;
-      auto count_visit = [&](uint32_t idx) {
-        const uint32_t shift = (idx & 1u) * 16u;
-        const uint32_t old = atomicAdd(&tile[tileWord(idx)], 1u << shift);
-        if ((old >> shift) & kTileFlag)
+        SegmentWalk sw;
+        loadSegmentWalk(b, raw, sw);
+        const uint32_t ray = sw.ray;
+        auto count_visit = [&](uint32_t idx) {
+          const uint32_t shift = (idx & 1u) * 16u;
+          const uint32_t old = atomicAdd(&tile[tileWord(idx)], 1u << shift);
+          if ((old >> shift) & kTileFlag)
+          {
+            const uint32_t at = reserveRecord(&record_chunk[warp], &b.counters->record_count);
+            if (at < b.record_capacity)
+            {
+              b.record_vid[at] = vbase + idx;
+              b.record_ray[at] = ray;
+            }
+            else
+            {
+              b.counters->record_overflow = 1;
+              b.counters->overflow_seen = 1;
+            }
+          }
+        };
+        if (dm.traversal)
         {
-          const uint32_t at = reserveRecord(&record_chunk[warp], &b.counters->record_count);
-          if (at < b.record_capacity)
-          {
-            b.record_vid[at] = vbase + idx;
-            b.record_ray[at] = ray;
-          }
-          else
-          {
-            b.counters->record_overflow = 1;
-            b.counters->overflow_seen = 1;
-          }
+          const int dx = g.dim[0], dxy = g.dim[0] * g.dim[1];
+          resumeSegment<true>(sw.init, sw.delta, sw.local0, sw.total, sw.flags, sw.st, sw.visits, b.ray_length[ray], g,
+                              [&](const int l[3], double t_enter, double t_exit, bool last_of_ray) {
+                                const uint32_t idx = (uint32_t)(l[0] + l[1] * dx + l[2] * dxy);
+                                count_visit(idx);
+                                atomicAdd(&dm.traversal[vbase + idx], (float)(t_exit - t_enter));
+                                if (last_of_ray)
+                                {
+                                  b.last_exit[ray] = t_exit;
+                                }
+                              });
         }
-      };
-      if (dm.traversal)
-      {
-        const int dx = g.dim[0], dxy = g.dim[0] * g.dim[1];
-        resumeSegment<true>(sw.init, sw.delta, sw.local0, sw.total, sw.flags, sw.st, sw.visits, b.ray_length[ray], g,
-                            [&](const int l[3], double t_enter, double t_exit, bool last_of_ray) {
-                              const uint32_t idx = (uint32_t)(l[0] + l[1] * dx + l[2] * dxy);
-                              count_visit(idx);
-                              atomicAdd(&dm.traversal[vbase + idx], (float)(t_exit - t_enter));
-                              if (last_of_ray)
-                              {
-                                b.last_exit[ray] = t_exit;
-                              }
-                            });
+        else
+        {
+          resumeSegmentFast(sw.init, sw.delta, sw.entry, sw.total, sw.flags, sw.st, sw.visits, g, count_visit);
+        }
       }
-      else
-      {
-        resumeSegmentFast(sw.init, sw.delta, sw.entry, sw.total, sw.flags, sw.st, sw.visits, g, count_visit);
-      }
+      __syncwarp();  // every lane of the warp is back together before the next pop
     }
     __syncthreads();
 
@@ -889,63 +889,63 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsNdt(const __grid_c
       {
         break;
       }
-      if (got == 2)
+      if (got == 1)
       {
-        continue;
-      }
-      SegmentWalk sw;
-      loadSegmentWalk(b, raw, sw);
-      const uint32_t ray = sw.ray;
-      auto count_visit = [&](uint32_t idx) {
-        const uint32_t shift = (idx & 1u) * 16u;
-        const uint32_t old = atomicAdd(&tile[tileWord(idx)], 1u << shift);
-        if ((old >> shift) & kTileFlag)
+        SegmentWalk sw;
+        loadSegmentWalk(b, raw, sw);
+        const uint32_t ray = sw.ray;
+        auto count_visit = [&](uint32_t idx) {
+          const uint32_t shift = (idx & 1u) * 16u;
+          const uint32_t old = atomicAdd(&tile[tileWord(idx)], 1u << shift);
+          if ((old >> shift) & kTileFlag)
+          {
+            const uint32_t at = reserveRecord(&record_chunk[warp], &b.counters->record_count);
+            if (at < b.record_capacity)
+            {
+              b.record_vid[at] = vbase + idx;
+              b.record_ray[at] = ray;
+            }
+            else
+            {
+              b.counters->record_overflow = 1;
+              b.counters->overflow_seen = 1;
+            }
+          }
+          else if ((kind[idx >> 5] >> (idx & 31u)) & 1u)
+          {
+            // Established Gaussian: evaluated later, one thread per visit (ndtGaussianMisses).
+            const uint32_t at = reserveRecord(&gauss_chunk[warp], &b.counters->gauss_count);
+            if (at < b.gauss_capacity)
+            {
+              b.gauss_keys[at] = ((unsigned long long)(vbase + idx) << 32) | ray;
+            }
+            else
+            {
+              b.counters->record_overflow = 1;
+              b.counters->overflow_seen = 1;
+            }
+          }
+        };
+        if (dm.traversal)
         {
-          const uint32_t at = reserveRecord(&record_chunk[warp], &b.counters->record_count);
-          if (at < b.record_capacity)
-          {
-            b.record_vid[at] = vbase + idx;
-            b.record_ray[at] = ray;
-          }
-          else
-          {
-            b.counters->record_overflow = 1;
-            b.counters->overflow_seen = 1;
-          }
+          const int dx = g.dim[0], dxy = g.dim[0] * g.dim[1];
+          resumeSegment<true>(sw.init, sw.delta, sw.local0, sw.total, sw.flags, sw.st, sw.visits, b.ray_length[ray], g,
+                              [&](const int l[3], double t_enter, double t_exit, bool last_of_ray) {
+                                const uint32_t idx = (uint32_t)(l[0] + l[1] * dx + l[2] * dxy);
+                                count_visit(idx);
+                                atomicAdd(&dm.traversal[vbase + idx], (float)(t_exit - t_enter));
+                                if (last_of_ray)
+                                {
+                                  b.last_exit[ray] = t_exit;
+                                }
+                              });
         }
-        else if ((kind[idx >> 5] >> (idx & 31u)) & 1u)
+        else
         {
-          // Established Gaussian: evaluated later, one thread per visit (ndtGaussianMisses).
-          const uint32_t at = reserveRecord(&gauss_chunk[warp], &b.counters->gauss_count);
-          if (at < b.gauss_capacity)
-          {
-            b.gauss_keys[at] = ((unsigned long long)(vbase + idx) << 32) | ray;
-          }
-          else
-          {
-            b.counters->record_overflow = 1;
-            b.counters->overflow_seen = 1;
-          }
+          resumeSegmentFast(sw.init, sw.delta, sw.entry, sw.total, sw.flags, sw.st, sw.visits, g, count_visit);
         }
-      };
-      if (dm.traversal)
-      {
-        const int dx = g.dim[0], dxy = g.dim[0] * g.dim[1];
-        resumeSegment<true>(sw.init, sw.delta, sw.local0, sw.total, sw.flags, sw.st, sw.visits, b.ray_length[ray], g,
-                            [&](const int l[3], double t_enter, double t_exit, bool last_of_ray) {
-                              const uint32_t idx = (uint32_t)(l[0] + l[1] * dx + l[2] * dxy);
-                              count_visit(idx);
-                              atomicAdd(&dm.traversal[vbase + idx], (float)(t_exit - t_enter));
-                              if (last_of_ray)
-                              {
-                                b.last_exit[ray] = t_exit;
-                              }
-                            });
       }
-      else
-      {
-        resumeSegmentFast(sw.init, sw.delta, sw.entry, sw.total, sw.flags, sw.st, sw.visits, g, count_visit);
-      }
+      __syncwarp();  // every lane of the warp is back together before the next pop
     }
     __syncthreads();
 

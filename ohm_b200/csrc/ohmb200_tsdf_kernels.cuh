@@ -239,30 +239,30 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsTsdf(const __grid_
       {
         break;
       }
-      if (got == 2)
+      if (got == 1)
       {
-        continue;
+        SegmentWalk sw;
+        loadSegmentWalk(b, raw, sw);
+        const uint32_t ray = sw.ray;
+        resumeSegmentFast(sw.init, sw.delta, sw.entry, sw.total, sw.flags, sw.st, sw.visits, g, [&](uint32_t idx) {
+          const uint32_t shift = (idx & 1u) * 16u;
+          const uint32_t old = atomicAdd(&tile[tileWord(idx)], 1u << shift);
+          if ((old >> shift) & kTileFlag)
+          {
+            const uint32_t at = reserveRecord(&record_chunk[warp], &b.counters->record_count);
+            if (at < b.record_capacity)
+            {
+              b.record_keys[at] = ((unsigned long long)(vbase + idx) << 32) | ray;
+            }
+            else
+            {
+              b.counters->record_overflow = 1;
+              b.counters->overflow_seen = 1;
+            }
+          }
+        });
       }
-      SegmentWalk sw;
-      loadSegmentWalk(b, raw, sw);
-      const uint32_t ray = sw.ray;
-      resumeSegmentFast(sw.init, sw.delta, sw.entry, sw.total, sw.flags, sw.st, sw.visits, g, [&](uint32_t idx) {
-        const uint32_t shift = (idx & 1u) * 16u;
-        const uint32_t old = atomicAdd(&tile[tileWord(idx)], 1u << shift);
-        if ((old >> shift) & kTileFlag)
-        {
-          const uint32_t at = reserveRecord(&record_chunk[warp], &b.counters->record_count);
-          if (at < b.record_capacity)
-          {
-            b.record_keys[at] = ((unsigned long long)(vbase + idx) << 32) | ray;
-          }
-          else
-          {
-            b.counters->record_overflow = 1;
-            b.counters->overflow_seen = 1;
-          }
-        }
-      });
+      __syncwarp();  // every lane of the warp is back together before the next pop
     }
     __syncthreads();
 

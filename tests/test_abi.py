@@ -80,7 +80,11 @@ def test_region_owner_partitions_regions():
         assert owners.min() >= 0 and owners.max() < world
         counts = np.bincount(owners, minlength=world)
         assert counts.min() > 0.5 * len(keys) / world, counts   # reasonably balanced
-        # 2x2x2-region blocks share an owner
-        a = lib.ohmb200_region_owner(np.array([2, 4, 0], dtype=np.int16).ctypes.data_as(C.POINTER(C.c_int16)), world)
-        b = lib.ohmb200_region_owner(np.array([3, 5, 1], dtype=np.int16).ctypes.data_as(C.POINTER(C.c_int16)), world)
-        assert a == b
+        # the formula in the header; with 8 owners face neighbours never share one
+        for k, o in zip(keys[::37], owners[::37]):
+            assert o == (int(k[0]) + 2 * int(k[1]) + 4 * int(k[2])) % world
+        if world == 8:
+            a = lib.ohmb200_region_owner(np.array([2, 4, 0], dtype=np.int16).ctypes.data_as(C.POINTER(C.c_int16)), world)
+            for d in ([1, 0, 0], [0, 1, 0], [0, 0, 1]):
+                n = np.array([2 + d[0], 4 + d[1], d[2]], dtype=np.int16)
+                assert lib.ohmb200_region_owner(n.ctypes.data_as(C.POINTER(C.c_int16)), world) != a
