@@ -1397,7 +1397,7 @@ int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_i
       const bool ndt_mode = m->mode == OHMB200_MODE_NDT || m->mode == OHMB200_MODE_NDT_TM;
       {
         KernelScope scope(m, kKLink);
-        linkRecords<<<m->sm_count * 4, 256, 0, s>>>(b, ndt_mode ? 1 : 0);
+        linkRecords<<<m->sm_count * 4, 256, 0, s>>>(b, ndt_mode ? 1 : 0, m->geom.vpr);
       }
       if (ndt_mode)
       {

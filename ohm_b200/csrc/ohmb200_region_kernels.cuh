@@ -142,37 +142,65 @@ __global__ void __launch_bounds__(128) prepSegments(DeviceMap dm, Geom g, Batch 
     if (rec.flags & kRecValid)
     {
       // Pass A: count this ray's segments per region (creating regions as they are first entered) and stage them.
+      // The two global round trips a segment needs — the hash probe of its region and the reply of the histogram
+      // atomic — are kept off the dependent chain: a segment is FINISHED when the next one has been found (the probe
+      // was issued a whole boundary search earlier), and the atomic's reply is looked at one segment later still.
+      bool pend_valid = false;
+      unsigned long long pend_key = 0, pend_probed = 0;
+      uint32_t pend_home = 0, pend_y = 0, pend_z = 0, pend_w = 0;
+      bool reply_valid = false;
+      uint32_t reply_slot = 0, reply_old = 0;
+      auto check_reply = [&]() {
+        // the adder that found the region's count at zero is the first to enter it in this batch
+        if (reply_valid && reply_old == 0u)
+        {
+          b.touched_list[atomicAdd(&b.counters->touched_count, 1u)] = reply_slot;
+        }
+        reply_valid = false;
+      };
+      auto finish = [&]() {
+        if (!pend_valid)
+        {
+          return;
+        }
+        pend_valid = false;
+        const int slot = (pend_probed == pend_key) ? (int)pend_home : regionSlot(dm, pend_key);
+        if (slot < 0)
+        {
+          return;
+        }
+        check_reply();
+        // one reduction per group of lanes that entered the same region
+        const unsigned peers = __match_any_sync(__activemask(), slot);
+        if ((int)(threadIdx.x & 31) == __ffs(peers) - 1)
+        {
+          reply_old = atomicAdd(&b.seg_count[slot], (uint32_t)__popc(peers));
+          reply_slot = (uint32_t)slot;
+          reply_valid = true;
+        }
+        if (staged < kStageSegments)
+        {
+          b.stage[(size_t)staged * b.stage_stride + i] = make_uint4((uint32_t)slot, pend_y, pend_z, pend_w);
+        }
+        ++staged;
+      };
       enumerateSegments(rec, g, [&](const int r[3], const int st[3], const int entry[3], int n) {
         if (!ownsRegion(dm, r))
         {
           return;
         }
-        const int slot = regionSlot(dm, packRegion(r[0], r[1], r[2]));
+        finish();
         visits += (unsigned)n;
-        if (slot >= 0)
-        {
-          // one fire-and-forget reduction per group of lanes that entered the same region
-          const unsigned peers = __match_any_sync(__activemask(), slot);
-          if ((int)(threadIdx.x & 31) == __ffs(peers) - 1)
-          {
-            // the adder that finds the region's count at zero is the first to enter it in this batch
-            if (atomicAdd(&b.seg_count[slot], (uint32_t)__popc(peers)) == 0u)
-            {
-              b.touched_list[atomicAdd(&b.counters->touched_count, 1u)] = (uint32_t)slot;
-            }
-          }
-          if (staged < kStageSegments)
-          {
-            uint4 raw;
-            raw.x = (uint32_t)slot;
-            raw.y = (uint32_t)st[0] | ((uint32_t)st[1] << 16);
-            raw.z = (uint32_t)st[2] | ((uint32_t)n << 16);
-            raw.w = (uint32_t)entry[0] | ((uint32_t)entry[1] << 8) | ((uint32_t)entry[2] << 16);
-            b.stage[(size_t)staged * b.stage_stride + i] = raw;
-          }
-          ++staged;
-        }
+        pend_key = packRegion(r[0], r[1], r[2]);
+        pend_home = hashRegion(pend_key) % dm.capacity;
+        pend_probed = __ldcg(&dm.keys[pend_home]);
+        pend_y = (uint32_t)st[0] | ((uint32_t)st[1] << 16);
+        pend_z = (uint32_t)st[2] | ((uint32_t)n << 16);
+        pend_w = (uint32_t)entry[0] | ((uint32_t)entry[1] << 8) | ((uint32_t)entry[2] << 16);
+        pend_valid = true;
       });
+      finish();
+      check_reply();
     }
     b.stage_count[i] = staged;
   }
@@ -681,7 +709,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegions(DeviceMap dm, Geo
 // Occupancy needs no more (misses of an interval commute).  NDT (keep_keys != 0) also leaves each record's interval
 // index in record_vid[], for scatterRecords to group the records by interval (a counting sort: these counts, one
 // exclusive scan, one scatter).  Slots reserved by a warp but never written keep the kInvalidVoxel fill and are skipped.
-__global__ void linkRecords(Batch b, int keep_keys)
+__global__ void linkRecords(Batch b, int keep_keys, uint32_t vpr)
 {
   const uint32_t count = min(b.counters->record_count, b.record_capacity);
   unsigned linked = 0;
@@ -692,8 +720,12 @@ __global__ void linkRecords(Batch b, int keep_keys)
     {
       continue;
     }
-    const uint32_t head = lowerBound(b.keys_out, b.n, vid);
-    const uint32_t k = lowerBound(b.keys_out, b.n, vid + 1u) - head;
+    // binary searches confined to the region's range of the sorted pairs (markRuns): ~7 steps instead of 17
+    const uint32_t slot = vid / vpr;
+    const uint32_t first = b.sample_begin[slot];
+    const uint32_t count_in_region = b.sample_end[slot] - first;
+    const uint32_t head = first + lowerBound(b.keys_out + first, count_in_region, vid);
+    const uint32_t k = first + lowerBound(b.keys_out + first, count_in_region, vid + 1u) - head;
     const uint32_t ray = b.record_ray[r];
     uint32_t lo = 0, hi = k;  // first hit whose ray index is greater than `ray`
     while (lo < hi)
