@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libohmb200.so")
+LIB_PATH = os.environ.get("OHMB200_LIB") or os.path.join(HERE, "libohmb200.so")  # OHMB200_LIB: instrumented builds
 
 LAYER_COUNT = 9
 

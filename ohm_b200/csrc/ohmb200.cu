@@ -827,6 +827,7 @@ struct ohmb200_map
   int sm_count = 148;
   int algo = 1;           // 1 = region-binned walk (shared-memory tiles), 0 = one thread per ray (global counters)
   size_t tile_bytes = 0;  // dynamic shared memory of walkRegions
+  TileLayout tile;        // layout of the shared-memory counter tile
   int walk_ctas_per_sm = 1;
   uint32_t heavy_run = 16;
   uint32_t *tsdf_near = nullptr;  // TSDF: per-batch bit per voxel, "visited near a sample in this batch"
@@ -1341,7 +1342,7 @@ int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_i
       }
       {
         KernelScope scope(m, kKWalkRegions);
-        walkRegionsTsdf<<<grid, kWalkThreads, m->tile_bytes, s>>>(m->dm, m->geom, m->mp, b, m->tsdf_near);
+        walkRegionsTsdf<<<grid, kWalkThreads, m->tile_bytes, s>>>(m->dm, m->geom, m->mp, b, m->tile, m->tsdf_near);
       }
       {
         KernelScope scope(m, kKTsdfClear);
@@ -1373,12 +1374,14 @@ int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_i
       if ((m->mode == OHMB200_MODE_NDT || m->mode == OHMB200_MODE_NDT_TM))
       {
         CUDA_TRY(cudaMemsetAsync(b.gauss_keys, 0xFF, sizeof(unsigned long long) * b.gauss_capacity, s));
-        walkRegionsNdt<<<m->sm_count * m->walk_ctas_per_sm, kWalkThreads, m->tile_bytes, s>>>(m->dm, m->geom, m->mp, b);
+        const auto kernel = m->dm.traversal ? walkRegionsNdt<true> : walkRegionsNdt<false>;
+        kernel<<<m->sm_count * m->walk_ctas_per_sm, kWalkThreads, m->tile_bytes, s>>>(m->dm, m->geom, m->mp, b, m->tile);
       }
       else
       {
-        walkRegions<<<m->sm_count * m->walk_ctas_per_sm, kWalkThreads, m->tile_bytes, s>>>(m->dm, m->geom, m->mp, b,
-                                                                                        has_samples ? 1 : 0);
+        const auto kernel = m->dm.traversal ? walkRegions<true> : walkRegions<false>;
+        kernel<<<m->sm_count * m->walk_ctas_per_sm, kWalkThreads, m->tile_bytes, s>>>(m->dm, m->geom, m->mp, b, m->tile,
+                                                                                   has_samples ? 1 : 0);
       }
     }
     if (m->mode == OHMB200_MODE_NDT || m->mode == OHMB200_MODE_NDT_TM)
@@ -1633,7 +1636,16 @@ ohmb200_map *ohmb200_create(const ohmb200_params *params, int mode, size_t devic
   refreshParams(m);
 
   // Walk algorithm: the region-binned path needs the u16 counter tile of a region to fit in shared memory.
-  m->tile_bytes = sizeof(uint32_t) * tileWords(m->geom.vpr);
+  m->tile = makeTileLayout(m->geom);
+  if (const char *env = getenv("OHMB200_TILE"))  // "row padding in words,slab bank": layout experiments
+  {
+    int row_pad = 1, slab_bank = 5;
+    if (sscanf(env, "%d,%d", &row_pad, &slab_bank) == 2 && row_pad >= 0 && row_pad < 64 && slab_bank < 32)
+    {
+      m->tile = makeTileLayout(m->geom, row_pad, slab_bank);
+    }
+  }
+  m->tile_bytes = sizeof(uint32_t) * m->tile.words;
   m->algo = 1;
   if (const char *env = getenv("OHMB200_ALGO"))
   {
@@ -1650,7 +1662,7 @@ ohmb200_map *ohmb200_create(const ohmb200_params *params, int mode, size_t devic
   const bool ndt = mode == OHMB200_MODE_NDT || mode == OHMB200_MODE_NDT_TM;
   if (ndt)
   {
-    m->tile_bytes = ((m->tile_bytes + 15u) & ~(size_t)15u) + sizeof(uint32_t) * ((m->geom.vpr + 31u) / 32u);
+    m->tile_bytes += sizeof(uint32_t) * (m->tile.words >> 4);  // + one "established Gaussian" bit per counter
     m->algo = 1;  // NDT runs on the region-binned path only
   }
   const bool tsdf = mode == OHMB200_MODE_TSDF;
@@ -1670,14 +1682,16 @@ ohmb200_map *ohmb200_create(const ohmb200_params *params, int mode, size_t devic
   }
   if (m->algo == 1)
   {
-    if (cudaFuncSetAttribute(walkRegions, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->tile_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(walkRegionsNdt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->tile_bytes) != cudaSuccess ||
+    if (cudaFuncSetAttribute(walkRegions<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->tile_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(walkRegions<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->tile_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(walkRegionsNdt<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->tile_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(walkRegionsNdt<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->tile_bytes) != cudaSuccess ||
         cudaFuncSetAttribute(walkRegionsTsdf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->tile_bytes) != cudaSuccess)
     {
       cudaGetLastError();
       m->algo = 0;
     }
-    m->walk_ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (220u * 1024u) / (m->tile_bytes + 1024u)));
+    m->walk_ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(kWalkCtasPerSm, (226u * 1024u) / (m->tile_bytes + 6u * 1024u)));
   }
   size_t bytes_per_region = (m->algo == 0) ? sizeof(uint32_t) * m->geom.vpr : 3 * sizeof(uint32_t);  // pending / counters
   if (tsdf)

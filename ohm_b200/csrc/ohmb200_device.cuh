@@ -12,6 +12,8 @@
 //   voxel walk          ohm/LineWalkCompute.h:162-413 (driven as ohm/LineWalk.h:112-129 does on the CPU)
 #pragma once
 
+#include <cfloat>
+
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -513,8 +515,54 @@ __device__ __forceinline__ float missOnce(float v, const MapParams &p, unsigned 
 }
 
 // `count` consecutive misses.  Stops early at a fixed point (min clamp, saturation, exclusion).
+// The usual case — no exclusion flags, saturation off (missIsPlain) — is v -> max(min, v + miss) after the first miss
+// has turned "unobserved" into 0 + miss: a four-instruction step instead of missOnce's flag logic, and when the count
+// is so large that the walk down certainly ends on the clamp (with room for the rounding of every add) the answer is
+// min itself.  (A fold that ran missOnce ten times per voxel of a fresh map was 60 % of walkRegions.)
+__device__ __forceinline__ bool missIsPlain(const MapParams &p, unsigned ray_flags)
+{
+  return (ray_flags & 0xE0u) == 0 && p.sat_min == -FLT_MAX && p.sat_max == FLT_MAX;
+}
+
+__device__ __forceinline__ float missRepeatPlain(float v, uint32_t count, float miss_value, float min_value)
+{
+  if (count == 0)
+  {
+    return v;
+  }
+  if (v == INFINITY)
+  {
+    v = fmaxf(min_value, 0.0f + miss_value);
+    --count;
+  }
+  if (miss_value < 0 && count > 2)
+  {
+    const float steps = (float)(count - 1u);
+    const float slack = 1e-6f * steps * (fabsf(v) + fabsf(min_value) + fabsf(miss_value));
+    if (v + steps * miss_value <= min_value - slack)
+    {
+      return min_value;
+    }
+  }
+  while (count)
+  {
+    const float n = fmaxf(min_value, v + miss_value);
+    if (n == v)
+    {
+      break;
+    }
+    v = n;
+    --count;
+  }
+  return v;
+}
+
 __device__ __forceinline__ float missRepeat(float v, uint32_t count, const MapParams &p, unsigned ray_flags)
 {
+  if (missIsPlain(p, ray_flags))
+  {
+    return missRepeatPlain(v, count, p.miss_value, p.min_value);
+  }
   while (count)
   {
     const float n = missOnce(v, p, ray_flags);
@@ -526,6 +574,64 @@ __device__ __forceinline__ float missRepeat(float v, uint32_t count, const MapPa
     --count;
   }
   return v;
+}
+
+// The miss ladder: T[k] = log-odds of a voxel that was unobserved and then took k misses (T[0] = +inf), up to the
+// first fixed point of the miss rule (the min clamp, an exclusion flag) or the end of the table.  missOnce is a pure
+// function of the value, so this one sequence answers "count misses on v" for every voxel whose history is misses
+// only — the free space along the rays, nearly every voxel a ray walks through — whatever the flags:
+// v == T[j]  =>  the result is T[min(j + count, fix)].  j is guessed as v / miss and CHECKED bit for bit, so a wrong
+// guess (a voxel that has seen hits) only falls back to the loop.  Built once per CTA in shared memory.
+constexpr int kMissLadder = 64;
+struct MissLadder
+{
+  float value[kMissLadder];
+  float inv_miss;  // 1 / miss value: the guess of j
+  uint32_t fix;    // value[fix] is a fixed point of the miss rule; kMissLadder if the table ends before one
+};
+
+__device__ __forceinline__ void buildMissLadder(MissLadder &ladder, const MapParams &p, unsigned ray_flags)
+{
+  float v = INFINITY;
+  ladder.fix = kMissLadder;
+  ladder.inv_miss = 1.0f / p.miss_value;
+  for (int k = 0; k < kMissLadder; ++k)
+  {
+    ladder.value[k] = v;
+    const float n = missOnce(v, p, ray_flags);
+    if (n == v && ladder.fix == kMissLadder)
+    {
+      ladder.fix = (uint32_t)k;
+    }
+    v = n;
+  }
+}
+
+// Branch-free lookup: the value after `count` misses when v is on the ladder (ok = true), so that the lookups of the
+// eight voxels of a group overlap; off the ladder (a voxel with hits in its history, a table without a fixed point)
+// ok = false and the caller runs missRepeat.
+__device__ __forceinline__ float missLadderLookup(const MissLadder &ladder, float v, uint32_t count, bool &ok)
+{
+  const uint32_t fix = ladder.fix;
+  const bool has_fix = fix < (uint32_t)kMissLadder;
+  const uint32_t last = has_fix ? fix : (uint32_t)kMissLadder - 1u;
+  float guess = (v == INFINITY) ? 0.0f : rintf(v * ladder.inv_miss);
+  guess = fminf(fmaxf(guess, 0.0f), (float)(kMissLadder - 1));  // NaN -> 0, and value[0] = inf != NaN
+  const uint32_t j = (uint32_t)guess;
+  const bool on_ladder = ladder.value[j] == v;
+  const bool at_fix = v == ladder.value[last] && has_fix;  // e.g. free space on the min clamp, wherever the guess fell
+  const uint32_t k = j + min(count, (uint32_t)kMissLadder);
+  ok = count == 0 || at_fix || (on_ladder && (has_fix || k < (uint32_t)kMissLadder));
+  const float after = ladder.value[min(k, last)];
+  return (count == 0 || at_fix) ? v : after;
+}
+
+__device__ __forceinline__ float missRepeatLadder(const MissLadder &ladder, float v, uint32_t count, const MapParams &p,
+                                                  unsigned ray_flags)
+{
+  bool ok;
+  const float after = missLadderLookup(ladder, v, count, ok);
+  return ok ? after : missRepeat(v, count, p, ray_flags);
 }
 
 // RayMapperOccupancy.cpp:262-279 + VoxelOccupancyCompute.h:44-54

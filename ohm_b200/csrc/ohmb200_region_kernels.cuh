@@ -339,7 +339,12 @@ __global__ void __launch_bounds__(128) emitSegments(DeviceMap dm, Geom g, Batch 
   });
 }
 
-constexpr int kWalkThreads = 512;
+#ifndef OHMB200_WALK_THREADS
+#define OHMB200_WALK_THREADS 512
+#define OHMB200_WALK_CTAS 2
+#endif
+constexpr int kWalkThreads = OHMB200_WALK_THREADS;  // x kWalkCtasPerSm: the registers of an SM at 64 per thread
+constexpr int kWalkCtasPerSm = OHMB200_WALK_CTAS;
 constexpr uint32_t kLengthBins = 128;  // visits per segment <= 3 * 255; 127+ share a bin
 
 // dm.voxel_bits: one persistent bit per voxel, [capacity][(vpr + 31) / 32] words (NDT: the voxel has an established
@@ -511,42 +516,400 @@ __device__ __forceinline__ void loadSegmentWalk(const Batch &b, const uint4 &raw
   }
 }
 
+// atomicAdd on the 32-bit word of the counter tile that holds the u16 counter at shared-memory byte address `at`.
+__device__ __forceinline__ uint32_t tileAdd(uint32_t at, uint32_t one)
+{
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(at & ~3u), "r"(one) : "memory");
+  return old;
+}
+
+// The fold's view of the counter tile: fn(v, position, lo, hi) for every word that holds voxels — v = index in the
+// region of the word's first voxel (its second is v + 1), position = counter position of that voxel, lo / hi = the two
+// raw counters (hi = 0 where the row ends on an odd voxel).  Words that are zero are skipped.  A warp takes 32 /
+// row_lanes rows at a time, lanes along x: the slab is then touched in runs of whole rows (128 B of log-odds per row
+// of a 32^3 region).
+template <typename Fn>
+__device__ __forceinline__ void foldTile(const uint32_t *tile, const TileLayout &tl, Fn &&fn)
+{
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t rows_per_warp = 32u / tl.row_lanes;
+  const uint32_t x0 = lane & (tl.row_lanes - 1u);
+  const uint32_t rows = (uint32_t)(tl.dy * tl.dz);
+  const uint32_t stride = (blockDim.x >> 5) * rows_per_warp;
+  for (uint32_t r = (threadIdx.x >> 5) * rows_per_warp + lane / tl.row_lanes; r < rows; r += stride)
+  {
+    const uint32_t z = (tl.dy > 1) ? __umulhi(r, tl.inv_dy) : r;
+    const uint32_t y = r - z * (uint32_t)tl.dy;
+    const uint32_t first_word = ((uint32_t)tl.row >> 1) * y + ((uint32_t)tl.slab >> 1) * z;
+    const uint32_t first_voxel = (uint32_t)tl.dx * y + (uint32_t)tl.dxy * z;
+    for (uint32_t xw = x0; xw < tl.row_words; xw += tl.row_lanes)
+    {
+      const uint32_t w = tile[first_word + xw];
+      if (w)
+      {
+        fn(first_voxel + 2u * xw, 2u * (first_word + xw), w & 0xffffu, (2u * xw + 1u < (uint32_t)tl.dx) ? (w >> 16) : 0u);
+      }
+    }
+  }
+}
+
+// Tile position (in counters, a multiple of 8) of group c of a fast layout.
+__device__ __forceinline__ uint32_t groupPosition(const TileLayout &tl, uint32_t c)
+{
+  const uint32_t r = (tl.row_groups > 1) ? __umulhi(c, tl.inv_row_groups) : c;
+  const uint32_t z = (tl.dy > 1) ? __umulhi(r, tl.inv_dy) : r;
+  return 8u * (c - r * tl.row_groups) + (uint32_t)tl.row * (r - z * (uint32_t)tl.dy) + (uint32_t)tl.slab * z;
+}
+
+// Fast layouts: group(c, position, counters) for every aligned group of eight voxels (8c .. 8c+7 of the region, at
+// counter position `position`, a multiple of 8) whose four tile words are not all zero.
+template <typename Group>
+__device__ __forceinline__ void foldGroups(const uint32_t *tile, const TileLayout &tl, Group &&group)
+{
+  const uint4 *tile4 = reinterpret_cast<const uint4 *>(tile);
+  const uint32_t groups = ((uint32_t)tl.dxy * (uint32_t)tl.dz) >> 3;
+  for (uint32_t c = threadIdx.x; c < groups; c += blockDim.x)
+  {
+    const uint32_t position = groupPosition(tl, c);
+    const uint4 t = tile4[position >> 3];
+    if (t.x | t.y | t.z | t.w)
+    {
+      group(c, position, t);
+    }
+  }
+}
+
+// The fold of a work item that is the sole writer of its region, fast layouts: kGroups groups of eight voxels per
+// thread in flight — tile reads, then the slab reads of all of them, then the updates — so that the L2 round trips
+// and the (branch-free) per-voxel updates of different voxels overlap.  Voxel = the slab's voxel type (4 or 8 bytes);
+// counts(position, counters, cnt[8]) fills the counts to apply and returns whether any is non-zero;
+// apply(voxel &, count) updates one voxel.
+template <int kGroups, typename Voxel, typename Counts, typename Apply>
+__device__ __forceinline__ void foldGroupsSole(const uint32_t *tile, const TileLayout &tl, Voxel *slab, Counts &&counts,
+                                               Apply &&apply)
+{
+  constexpr int kChunks = (int)sizeof(Voxel) * 8 / 16;  // 16-byte chunks per group
+  const uint4 *tile4 = reinterpret_cast<const uint4 *>(tile);
+  const uint32_t groups = ((uint32_t)tl.dxy * (uint32_t)tl.dz) >> 3;
+  // Round i of warp w takes the block of 32 groups ((w + 5 i) mod warps) of the round's span, not block w every time: the
+  // voxels a batch touches sit in a few bands of y or z of the region, and a fixed assignment leaves a quarter of
+  // the warps with all the work (measured: warps waited 10 k cycles per item at the barrier after the fold).
+  const uint32_t span = kGroups * blockDim.x;
+  uint32_t turn = threadIdx.x;
+  for (uint32_t base = 0; base < groups; base += span, turn += 5u * 32u)
+  {
+    turn = (turn >= blockDim.x) ? turn - blockDim.x : turn;
+    const uint32_t c0 = base + turn;
+    uint32_t cnt[kGroups][8];
+    bool any[kGroups];
+    union
+    {
+      uint4 chunk[kChunks];
+      Voxel voxel[8];
+    } value[kGroups];
+#pragma unroll
+    for (int u = 0; u < kGroups; ++u)
+    {
+      const uint32_t c = c0 + (uint32_t)u * blockDim.x;
+      any[u] = false;
+      if (c < groups)
+      {
+        const uint32_t position = groupPosition(tl, c);
+        const uint4 t = tile4[position >> 3];
+        any[u] = (t.x | t.y | t.z | t.w) != 0 && counts(position, t, cnt[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kGroups; ++u)
+    {
+      if (any[u])
+      {
+        const uint4 *src = reinterpret_cast<const uint4 *>(slab + 8u * (c0 + (uint32_t)u * blockDim.x));
+#pragma unroll
+        for (int k = 0; k < kChunks; ++k)
+        {
+          value[u].chunk[k] = src[k];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kGroups; ++u)
+    {
+      if (any[u])
+      {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+        {
+          apply(value[u].voxel[k], cnt[u][k]);
+        }
+        uint4 *dst = reinterpret_cast<uint4 *>(slab + 8u * (c0 + (uint32_t)u * blockDim.x));
+#pragma unroll
+        for (int k = 0; k < kChunks; ++k)
+        {
+          dst[k] = value[u].chunk[k];
+        }
+      }
+    }
+  }
+}
+
+// The update of one 64-bit unit of a slab by a work item that shares its region with other items (a hot region is
+// cut into several): compare-and-swap, repeated on the value it returned when another item's fold got in between.
+template <typename Update>
+__device__ __forceinline__ void foldUnitShared(unsigned long long *unit, unsigned long long seen, Update &&update)
+{
+  for (;;)
+  {
+    const unsigned long long want = update(seen);
+    if (want == seen)
+    {
+      return;
+    }
+    const unsigned long long got = atomicCAS(unit, seen, want);
+    if (got == seen)
+    {
+      return;
+    }
+    seen = got;
+  }
+}
+
+// Pulls a region's slab of one layer towards the L2 while the work item is walked (the fold reads it afterwards).
+__device__ __forceinline__ void prefetchSlab(const void *slab, size_t bytes)
+{
+  const char *p = static_cast<const char *>(slab);
+  for (size_t at = (size_t)threadIdx.x * 128u; at < bytes; at += (size_t)blockDim.x * 128u)
+  {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + at));
+  }
+}
+
+// ---- the folds: counter tile -> slab ------------------------------------------------------------------------
+// The folds take the tile layout through foldLayout(): values the compiler cannot see through, so that none of the
+// folds' address arithmetic is hoisted out of the persistent loop (it would stay live through the walk, whose inner
+// loop then spills).
+__device__ __forceinline__ uint32_t opaque(uint32_t x)
+{
+  asm volatile("" : "+r"(x));
+  return x;
+}
+__device__ __forceinline__ TileLayout foldLayout(const TileLayout &tl)
+{
+  TileLayout f = tl;
+  f.dx = (int)opaque((uint32_t)tl.dx);
+  f.dy = (int)opaque((uint32_t)tl.dy);
+  f.dz = (int)opaque((uint32_t)tl.dz);
+  f.dxy = (int)opaque((uint32_t)tl.dxy);
+  f.row = (int)opaque((uint32_t)tl.row);
+  f.slab = (int)opaque((uint32_t)tl.slab);
+  f.row_words = opaque(tl.row_words);
+  f.row_lanes = opaque(tl.row_lanes);
+  f.row_shift = opaque(tl.row_shift);
+  f.inv_dy = opaque(tl.inv_dy);
+  return f;
+}
+
+// The slowest, general form: one voxel at a time (odd region rows: a tile word's two voxels are no aligned pair).
+template <typename Voxel>
+__device__ __forceinline__ void foldTileVoxels(const uint32_t *tile, const TileLayout &tl, Voxel &&voxel)
+{
+  foldTile(tile, tl, [&](uint32_t v, uint32_t position, uint32_t lo, uint32_t hi) {
+    voxel(v, position, lo);
+    voxel(v + 1u, position + 1u, hi);
+  });
+}
+
+// One voxel's log-odds, `count` misses, by compare-and-swap (or a plain store for the sole writer of the region).
+__device__ __forceinline__ void foldLogOdds(float *occ, uint32_t v, uint32_t count, const MapParams &mp, unsigned ray_flags,
+                                            const MissLadder &ladder, bool sole)
+{
+  int *addr = reinterpret_cast<int *>(occ + v);
+  int seen = *reinterpret_cast<volatile int *>(addr);
+  for (;;)
+  {
+    const float next = missRepeatLadder(ladder, __int_as_float(seen), count, mp, ray_flags);
+    if (__float_as_int(next) == seen)
+    {
+      break;
+    }
+    if (sole)
+    {
+      occ[v] = next;
+      break;
+    }
+    const int prev = atomicCAS(addr, seen, __float_as_int(next));
+    if (prev == seen)
+    {
+      break;
+    }
+    seen = prev;
+  }
+}
+
+// Occupancy maps: k identical misses commute, so the count is all that matters (missRepeat).  `kind` (NDT maps; else
+// null) marks the voxels with an established Gaussian: those are handled by ndtGaussianMisses / ndtClampGaussians;
+// `hit_miss` (NDT-TM; else null) counts every plain miss.  Flagged voxels are replayed with their samples.
+__device__ __forceinline__ void foldLogOddsTile(const uint32_t *tile, const uint32_t *kind, const TileLayout &layout,
+                                                float *occ, uint2 *hit_miss, const MapParams &mp, unsigned ray_flags,
+                                                const MissLadder &ladder, uint32_t shared)
+{
+  const TileLayout tl = foldLayout(layout);
+  const auto misses = [&](float v, uint32_t count) { return missRepeatLadder(ladder, v, count, mp, ray_flags); };
+  if (!tl.fast)
+  {
+    foldTileVoxels(tile, tl, [&](uint32_t v, uint32_t position, uint32_t half) {
+      const bool gauss = kind && ((kind[position >> 5] >> (position & 31u)) & 1u);
+      if (half != 0 && !(half & kTileFlag) && !gauss)
+      {
+        if (hit_miss)
+        {
+          atomicAdd(&hit_miss[v].y, half);  // every plain NDT miss counts as a miss
+        }
+        foldLogOdds(occ, v, half, mp, ray_flags, ladder, !shared);
+      }
+    });
+    return;
+  }
+  // counts of the plain voxels of a group: flagged voxels are replayed with their samples, Gaussian voxels (NDT) are
+  // handled by ndtGaussianMisses / ndtClampGaussians; every plain NDT miss counts as a miss (hit_miss, NDT-TM)
+  const auto counts = [&](uint32_t position, const uint4 &t, uint32_t cnt[8]) {
+    const uint32_t w4[4] = { t.x, t.y, t.z, t.w };
+    // position is a multiple of 8: the eight Gaussian bits are one byte of `kind`
+    const uint32_t gauss8 = kind ? reinterpret_cast<const uint8_t *>(kind)[position >> 3] : 0u;
+    uint32_t any = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+    {
+      const uint32_t half = (w4[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+      cnt[k] = ((half & kTileFlag) || ((gauss8 >> k) & 1u)) ? 0u : half;
+      any |= cnt[k];
+    }
+    return any != 0;
+  };
+  if (hit_miss)
+  {
+    foldGroups(tile, tl, [&](uint32_t c, uint32_t position, const uint4 &t) {
+      uint32_t cnt[8];
+      counts(position, t, cnt);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+      {
+        if (cnt[k])
+        {
+          atomicAdd(&hit_miss[c * 8u + (uint32_t)k].y, cnt[k]);
+        }
+      }
+    });
+  }
+  if (!shared)
+  {
+    // sole writer of the region's log-odds until this kernel ends
+    foldGroupsSole<2>(tile, tl, occ, counts, [&](float &v, uint32_t count) {
+      bool ok;
+      const float after = missLadderLookup(ladder, v, count, ok);
+      v = ok ? after : missRepeat(v, count, mp, ray_flags);
+    });
+    return;
+  }
+  foldGroups(tile, tl, [&](uint32_t c, uint32_t position, const uint4 &t) {
+    uint32_t cnt[8];
+    if (!counts(position, t, cnt))
+    {
+      return;
+    }
+    // shared region: a compare-and-swap per pair of voxels, the four reads in flight together
+    unsigned long long *units = reinterpret_cast<unsigned long long *>(occ) + 4u * c;
+    unsigned long long seen[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+      seen[k] = (cnt[2 * k] | cnt[2 * k + 1]) ? __ldcg(units + k) : 0ull;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+      if (cnt[2 * k] | cnt[2 * k + 1])
+      {
+        foldUnitShared(units + k, seen[k], [&](unsigned long long old) {
+          const float x = misses(__uint_as_float((uint32_t)old), cnt[2 * k]);
+          const float y = misses(__uint_as_float((uint32_t)(old >> 32)), cnt[2 * k + 1]);
+          return (unsigned long long)__float_as_uint(x) | ((unsigned long long)__float_as_uint(y) << 32);
+        });
+      }
+    }
+  });
+}
+
+// Work item w of the batch, or the "no more work" marker.
+__device__ __forceinline__ void loadWorkItem(const Batch &b, uint32_t w, WorkItem *dst)
+{
+  if (w < min(b.counters->item_count, b.item_capacity))
+  {
+    *dst = b.items[w];
+  }
+  else
+  {
+    dst->slot = 0xFFFFFFFFu;
+  }
+}
+
 // Persistent CTAs: one (region, segment range) work item at a time against a shared-memory counter tile.
-__global__ void __launch_bounds__(kWalkThreads, 2) walkRegions(DeviceMap dm, Geom g, MapParams mp, Batch b, int has_samples)
+template <bool kTraversal>  // kTraversal: also accumulate the traversal layer (enter / exit ranges of every visit)
+__global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegions(const __grid_constant__ DeviceMap dm, const __grid_constant__ Geom g,
+                                                               const __grid_constant__ MapParams mp, const __grid_constant__ Batch b,
+                                                               const __grid_constant__ TileLayout tl, int has_samples)
 {
   extern __shared__ uint32_t tile[];
-  __shared__ WorkItem item;
+  __shared__ WorkItem items2[2];  // this work item and the next one (fetched during the walk)
+  uint32_t parity = 1;
   // per-warp reservation of ordered-miss record slots: (base << 32) | used
   __shared__ unsigned long long record_chunk[kWalkThreads / 32];
   __shared__ SegmentQueue queue;
-  const uint32_t words = tileWords(g.vpr);
+  __shared__ MissLadder ladder;
+  const uint32_t words = tl.words;
+  const uint32_t tile_base = (uint32_t)__cvta_generic_to_shared(tile);
   const uint32_t tid = threadIdx.x;
   const uint32_t warp = tid >> 5;
   if ((tid & 31u) == 0)
   {
     record_chunk[warp] = (unsigned long long)kRecordChunk;  // "full": the first record reserves a chunk
   }
+  if (tid == 32)
+  {
+    buildMissLadder(ladder, mp, b.ray_flags);
+  }
 
+  if (tid == 0)
+  {
+    loadWorkItem(b, atomicAdd(&b.counters->work_next, 1u), &items2[0]);
+  }
+#ifdef OHMB200_PHASE_CLOCKS
+  long long ph[7] = { 0, 0, 0, 0, 0, 0, 0 }, tc[7];
+
+  unsigned ph_items = 0, ph_shared = 0;
+  tc[6] = clock64();
+#define PHASE(i) tc[i] = clock64()
+#else
+#define PHASE(i)
+#endif
   for (;;)
   {
-    __syncthreads();
-    if (tid == 0)
-    {
-      const uint32_t w = atomicAdd(&b.counters->work_next, 1u);
-      if (w < min(b.counters->item_count, b.item_capacity))
-      {
-        item = b.items[w];
-      }
-      else
-      {
-        item.slot = 0xFFFFFFFFu;
-      }
-    }
-    __syncthreads();
+    parity ^= 1u;
+    __syncthreads();  // the item is in place; the previous fold is done with the tile
+    const WorkItem &item = items2[parity];
     if (item.slot == 0xFFFFFFFFu)
     {
+#ifdef OHMB200_PHASE_CLOCKS
+      if (tid == 0)
+      {
+        printf("PH %u items %u shared %u top %lld zero %lld build %lld walk %lld wait %lld fold %lld foldshared %lld\n", blockIdx.x,
+               ph_items, ph_shared, ph[0], ph[1], ph[2], ph[3], ph[4], ph[5], ph[6]);
+      }
+#endif
       return;
     }
+    PHASE(0);
     const uint32_t slot = item.slot;
     const uint32_t vbase = slot * g.vpr;
     if ((words & 3u) == 0)
@@ -564,7 +927,9 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegions(DeviceMap dm, Geo
         tile[w] = 0;
       }
     }
+    prefetchSlab(dm.occupancy + (size_t)vbase, sizeof(float) * g.vpr);
     __syncthreads();
+    PHASE(1);
     if (has_samples)
     {
       // Voxels that also receive samples in this batch: their misses must stay ordered against the hits.
@@ -572,11 +937,17 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegions(DeviceMap dm, Geo
       const uint32_t sample_end = b.sample_end[slot];
       for (uint32_t s = b.sample_begin[slot] + tid; s < sample_end; s += blockDim.x)
       {
-        const uint32_t v = b.keys_out[s] - vbase;
-        atomicOr(&tile[tileWord(v)], kTileFlag << ((v & 1u) * 16u));
+        const uint32_t half = tileHalf(tl, b.keys_out[s] - vbase);
+        atomicOr(&tile[half >> 1], kTileFlag << ((half & 1u) * 16u));
       }
     }
     queueBuild(queue, b, item);
+    PHASE(2);
+    uint32_t next_work = 0;
+    if (tid == 0)
+    {
+      next_work = atomicAdd(&b.counters->work_next, 1u);  // the reply arrives while this item is walked
+    }
 
     for (;;)
     {
@@ -591,15 +962,13 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegions(DeviceMap dm, Geo
         SegmentWalk sw;
         loadSegmentWalk(b, raw, sw);
         const uint32_t ray = sw.ray;
-        auto count_visit = [&](uint32_t idx) {
-          const uint32_t shift = (idx & 1u) * 16u;
-          const uint32_t old = atomicAdd(&tile[tileWord(idx)], 1u << shift);
-          if ((old >> shift) & kTileFlag)
+        auto count_visit = [&](uint32_t offset, uint32_t one) {
+          if (tileAdd(offset, one) & (one << 15))
           {
             const uint32_t at = reserveRecord(&record_chunk[warp], &b.counters->record_count);
             if (at < b.record_capacity)
             {
-              b.record_vid[at] = vbase + idx;
+              b.record_vid[at] = vbase + tileVoxel(tl, (offset - tile_base) >> 1);
               b.record_ray[at] = ray;
             }
             else
@@ -609,13 +978,14 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegions(DeviceMap dm, Geo
             }
           }
         };
-        if (dm.traversal)
+        if (kTraversal)
         {
           const int dx = g.dim[0], dxy = g.dim[0] * g.dim[1];
           resumeSegment<true>(sw.init, sw.delta, sw.local0, sw.total, sw.flags, sw.st, sw.visits, b.ray_length[ray], g,
                               [&](const int l[3], double t_enter, double t_exit, bool last_of_ray) {
                                 const uint32_t idx = (uint32_t)(l[0] + l[1] * dx + l[2] * dxy);
-                                count_visit(idx);
+                                count_visit(tile_base + 2u * (uint32_t)(l[0] + l[1] * tl.row + l[2] * tl.slab),
+                                            (l[0] & 1) ? 0x10000u : 1u);
                                 atomicAdd(&dm.traversal[vbase + idx], (float)(t_exit - t_enter));
                                 if (last_of_ray)
                                 {
@@ -625,80 +995,33 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegions(DeviceMap dm, Geo
         }
         else
         {
-          resumeSegmentFast(sw.init, sw.delta, sw.entry, sw.total, sw.flags, sw.st, sw.visits, g, count_visit);
+          resumeSegmentTile(sw.init, sw.delta, sw.entry, sw.total, sw.flags, sw.st, sw.visits, tl, tile_base, count_visit);
         }
       }
       __syncwarp();  // every lane of the warp is back together before the next pop
     }
+    PHASE(3);
+    if (tid == 0)
+    {
+      loadWorkItem(b, next_work, &items2[parity ^ 1u]);
+    }
     __syncthreads();
+    PHASE(4);
 
     // Fold the miss counts into the occupancy slab.  k identical misses commute, so the count is all that matters.
-    float *occ = dm.occupancy + (size_t)vbase;
-    if (!item.shared && (g.vpr & 7u) == 0)
-    {
-      const uint4 *tile4 = reinterpret_cast<const uint4 *>(tile);
-      float4 *occ4 = reinterpret_cast<float4 *>(occ);
-      for (uint32_t c = tid; c < (g.vpr >> 3); c += blockDim.x)
-      {
-        const uint4 t = tile4[tileGroup(c)];
-        const uint32_t w4[4] = { t.x, t.y, t.z, t.w };
-        uint32_t cnt[8];
-        uint32_t any = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-        {
-          const uint32_t lo = w4[k] & 0xffffu, hi = w4[k] >> 16;
-          cnt[2 * k] = (lo & kTileFlag) ? 0u : lo;
-          cnt[2 * k + 1] = (hi & kTileFlag) ? 0u : hi;
-          any |= cnt[2 * k] | cnt[2 * k + 1];
-        }
-        if (any)
-        {
-          float4 a = occ4[2 * c], d = occ4[2 * c + 1];
-          a.x = missRepeat(a.x, cnt[0], mp, b.ray_flags);
-          a.y = missRepeat(a.y, cnt[1], mp, b.ray_flags);
-          a.z = missRepeat(a.z, cnt[2], mp, b.ray_flags);
-          a.w = missRepeat(a.w, cnt[3], mp, b.ray_flags);
-          d.x = missRepeat(d.x, cnt[4], mp, b.ray_flags);
-          d.y = missRepeat(d.y, cnt[5], mp, b.ray_flags);
-          d.z = missRepeat(d.z, cnt[6], mp, b.ray_flags);
-          d.w = missRepeat(d.w, cnt[7], mp, b.ray_flags);
-          occ4[2 * c] = a;
-          occ4[2 * c + 1] = d;
-        }
-      }
-    }
-    else
-    {
-      for (uint32_t v = tid; v < g.vpr; v += blockDim.x)
-      {
-        const uint32_t half = (tile[tileWord(v)] >> ((v & 1u) * 16u)) & 0xffffu;
-        if (half == 0 || (half & kTileFlag))
-        {
-          continue;
-        }
-        if (!item.shared)
-        {
-          occ[v] = missRepeat(occ[v], half, mp, b.ray_flags);
-        }
-        else
-        {
-          // Region split over several work items: serialise the read-modify-write per voxel.
-          int *addr = reinterpret_cast<int *>(occ + v);
-          int seen = *reinterpret_cast<volatile int *>(addr);
-          for (;;)
-          {
-            const float next = missRepeat(__int_as_float(seen), half, mp, b.ray_flags);
-            const int prev = atomicCAS(addr, seen, __float_as_int(next));
-            if (prev == seen)
-            {
-              break;
-            }
-            seen = prev;
-          }
-        }
-      }
-    }
+    foldLogOddsTile(tile, nullptr, tl, dm.occupancy + (size_t)vbase, nullptr, mp, b.ray_flags, ladder, item.shared);
+#ifdef OHMB200_PHASE_CLOCKS
+    PHASE(5);
+    ph[0] += tc[0] - tc[6];
+    ph[1] += tc[1] - tc[0];
+    ph[2] += tc[2] - tc[1];
+    ph[3] += tc[3] - tc[2];
+    ph[4] += tc[4] - tc[3];
+    ph[item.shared ? 6 : 5] += tc[5] - tc[4];
+    tc[6] = tc[5];
+    ++ph_items;
+    ph_shared += item.shared ? 1u : 0u;
+#endif
   }
 }
 
@@ -849,16 +1172,22 @@ __global__ void __launch_bounds__(256) ndtClampGaussians(DeviceMap dm, MapParams
 
 // walkRegions for NDT maps: same counter tile, plus a bit per voxel saying "established Gaussian" (mean count >=
 // sample threshold), staged from the mean layer when the work item starts.
-__global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsNdt(const __grid_constant__ DeviceMap dm, const __grid_constant__ Geom g,
-                                                                  const __grid_constant__ MapParams mp, const __grid_constant__ Batch b)
+template <bool kTraversal>
+__global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegionsNdt(const __grid_constant__ DeviceMap dm, const __grid_constant__ Geom g,
+                                                                  const __grid_constant__ MapParams mp, const __grid_constant__ Batch b,
+                                                                  const __grid_constant__ TileLayout tl)
 {
   extern __shared__ uint32_t tile[];
-  __shared__ WorkItem item;
+  __shared__ WorkItem items2[2];  // this work item and the next one (fetched during the walk)
+  uint32_t parity = 1;
   __shared__ unsigned long long record_chunk[kWalkThreads / 32];
   __shared__ unsigned long long gauss_chunk[kWalkThreads / 32];
   __shared__ SegmentQueue queue;
-  const uint32_t words = tileWords(g.vpr);
-  const uint32_t kind_words = (g.vpr + 31u) >> 5;
+  __shared__ MissLadder ladder;
+  const uint32_t words = tl.words;
+  const uint32_t tile_base = (uint32_t)__cvta_generic_to_shared(tile);
+  const uint32_t bit_words = (g.vpr + 31u) >> 5;  // the persistent bits of a region, indexed by voxel
+  const uint32_t kind_words = words >> 4;         // their copy in shared memory, indexed by counter position
   uint32_t *kind = tile + ((words + 3u) & ~3u);
   const uint32_t tid = threadIdx.x;
   const uint32_t warp = tid >> 5;
@@ -867,22 +1196,19 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsNdt(const __grid_c
     record_chunk[warp] = (unsigned long long)kRecordChunk;
     gauss_chunk[warp] = (unsigned long long)kRecordChunk;
   }
+  if (tid == 32)
+  {
+    buildMissLadder(ladder, mp, 0u);  // RayMapperNdt applies no exclusion flags
+  }
+  if (tid == 0)
+  {
+    loadWorkItem(b, atomicAdd(&b.counters->work_next, 1u), &items2[0]);
+  }
   for (;;)
   {
-    __syncthreads();
-    if (tid == 0)
-    {
-      const uint32_t w = atomicAdd(&b.counters->work_next, 1u);
-      if (w < min(b.counters->item_count, b.item_capacity))
-      {
-        item = b.items[w];
-      }
-      else
-      {
-        item.slot = 0xFFFFFFFFu;
-      }
-    }
-    __syncthreads();
+    parity ^= 1u;
+    __syncthreads();  // the item is in place; the previous fold is done with the tile
+    const WorkItem &item = items2[parity];
     if (item.slot == 0xFFFFFFFFu)
     {
       return;
@@ -897,21 +1223,50 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsNdt(const __grid_c
       }
     }
     {
-      // established Gaussians: the persistent bit per voxel (mean count >= sample threshold)
-      const uint32_t *bits = dm.voxel_bits + (size_t)slot * kind_words;
+      // established Gaussians: the persistent bit per voxel (mean count >= sample threshold), laid out like the tile
+      const uint32_t fill = (mp.sample_threshold == 0) ? 0xFFFFFFFFu : 0u;
       for (uint32_t w = tid; w < kind_words; w += blockDim.x)
       {
-        kind[w] = (mp.sample_threshold == 0) ? 0xFFFFFFFFu : bits[w];
+        kind[w] = fill;
       }
     }
     __syncthreads();
+    if (mp.sample_threshold != 0 && tl.fast)
+    {
+      // eight voxels = one byte in both layouts
+      const uint8_t *bits8 = reinterpret_cast<const uint8_t *>(dm.voxel_bits + (size_t)slot * bit_words);
+      uint8_t *kind8 = reinterpret_cast<uint8_t *>(kind);
+      for (uint32_t c = tid; c < (g.vpr >> 3); c += blockDim.x)
+      {
+        kind8[groupPosition(tl, c) >> 3] = bits8[c];
+      }
+    }
+    else if (mp.sample_threshold != 0)
+    {
+      const uint32_t *bits = dm.voxel_bits + (size_t)slot * bit_words;
+      for (uint32_t w = tid; w < bit_words; w += blockDim.x)
+      {
+        uint32_t set = bits[w];
+        while (set)
+        {
+          const uint32_t half = tileHalf(tl, (w << 5) + (uint32_t)__ffs(set) - 1u);
+          set &= set - 1u;
+          atomicOr(&kind[half >> 5], 1u << (half & 31u));
+        }
+      }
+    }
     const uint32_t sample_end = b.sample_end[slot];
     for (uint32_t s = b.sample_begin[slot] + tid; s < sample_end; s += blockDim.x)
     {
-      const uint32_t v = b.keys_out[s] - vbase;
-      atomicOr(&tile[tileWord(v)], kTileFlag << ((v & 1u) * 16u));
+      const uint32_t half = tileHalf(tl, b.keys_out[s] - vbase);
+      atomicOr(&tile[half >> 1], kTileFlag << ((half & 1u) * 16u));
     }
     queueBuild(queue, b, item);
+    uint32_t next_work = 0;
+    if (tid == 0)
+    {
+      next_work = atomicAdd(&b.counters->work_next, 1u);  // the reply arrives while this item is walked
+    }
 
     for (;;)
     {
@@ -926,15 +1281,13 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsNdt(const __grid_c
         SegmentWalk sw;
         loadSegmentWalk(b, raw, sw);
         const uint32_t ray = sw.ray;
-        auto count_visit = [&](uint32_t idx) {
-          const uint32_t shift = (idx & 1u) * 16u;
-          const uint32_t old = atomicAdd(&tile[tileWord(idx)], 1u << shift);
-          if ((old >> shift) & kTileFlag)
+        auto count_visit = [&](uint32_t offset, uint32_t one) {
+          if (tileAdd(offset, one) & (one << 15))
           {
             const uint32_t at = reserveRecord(&record_chunk[warp], &b.counters->record_count);
             if (at < b.record_capacity)
             {
-              b.record_vid[at] = vbase + idx;
+              b.record_vid[at] = vbase + tileVoxel(tl, (offset - tile_base) >> 1);
               b.record_ray[at] = ray;
             }
             else
@@ -943,13 +1296,13 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsNdt(const __grid_c
               b.counters->overflow_seen = 1;
             }
           }
-          else if ((kind[idx >> 5] >> (idx & 31u)) & 1u)
+          else if ((kind[(offset - tile_base) >> 6] >> (((offset - tile_base) >> 1) & 31u)) & 1u)
           {
             // Established Gaussian: evaluated later, one thread per visit (ndtGaussianMisses).
             const uint32_t at = reserveRecord(&gauss_chunk[warp], &b.counters->gauss_count);
             if (at < b.gauss_capacity)
             {
-              b.gauss_keys[at] = ((unsigned long long)(vbase + idx) << 32) | ray;
+              b.gauss_keys[at] = ((unsigned long long)(vbase + tileVoxel(tl, (offset - tile_base) >> 1)) << 32) | ray;
             }
             else
             {
@@ -958,13 +1311,14 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsNdt(const __grid_c
             }
           }
         };
-        if (dm.traversal)
+        if (kTraversal)
         {
           const int dx = g.dim[0], dxy = g.dim[0] * g.dim[1];
           resumeSegment<true>(sw.init, sw.delta, sw.local0, sw.total, sw.flags, sw.st, sw.visits, b.ray_length[ray], g,
                               [&](const int l[3], double t_enter, double t_exit, bool last_of_ray) {
                                 const uint32_t idx = (uint32_t)(l[0] + l[1] * dx + l[2] * dxy);
-                                count_visit(idx);
+                                count_visit(tile_base + 2u * (uint32_t)(l[0] + l[1] * tl.row + l[2] * tl.slab),
+                                            (l[0] & 1) ? 0x10000u : 1u);
                                 atomicAdd(&dm.traversal[vbase + idx], (float)(t_exit - t_enter));
                                 if (last_of_ray)
                                 {
@@ -974,95 +1328,21 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsNdt(const __grid_c
         }
         else
         {
-          resumeSegmentFast(sw.init, sw.delta, sw.entry, sw.total, sw.flags, sw.st, sw.visits, g, count_visit);
+          resumeSegmentTile(sw.init, sw.delta, sw.entry, sw.total, sw.flags, sw.st, sw.visits, tl, tile_base, count_visit);
         }
       }
       __syncwarp();  // every lane of the warp is back together before the next pop
+    }
+    if (tid == 0)
+    {
+      loadWorkItem(b, next_work, &items2[parity ^ 1u]);
     }
     __syncthreads();
 
     // Fold.  Plain voxels: k identical misses (RayMapperNdt applies no exclusion flags).  Gaussian voxels: the
     // adjustments are already in the slab; apply occupancyAdjustDown's clamp.
-    float *occ = dm.occupancy + (size_t)vbase;
-    const uint4 *tile4 = reinterpret_cast<const uint4 *>(tile);
-    for (uint32_t c = tid; c < ((g.vpr + 7u) >> 3); c += blockDim.x)
-    {
-      const uint4 t = tile4[tileGroup(c)];
-      const uint32_t w4[4] = { t.x, t.y, t.z, t.w };
-      const uint32_t gauss8 = (kind[c >> 2] >> ((c & 3u) * 8u)) & 0xffu;
-      // counts of the plain voxels of the group (flagged voxels are replayed by applySamplesNdt, Gaussian voxels are
-      // handled by ndtGaussianMisses / ndtClampGaussians)
-      uint32_t cnt[8], any = 0;
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-      {
-        const uint32_t half = (w4[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
-        cnt[k] = ((half & kTileFlag) || ((gauss8 >> k) & 1u) || c * 8u + (uint32_t)k >= g.vpr) ? 0u : half;
-        any |= cnt[k];
-      }
-      if (!any)
-      {
-        continue;
-      }
-      if (dm.hit_miss)
-      {
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-        {
-          if (cnt[k])
-          {
-            atomicAdd(&dm.hit_miss[vbase + c * 8u + (uint32_t)k].y, cnt[k]);  // every plain NDT miss counts as a miss
-          }
-        }
-      }
-      if (!item.shared && (g.vpr & 7u) == 0)
-      {
-        // sole writer of the region's log-odds until this kernel ends: 2 x 128-bit read-modify-write
-        float4 *occ4 = reinterpret_cast<float4 *>(occ);
-        float4 a = occ4[2 * c], d = occ4[2 * c + 1];
-        a.x = missRepeat(a.x, cnt[0], mp, 0u);
-        a.y = missRepeat(a.y, cnt[1], mp, 0u);
-        a.z = missRepeat(a.z, cnt[2], mp, 0u);
-        a.w = missRepeat(a.w, cnt[3], mp, 0u);
-        d.x = missRepeat(d.x, cnt[4], mp, 0u);
-        d.y = missRepeat(d.y, cnt[5], mp, 0u);
-        d.z = missRepeat(d.z, cnt[6], mp, 0u);
-        d.w = missRepeat(d.w, cnt[7], mp, 0u);
-        occ4[2 * c] = a;
-        occ4[2 * c + 1] = d;
-        continue;
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-      {
-        if (cnt[k] == 0)
-        {
-          continue;
-        }
-        const uint32_t v = c * 8u + (uint32_t)k;
-        int *addr = reinterpret_cast<int *>(occ + v);
-        int seen = *reinterpret_cast<volatile int *>(addr);
-        for (;;)
-        {
-          const float next = missRepeat(__int_as_float(seen), cnt[k], mp, 0u);
-          if (__float_as_int(next) == seen)
-          {
-            break;
-          }
-          if (!item.shared)
-          {
-            occ[v] = next;
-            break;
-          }
-          const int prev = atomicCAS(addr, seen, __float_as_int(next));
-          if (prev == seen)
-          {
-            break;
-          }
-          seen = prev;
-        }
-      }
-    }
+    foldLogOddsTile(tile, kind, tl, dm.occupancy + (size_t)vbase, dm.hit_miss ? dm.hit_miss + (size_t)vbase : nullptr, mp, 0u,
+                    ladder, item.shared);
   }
 }
 

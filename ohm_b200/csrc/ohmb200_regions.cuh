@@ -13,29 +13,79 @@
 
 #include "ohmb200_device.cuh"
 
+#include <cstring>
+
 namespace ohmb200
 {
 constexpr unsigned kRecValid = 1u << 3, kRecExcludeStart = 1u << 4, kRecExcludeEnd = 1u << 5;
 constexpr uint32_t kMaxSegmentsPerItem = 2048;  // < 32768: tile counters are 15 bit + flag
 constexpr uint32_t kRecordChunk = 256;
-// Counter tile addressing.  Two u16 counters per 32-bit word; the word index is XOR-swizzled in bits 2..4 with a hash of
-// the higher bits (the y and z coordinates of the voxel), so lanes walking the same x/y column at different heights —
-// a lidar's elevation fan — spread over the shared-memory banks instead of queueing on one.  Groups of four words stay
-// together (128-bit accesses of the fold remain valid).  A tile holds tileWords() words (a multiple of 32).
-OHMB200_HD __forceinline__ uint32_t tileWords(uint32_t vpr)
+// Counter tile addressing.  One u16 counter per voxel (15-bit count + flag bit), two per 32-bit word.  The tile is a
+// padded copy of the region, the position of a voxel LINEAR in its coordinates:
+//        position(x, y, z) = x + row * y + slab * z          (counters; row and slab are even)
+// so a walking lane keeps a running byte offset and adds a constant per step — no index arithmetic per visit.
+// Rows are padded to an even length; a slab is padded to 8 counters more than a multiple of 64, so that the lanes of a
+// warp that walk one x/y column at different heights (neighbouring beams of one azimuth) do not all share a bank.
+// (Measured: the choice of paddings — OHMB200_TILE — does not move walkRegions; the fold's instruction count does.)
+// When dim x is a multiple of 8 (`fast`) the eight voxels 8c .. 8c+7 of the region are one aligned 16-byte group of
+// the tile: the fold scans the tile with 128-bit loads and skips empty groups.
+struct TileLayout
 {
-  return (((vpr + 1u) >> 1) + 31u) & ~31u;
+  int dx, dy, dz, dxy;  // region dimensions in voxels
+  int row, slab;        // tile strides in counters
+  uint32_t words;       // 32-bit words of the tile, a multiple of 32
+  uint32_t row_words;   // words of a row that hold voxels
+  uint32_t row_lanes;   // lanes the word-wise fold spends on a row: the power of two >= row_words, at most 32
+  uint32_t row_shift;   // log2(row_lanes)
+  uint32_t inv_dy;      // ceil(2^32 / dy): row number -> z with one multiply-high (exact below 2^21 rows)
+  uint32_t fast;        // groups of eight voxels are aligned 16-byte groups of the tile
+  uint32_t row_groups;  // fast: groups per row (dx / 8), and ceil(2^32 / row_groups)
+  uint32_t inv_row_groups;
+};
+OHMB200_HD inline TileLayout makeTileLayout(const Geom &g, int row_pad_words = 0, int slab_bank = 4)
+{
+  TileLayout t;
+  t.dx = g.dim[0];
+  t.dy = g.dim[1];
+  t.dz = g.dim[2];
+  t.dxy = g.dim[0] * g.dim[1];
+  t.row_words = (uint32_t)(g.dim[0] + 1) >> 1;
+  const uint32_t row_w = t.row_words + (uint32_t)row_pad_words;
+  uint32_t slab_w = row_w * (uint32_t)g.dim[1];
+  if (slab_bank >= 0)
+  {
+    slab_w += ((uint32_t)slab_bank + 32u - (slab_w & 31u)) & 31u;
+  }
+  t.row = (int)(2u * row_w);
+  t.slab = (int)(2u * slab_w);
+  t.words = (slab_w * (uint32_t)g.dim[2] + 31u) & ~31u;
+  t.row_lanes = 1;
+  t.row_shift = 0;
+  while (t.row_lanes < t.row_words && t.row_lanes < 32u)
+  {
+    t.row_lanes <<= 1;
+    ++t.row_shift;
+  }
+  t.inv_dy = (g.dim[1] > 1) ? (uint32_t)((0x100000000ull + (uint32_t)g.dim[1] - 1u) / (uint32_t)g.dim[1]) : 0u;
+  t.fast = (g.dim[0] % 8 == 0 && row_w % 4u == 0 && slab_w % 4u == 0) ? 1u : 0u;
+  t.row_groups = (uint32_t)g.dim[0] >> 3;
+  t.inv_row_groups = (t.row_groups > 1) ? (uint32_t)((0x100000000ull + t.row_groups - 1u) / t.row_groups) : 0u;
+  return t;
 }
-OHMB200_HD __forceinline__ uint32_t tileWord(uint32_t voxel)
+// counter position of voxel v (index inside the region) and back; divisions: not for the per-visit path
+OHMB200_HD __forceinline__ uint32_t tileHalf(const TileLayout &t, uint32_t v)
 {
-  const uint32_t w = voxel >> 1;
-  const uint32_t u = w >> 5;
-  return w ^ (((u ^ (u >> 3) ^ (u >> 6)) & 7u) << 2);
+  const uint32_t z = v / (uint32_t)t.dxy;
+  const uint32_t r = v - z * (uint32_t)t.dxy;
+  const uint32_t y = r / (uint32_t)t.dx;
+  return (r - y * (uint32_t)t.dx) + y * (uint32_t)t.row + z * (uint32_t)t.slab;
 }
-OHMB200_HD __forceinline__ uint32_t tileGroup(uint32_t group)  // group = word index / 4
+OHMB200_HD __forceinline__ uint32_t tileVoxel(const TileLayout &t, uint32_t half)
 {
-  const uint32_t u = group >> 3;
-  return group ^ ((u ^ (u >> 3) ^ (u >> 6)) & 7u);
+  const uint32_t z = half / (uint32_t)t.slab;
+  const uint32_t r = half - z * (uint32_t)t.slab;
+  const uint32_t y = r / (uint32_t)t.row;
+  return (r - y * (uint32_t)t.row) + y * (uint32_t)t.dx + z * (uint32_t)t.dxy;
 }
 constexpr uint32_t kStageSegments = 96;  // segments per ray that pass A hands to pass B without a second enumeration         // ordered-miss records are reserved per warp in chunks
 constexpr uint32_t kTileFlag = 0x8000u;
@@ -375,6 +425,76 @@ OHMB200_HD __forceinline__ void resumeSegmentFast(const double init[3], const do
       m1 += 1.0;
       idx += step1;
       t1 = (s1 < total[1]) ? init[1] + delta[1] * m1 : (double)INFINITY;
+    }
+  }
+}
+
+// High word of a double.  For integer values below 2^20 it identifies the value (the low word is zero).
+OHMB200_HD __forceinline__ int hiWord(double x)
+{
+#ifdef __CUDA_ARCH__
+  return __double2hiint(x);
+#else
+  unsigned long long u;
+  memcpy(&u, &x, sizeof(u));
+  return (int)(u >> 32);
+#endif
+}
+
+// The walk of the counting kernels: resumeSegmentFast against the counter tile.  visit(offset, one) receives the BYTE
+// offset of the voxel's u16 counter in the tile (plus tile_base: the kernels pass the tile's shared-memory address, so
+// that `offset & ~3` is the address of the word) and the increment of that counter inside its 32-bit word (1 or 1 << 16);
+// both are carried along — a constant is added per step, the increment swaps halves on x steps (tile rows and slabs
+// have even strides) — so a visit costs one AND, the shared-memory atomic and the flag test.  The per-axis step count
+// lives only in the double m (the multiplier of LineWalkCompute.h:373-376); "axis finished" compares its high word
+// with that of the axis total (both are integers below 2^16).  Same arithmetic, same order of comparisons as
+// walkSelectNextAxis: strict '<', ties go to the higher axis.
+// (Measured alternatives that lost: computing the next exit time one step ahead and testing the flag of a visit one
+// step later shorten the dependent chain but add instructions — the walk phase is bound by issue slots, +8 %.)
+template <typename Visit>
+OHMB200_HD __forceinline__ void resumeSegmentTile(const double init[3], const double delta[3], const int entry[3],
+                                                  const int total[3], uint32_t flags, const int st_in[3], int visits,
+                                                  const TileLayout &tl, uint32_t tile_base, Visit &&visit)
+{
+  int offset = (int)tile_base + 2 * (entry[0] + entry[1] * tl.row + entry[2] * tl.slab);
+  uint32_t one = (entry[0] & 1) ? 0x10000u : 1u;
+  const int step0 = (flags & 1u) ? -2 : 2;
+  const int step1 = (flags & 2u) ? -2 * tl.row : 2 * tl.row;
+  const int step2 = (flags & 4u) ? -2 * tl.slab : 2 * tl.slab;
+  double m0 = (double)st_in[0], m1 = (double)st_in[1], m2 = (double)st_in[2];
+  const int end0 = hiWord((double)total[0]), end1 = hiWord((double)total[1]), end2 = hiWord((double)total[2]);
+  double t0 = (st_in[0] < total[0]) ? (st_in[0] == 0 ? init[0] : init[0] + delta[0] * m0) : (double)INFINITY;
+  double t1 = (st_in[1] < total[1]) ? (st_in[1] == 0 ? init[1] : init[1] + delta[1] * m1) : (double)INFINITY;
+  double t2 = (st_in[2] < total[2]) ? (st_in[2] == 0 ? init[2] : init[2] + delta[2] * m2) : (double)INFINITY;
+  for (int v = 0;;)
+  {
+    visit((uint32_t)offset, one);
+    if (++v >= visits)
+    {
+      break;
+    }
+    const bool x_before_y = t0 < t1, x_before_z = t0 < t2, y_before_z = t1 < t2;
+    if (x_before_y && x_before_z)
+    {
+      m0 += 1.0;
+      offset += step0;
+      one = (one << 16) | (one >> 16);
+      const double t = init[0] + delta[0] * m0;
+      t0 = (hiWord(m0) != end0) ? t : (double)INFINITY;
+    }
+    else if (!x_before_y && y_before_z)
+    {
+      m1 += 1.0;
+      offset += step1;
+      const double t = init[1] + delta[1] * m1;
+      t1 = (hiWord(m1) != end1) ? t : (double)INFINITY;
+    }
+    else
+    {
+      m2 += 1.0;
+      offset += step2;
+      const double t = init[2] + delta[2] * m2;
+      t2 = (hiWord(m2) != end2) ? t : (double)INFINITY;
     }
   }
 }

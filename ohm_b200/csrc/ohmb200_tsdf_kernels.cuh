@@ -163,18 +163,124 @@ __global__ void __launch_bounds__(128) markTsdfNear(const __grid_constant__ Devi
   }
 }
 
+// The fold of walkRegionsTsdf: k commuting far visits of a voxel -> (trunc, min(w + 1, max) k times).
+__device__ __forceinline__ void foldTsdfTile(const uint32_t *tile, const TileLayout &layout, float2 *slab,
+                                             const MapParams &mp, uint32_t shared)
+{
+  const TileLayout tl = foldLayout(layout);
+  auto far_visits = [&](float w, uint32_t k) {
+    if (w == floorf(w) && w + (float)k <= 16777216.0f)
+    {
+      return fminf(w + (float)k, mp.tsdf_max_weight);  // integer weights: every +1 is exact
+    }
+    for (uint32_t n = 0; n < k; ++n)
+    {
+      const float next = fminf(w + 1.0f, mp.tsdf_max_weight);
+      if (next == w)
+      {
+        break;
+      }
+      w = next;
+    }
+    return w;
+  };
+  const auto voxel_after = [&](unsigned long long old, uint32_t count) {
+    const float w = far_visits(__uint_as_float((uint32_t)old), count);
+    return (unsigned long long)__float_as_uint(w) | ((unsigned long long)__float_as_uint(mp.tsdf_trunc) << 32);
+  };
+  if (!tl.fast)
+  {
+    foldTileVoxels(tile, tl, [&](uint32_t v, uint32_t, uint32_t half) {
+      if (half == 0 || (half & kTileFlag))
+      {
+        return;
+      }
+      unsigned long long *unit = reinterpret_cast<unsigned long long *>(slab + v);
+      if (!shared)
+      {
+        *unit = voxel_after(*unit, half);
+      }
+      else
+      {
+        foldUnitShared(unit, __ldcg(unit), [&](unsigned long long old) { return voxel_after(old, half); });
+      }
+    });
+    return;
+  }
+  foldGroups(tile, tl, [&](uint32_t c, uint32_t, const uint4 &t) {
+    const uint32_t w4[4] = { t.x, t.y, t.z, t.w };
+    uint32_t cnt[8], any = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+    {
+      const uint32_t half = (w4[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+      cnt[k] = (half & kTileFlag) ? 0u : half;
+      any |= cnt[k];
+    }
+    if (!any)
+    {
+      return;
+    }
+    if (!shared)
+    {
+      // sole writer of the region in this batch: 64-byte read-modify-write of eight voxels at a time
+      float4 *slab4 = reinterpret_cast<float4 *>(slab) + 4u * c;
+      float4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+      {
+        v[k] = slab4[k];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+      {
+        if (cnt[2 * k])
+        {
+          v[k].x = far_visits(v[k].x, cnt[2 * k]);
+          v[k].y = mp.tsdf_trunc;
+        }
+        if (cnt[2 * k + 1])
+        {
+          v[k].z = far_visits(v[k].z, cnt[2 * k + 1]);
+          v[k].w = mp.tsdf_trunc;
+        }
+        slab4[k] = v[k];
+      }
+      return;
+    }
+    unsigned long long *units = reinterpret_cast<unsigned long long *>(slab) + 8u * c;
+    unsigned long long seen[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+    {
+      seen[k] = cnt[k] ? __ldcg(units + k) : 0ull;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+    {
+      if (cnt[k])
+      {
+        foldUnitShared(units + k, seen[k], [&](unsigned long long old) { return voxel_after(old, cnt[k]); });
+      }
+    }
+  });
+}
+
 // Pass 2: count far visits of unflagged voxels in the tile, record every visit of flagged voxels (stored state not
 // order-free, or near a sample in this batch), fold the counts.
-__global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsTsdf(const __grid_constant__ DeviceMap dm,
+__global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegionsTsdf(const __grid_constant__ DeviceMap dm,
                                                                    const __grid_constant__ Geom g,
                                                                    const __grid_constant__ MapParams mp,
-                                                                   const __grid_constant__ Batch b, const uint32_t *near)
+                                                                   const __grid_constant__ Batch b,
+                                                                   const __grid_constant__ TileLayout tl, const uint32_t *near)
 {
   extern __shared__ uint32_t tile[];
-  __shared__ WorkItem item;
+  __shared__ WorkItem items2[2];  // this work item and the next one (fetched during the walk)
+  uint32_t parity = 1;
   __shared__ unsigned long long record_chunk[kWalkThreads / 32];
   __shared__ SegmentQueue queue;
-  const uint32_t words = tileWords(g.vpr);
+  const uint32_t words = tl.words;
+  const uint32_t tile_base = (uint32_t)__cvta_generic_to_shared(tile);
   const uint32_t flag_words = (g.vpr + 31u) >> 5;
   const uint32_t tid = threadIdx.x;
   const uint32_t warp = tid >> 5;
@@ -183,22 +289,15 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsTsdf(const __grid_
   {
     record_chunk[warp] = (unsigned long long)kRecordChunk;
   }
+  if (tid == 0)
+  {
+    loadWorkItem(b, atomicAdd(&b.counters->work_next, 1u), &items2[0]);
+  }
   for (;;)
   {
-    __syncthreads();
-    if (tid == 0)
-    {
-      const uint32_t w = atomicAdd(&b.counters->work_next, 1u);
-      if (w < min(b.counters->item_count, b.item_capacity))
-      {
-        item = b.items[w];
-      }
-      else
-      {
-        item.slot = 0xFFFFFFFFu;
-      }
-    }
-    __syncthreads();
+    parity ^= 1u;
+    __syncthreads();  // the item is in place; the previous fold is done with the tile
+    const WorkItem &item = items2[parity];
     if (item.slot == 0xFFFFFFFFu)
     {
       return;
@@ -223,13 +322,18 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsTsdf(const __grid_
         uint32_t bits = ordered_bits[w] | near_bits[w];
         while (bits)
         {
-          const uint32_t v = (w << 5) + (uint32_t)__ffs(bits) - 1u;
+          const uint32_t half = tileHalf(tl, (w << 5) + (uint32_t)__ffs(bits) - 1u);
           bits &= bits - 1u;
-          atomicOr(&tile[tileWord(v)], kTileFlag << ((v & 1u) * 16u));
+          atomicOr(&tile[half >> 1], kTileFlag << ((half & 1u) * 16u));
         }
       }
     }
     queueBuild(queue, b, item);
+    uint32_t next_work = 0;
+    if (tid == 0)
+    {
+      next_work = atomicAdd(&b.counters->work_next, 1u);  // the reply arrives while this item is walked
+    }
 
     for (;;)
     {
@@ -244,15 +348,13 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsTsdf(const __grid_
         SegmentWalk sw;
         loadSegmentWalk(b, raw, sw);
         const uint32_t ray = sw.ray;
-        resumeSegmentFast(sw.init, sw.delta, sw.entry, sw.total, sw.flags, sw.st, sw.visits, g, [&](uint32_t idx) {
-          const uint32_t shift = (idx & 1u) * 16u;
-          const uint32_t old = atomicAdd(&tile[tileWord(idx)], 1u << shift);
-          if ((old >> shift) & kTileFlag)
+        resumeSegmentTile(sw.init, sw.delta, sw.entry, sw.total, sw.flags, sw.st, sw.visits, tl, tile_base, [&](uint32_t offset, uint32_t one) {
+          if (tileAdd(offset, one) & (one << 15))
           {
             const uint32_t at = reserveRecord(&record_chunk[warp], &b.counters->record_count);
             if (at < b.record_capacity)
             {
-              b.record_keys[at] = ((unsigned long long)(vbase + idx) << 32) | ray;
+              b.record_keys[at] = ((unsigned long long)(vbase + tileVoxel(tl, (offset - tile_base) >> 1)) << 32) | ray;
             }
             else
             {
@@ -264,99 +366,13 @@ __global__ void __launch_bounds__(kWalkThreads, 2) walkRegionsTsdf(const __grid_
       }
       __syncwarp();  // every lane of the warp is back together before the next pop
     }
+    if (tid == 0)
+    {
+      loadWorkItem(b, next_work, &items2[parity ^ 1u]);
+    }
     __syncthreads();
 
-    // Fold: k commuting far visits -> (trunc, min(w + 1, max) k times).
-    float2 *slab = dm.tsdf + (size_t)vbase;
-    const uint4 *tile4 = reinterpret_cast<const uint4 *>(tile);
-    auto far_visits = [&](float w, uint32_t k) {
-      if (w == floorf(w) && w + (float)k <= 16777216.0f)
-      {
-        return fminf(w + (float)k, mp.tsdf_max_weight);  // integer weights: every +1 is exact
-      }
-      for (uint32_t n = 0; n < k; ++n)
-      {
-        const float next = fminf(w + 1.0f, mp.tsdf_max_weight);
-        if (next == w)
-        {
-          break;
-        }
-        w = next;
-      }
-      return w;
-    };
-    if (!item.shared && (g.vpr & 7u) == 0)
-    {
-      // sole writer of the region in this batch: 64-byte read-modify-write of eight voxels at a time
-      float4 *slab4 = reinterpret_cast<float4 *>(slab);
-      for (uint32_t c = tid; c < (g.vpr >> 3); c += blockDim.x)
-      {
-        const uint4 t = tile4[tileGroup(c)];
-        const uint32_t w4[4] = { t.x, t.y, t.z, t.w };
-        uint32_t cnt[8], any = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-        {
-          const uint32_t half = (w4[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
-          cnt[k] = (half & kTileFlag) ? 0u : half;
-          any |= cnt[k];
-        }
-        if (any)
-        {
-          float4 v[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-          {
-            v[k] = slab4[4 * c + k];
-          }
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-          {
-            if (cnt[2 * k])
-            {
-              v[k].x = far_visits(v[k].x, cnt[2 * k]);
-              v[k].y = mp.tsdf_trunc;
-            }
-            if (cnt[2 * k + 1])
-            {
-              v[k].z = far_visits(v[k].z, cnt[2 * k + 1]);
-              v[k].w = mp.tsdf_trunc;
-            }
-            slab4[4 * c + k] = v[k];
-          }
-        }
-      }
-    }
-    else
-    {
-      for (uint32_t v = tid; v < g.vpr; v += blockDim.x)
-      {
-        const uint32_t half = (tile[tileWord(v)] >> ((v & 1u) * 16u)) & 0xffffu;
-        if (half == 0 || (half & kTileFlag))
-        {
-          continue;
-        }
-        unsigned long long *addr = reinterpret_cast<unsigned long long *>(slab + v);
-        unsigned long long seen = *reinterpret_cast<volatile unsigned long long *>(addr);
-        for (;;)
-        {
-          const float w = far_visits(__uint_as_float((uint32_t)seen), half);
-          const unsigned long long want =
-            (unsigned long long)__float_as_uint(w) | ((unsigned long long)__float_as_uint(mp.tsdf_trunc) << 32);
-          if (!item.shared)
-          {
-            *addr = want;
-            break;
-          }
-          const unsigned long long prev = atomicCAS(addr, seen, want);
-          if (prev == seen)
-          {
-            break;
-          }
-          seen = prev;
-        }
-      }
-    }
+    foldTsdfTile(tile, tl, dm.tsdf + (size_t)vbase, mp, item.shared);
   }
 }
 

@@ -61,7 +61,9 @@ static bool checkRay(const Geom &g, const double start[3], const double end[3], 
   const double len2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
   const double length = (len2 > 1e-6) ? sqrt(len2) : 0;
   std::vector<Visit> seg;
-  std::vector<uint32_t> fast_idx;
+  std::vector<uint32_t> fast_idx, tile_idx;
+  const TileLayout tl = makeTileLayout(g);
+  bool tile_ok = true;
   int last_flags = 0;
   enumerateSegments(rec, g, [&](const int r[3], const int st[3], const int entry[3], int n) {
     ++g_segments;
@@ -80,6 +82,14 @@ static bool checkRay(const Geom &g, const double start[3], const double end[3], 
     // the hot-path variant must visit the same voxels (as linear indices inside the region)
     resumeSegmentFast(rec.initial, rec.delta, entry, total, rec.flags, st, n, g,
                       [&](uint32_t idx) { fast_idx.push_back(idx); });
+    // and so must the counter-tile walker: its running byte offset must address the counter of the same voxel, and
+    // its running increment must select the right half of the word
+    resumeSegmentTile(rec.initial, rec.delta, entry, total, rec.flags, st, n, tl, 0u, [&](uint32_t offset, uint32_t one) {
+      const uint32_t half = offset >> 1;
+      tile_ok = tile_ok && (offset & 1u) == 0 && one == ((half & 1u) ? 0x10000u : 1u);
+      tile_ok = tile_ok && half < 2u * tl.words && tileHalf(tl, tileVoxel(tl, half)) == half;
+      tile_idx.push_back(tileVoxel(tl, half));
+    });
   });
   ++g_rays;
   g_visits += (long long)seq.size();
@@ -92,7 +102,7 @@ static bool checkRay(const Geom &g, const double start[3], const double end[3], 
     ok = ok && (i == 0 || memcmp(&seq[i].enter, &seg[i].enter, sizeof(double)) == 0);
   }
   ok = ok && (seq.empty() || last_flags == 1);
-  ok = ok && fast_idx.size() == seg.size();
+  ok = ok && fast_idx.size() == seg.size() && tile_ok && tile_idx == fast_idx;
   for (size_t i = 0; ok && i < seg.size(); ++i)
   {
     ok = fast_idx[i] == (uint32_t)(seg[i].l[0] + seg[i].l[1] * g.dim[0] + seg[i].l[2] * g.dim[0] * g.dim[1]);

@@ -103,6 +103,23 @@ def test_ndt_random_rays_batched(gpu):
     check_counts(g, c)
 
 
+@pytest.mark.parametrize("dims", [(12, 10, 6), (5, 7, 3), (16, 24, 8)])
+def test_ndt_region_dimensions(gpu, dims):
+    # the Gaussian bits follow the counter tile's layout: byte copies when dim x is a multiple of 8, bit by bit otherwise
+    g, c = make_pair(0.25, mode="ndt", region_dim=dims, origin=(0.3, -0.7, 0.11))
+    rng = np.random.RandomState(dims[0])
+    rays = np.empty((2 * 8192, 3))
+    rays[0::2] = [0.05, 0.05, 0.05]
+    pts = rng.uniform(-6, 6, size=(8192, 3))
+    pts[:4096, 2] = -1.0 + rng.normal(scale=0.02, size=4096)
+    pts[4096:6144, 0] = 4.0 + rng.normal(scale=0.02, size=2048)
+    rays[1::2] = pts
+    integrate_both(g, c, rays, batch=2048)
+    integrate_both(g, c, rays[::-1].copy().reshape(-1, 3), batch=4096)
+    compare_maps(g, c, tol_layers=OCC_TOL)
+    check_counts(g, c)
+
+
 def test_ndt_all_layers_with_timestamps(gpu):
     layers = [gm.LAYER_OCCUPANCY, gm.LAYER_MEAN, gm.LAYER_COVARIANCE, gm.LAYER_TOUCH_TIME, gm.LAYER_INCIDENT,
               gm.LAYER_TRAVERSAL]

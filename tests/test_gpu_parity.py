@@ -88,6 +88,23 @@ def test_compare_in_voxel_rays_then_clear(gpu):
     assert np.all(occ[0, :15, :] < 0) and np.all(occ[0, 15, :] > 0) and np.all(occ[1:] == np.float32(g.hit_value()))
 
 
+@pytest.mark.parametrize("dims", [(12, 10, 6), (5, 7, 3), (16, 24, 8), (9, 32, 4)])
+def test_region_dimensions_and_origin(gpu, dims):
+    # counter tiles of every shape: odd rows (padded to an even stride), rows that are not a multiple of 8 (scalar
+    # fold), slabs that are (the 128-bit fold); several work items per region (a hot region is split and folded by CAS)
+    g, c = make_pair(0.25, region_dim=dims, origin=(0.3, -0.7, 0.11),
+                     layers=[gm.LAYER_OCCUPANCY, gm.LAYER_MEAN, gm.LAYER_TRAVERSAL])
+    rays = random_rays(12000, 9.0, seed=dims[0])
+    integrate_both(g, c, rays[:16000])
+    integrate_both(g, c, rays[16000:], batch=1500)
+    compare_maps(g, c, tol_layers={gm.LAYER_TRAVERSAL: (2e-5, 1e-6)})
+    check_counts(g, c)
+    g2, c2 = make_pair(0.25, region_dim=dims, origin=(0.3, -0.7, 0.11))   # without traversal: the counting walker
+    integrate_both(g2, c2, rays)
+    compare_maps(g2, c2)
+    check_counts(g2, c2)
+
+
 @pytest.mark.parametrize("flags", [
     gm.RF_END_POINT_AS_FREE, gm.RF_EXCLUDE_ORIGIN, gm.RF_EXCLUDE_SAMPLE, gm.RF_EXCLUDE_RAY,
     gm.RF_EXCLUDE_UNOBSERVED, gm.RF_EXCLUDE_FREE, gm.RF_EXCLUDE_OCCUPIED, gm.RF_REVERSE_WALK,

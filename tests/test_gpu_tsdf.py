@@ -50,6 +50,16 @@ def test_tsdf_random_rays_batched(gpu):
     check_visits(g, c)
 
 
+@pytest.mark.parametrize("dims", [(12, 10, 6), (5, 7, 3), (16, 24, 8)])
+def test_tsdf_region_dimensions(gpu, dims):
+    g, c = make_pair(0.1, mode="tsdf", region_dim=dims, origin=(0.03, -0.07, 0.011))
+    rays = random_rays(6000, 3.0, dims[1])
+    integrate_both(g, c, rays, batch=2048)
+    integrate_both(g, c, rays[::-1].copy().reshape(-1, 3))
+    compare_maps(g, c)
+    check_visits(g, c)
+
+
 @pytest.mark.parametrize("kw", [dict(tsdf_trunc=0.3, tsdf_max_weight=20.0), dict(tsdf_dropoff=0.05),
                                 dict(tsdf_sparsity=2.5), dict(tsdf_sparsity=0.0, tsdf_trunc=0.25)])
 def test_tsdf_options(gpu, kw):
