@@ -14,9 +14,12 @@ map working set (> L2) from HBM.
   e2e     the same step through the reference-facing call ohmb200_integrate with HOST (pinned) ray buffers:
           host->device copy of the rays, all kernels, device->host read of the step's counters, and the
           syncVoxels-equivalent download of every occupancy region chunk, all inside the timed span.
-  N>1     regions are sharded over the GPUs (ohmb200_set_partition); rank r holds 1/N of the sweep's rays, one
-          NCCL all-gather per step hands every GPU the whole sweep, and each GPU applies the visits/samples that
-          fall in the regions it owns.  Strong scaling: the sweep is fixed as N grows.
+  N>1     weak scaling: a step is N consecutive sweeps of the moving sensor (one per GPU, BASELINE config 5's
+          trajectory) integrated as ONE batch into ONE map whose regions are sharded over the GPUs
+          (ohmb200_set_partition).  Rank r holds sweep r; one NCCL all-gather per step hands every GPU the whole
+          batch, and each GPU applies the visits/samples that fall in the regions it owns.  The union of the N
+          maps is bit-identical to one GPU (or the CPU mapper) integrating the same batch.  value = rays of all
+          N sweeps / step time.
 """
 import argparse
 import ctypes
@@ -115,10 +118,12 @@ class ClockSampler:
         return out
 
 
-def sweep_rays():
+def sweep_rays(count=1):
+    """The first `count` sweeps of the trajectory, as a list of (2n, 3) ray arrays (count == 1: the config-2 sweep)."""
     from ohm_b200.lidar import LidarBox
-    rays, _, _ = LidarBox(1).sweep()
-    return np.ascontiguousarray(rays)
+    box = LidarBox(count)
+    sweeps = [np.ascontiguousarray(box.sweep()[0]) for _ in range(count)]
+    return sweeps[0] if count == 1 else sweeps
 
 
 def cpu_mapper():
@@ -176,7 +181,7 @@ def run_reference(args):
             if kind == "reference" else "C port of ohm::RayMapperOccupancy (oracle/ohm_oracle.c)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64 walk / f32 log-odds", "data": "synthetic",
         "config": {"workload": WORKLOAD, "rays_per_step": n,
                    "note": f"{what}; 1 thread — the mapper is single-threaded by design (ohm/RayMapperOccupancy.h:25-27); "
@@ -207,7 +212,9 @@ def run_gpu(args):
         os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    rays = sweep_rays()
+    # One sweep per rank: the step's batch is the concatenation of the N sweeps, in sweep order.
+    sweeps = [sweep_rays()] if world == 1 else sweep_rays(world)
+    rays = np.concatenate(sweeps)
     n = rays.shape[0] // 2
     gpu = ohm_b200.GpuMap(RESOLUTION, device_bytes=int(args.device_gib * (1 << 30)), device=local_rank)
     if world > 1:
@@ -215,12 +222,12 @@ def run_gpu(args):
     stream = torch.cuda.Stream()
     gpu.set_stream(stream.cuda_stream)
 
-    # Device-resident rays: every rank holds its 1/world slice; the gathered sweep is the kernels' input.
-    per = (n + world - 1) // world
+    # Device-resident rays: every rank holds its own sweep; the gathered batch is the kernels' input.
+    per = max(s.shape[0] // 2 for s in sweeps)
     pad = per * world
-    rays_padded = np.full((pad * 2, 3), np.nan)  # NaN rays are rejected by the filter (padding only)
-    rays_padded[:2 * n] = rays
-    d_slice = torch.from_numpy(rays_padded[2 * per * rank:2 * per * (rank + 1)].copy()).cuda()
+    mine = np.full((per * 2, 3), np.nan)  # NaN rays are rejected by the filter (padding to the longest sweep only)
+    mine[:sweeps[rank].shape[0]] = sweeps[rank]
+    d_slice = torch.from_numpy(mine).cuda()
     d_full = torch.empty((pad * 2, 3), dtype=torch.float64, device="cuda")
     if world == 1:
         d_full.copy_(d_slice)
@@ -380,15 +387,17 @@ def run_gpu(args):
         dom_ms = dom_t["ms"] / max(dom_t["launches"], 1)
         achieved = alg_bytes / (dom_ms * 1e-3) / 1e9 / max(world, 1) if dom_ms > 0 else 0.0
         traffic = ncu_traffic()
-        cpu = cpu_baseline(rays, reps=args.cpu_reps) if args.cpu_reps > 0 else None
+        cpu = cpu_baseline(sweeps[0], reps=args.cpu_reps) if args.cpu_reps > 0 and world == 1 else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 walk / f32 log-odds", "data": "synthetic",
             "config": {
-                "workload": WORKLOAD, "rays_per_step": n, "voxel_visits_per_step": visits,
+                "workload": WORKLOAD if world == 1 else
+                f"{WORKLOAD} per GPU: {world} consecutive sweeps of the moving sensor as one batch into one region-sharded map",
+                "rays_per_step": n, "voxel_visits_per_step": visits,
                 "sample_updates_per_step": samples, "regions": regions, "resolution_m": RESOLUTION,
-                "parallelism": "single GPU" if world == 1 else f"regions sharded over {world} GPUs (owner = (rx + 2 ry + 4 rz) mod {world}), 1 NCCL all-gather of the rays per step, queued one step ahead on its own stream",
+                "parallelism": "single GPU" if world == 1 else f"regions sharded over {world} GPUs (owner = (rx + 2 ry + 4 rz) mod {world}); rank r brings sweep r, 1 NCCL all-gather of the batch per step, queued one step ahead on its own stream",
                 "l2": "map cleared + 512 MiB L2 flush between timed steps (outside the timed spans); the per-step map "
                       "working set (pending + occupancy tiles of every touched region) exceeds the 126 MB L2",
                 "timing": "CUDA events on the launch stream per step, max over ranks, summed over steps",

@@ -267,6 +267,19 @@ typedef struct ohmb200_kernel_time
 OHMB200_API int ohmb200_set_profiling(ohmb200_map *map, int enabled);
 OHMB200_API int ohmb200_kernel_times(ohmb200_map *map, ohmb200_kernel_time *out, int capacity, int reset);
 
+/* ---- paging: the GpuLayerCache of this build (ohmgpu/GpuLayerCache.cpp:429-633, GpuCache.h) ------------------------
+ * The map is resident in device memory (device_bytes / bytes per region = the slots of the region table).  When a
+ * batch may not find enough free slots, the least recently walked regions are copied to a host-side store and their
+ * slots freed (GpuLayerCache evicts its oldest cache entry and syncs it to the MapChunk); a region that is touched
+ * again is uploaded before the batch updates it (GpuLayerCache::upload on a cache miss).  Reads, enumeration and the
+ * region count cover both halves.  Eviction waits for the queued work, so a map that fits never pays for it.
+ * ohmb200_set_region_reserve: free slots to guarantee before every batch (default min(4096, capacity / 2)); a single
+ * batch that creates more regions than that can still fill the table (ohmb200_sync -> OHMB200_E_CACHE_FULL). */
+OHMB200_API int ohmb200_set_region_reserve(ohmb200_map *map, uint32_t free_slots);
+/* resident = regions in device memory, stored = regions in the host store, evicted / paged_in = totals so far. */
+OHMB200_API int ohmb200_paging_stats(ohmb200_map *map, uint64_t *resident, uint64_t *stored, uint64_t *evicted,
+                                     uint64_t *paged_in);
+
 /* Message of the last failure on this thread. */
 OHMB200_API const char *ohmb200_last_error(void);
 

@@ -252,6 +252,23 @@ public:
   {
     return map_ && ohmb200_read_region(map_, reinterpret_cast<const int16_t *>(&key), layer, dst, bytes) == OHMB200_OK;
   }
+  /// Paging (GpuLayerCache's eviction / upload on a miss, ohmgpu/GpuLayerCache.cpp:429-633): the regions that do not
+  /// fit in device memory live in a host-side store inside the library; every read covers both halves.
+  struct PagingStats
+  {
+    uint64_t resident = 0, stored = 0, evicted = 0, paged_in = 0;
+  };
+  PagingStats pagingStats() const
+  {
+    PagingStats s;
+    if (map_)
+    {
+      ohmb200_paging_stats(map_, &s.resident, &s.stored, &s.evicted, &s.paged_in);
+    }
+    return s;
+  }
+  /// Free region slots guaranteed before every batch (the gpu_mem_size counterpart for regions created per batch).
+  bool setRegionReserve(uint32_t free_slots) { return map_ && ohmb200_set_region_reserve(map_, free_slots) == OHMB200_OK; }
   /// GpuCache::clear + OccupancyMap::clear
   void clear()
   {

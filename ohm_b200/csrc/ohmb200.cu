@@ -28,6 +28,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 using namespace ohmb200;
@@ -35,6 +36,18 @@ using namespace ohmb200;
 // ---------------------------------------------------------------------------------------------------------
 // Errors
 // ---------------------------------------------------------------------------------------------------------
+#define PAGING_TRACE(...)                          \
+  do                                               \
+  {                                                \
+    static const bool on = getenv("OHMB200_TRACE_PAGING") != nullptr; \
+    if (on)                                        \
+    {                                              \
+      fprintf(stderr, "[paging] " __VA_ARGS__);    \
+      fputc('\n', stderr);                         \
+      fflush(stderr);                              \
+    }                                              \
+  } while (0)
+
 static thread_local char g_last_error[512] = "";
 
 static int setError(int code, const char *fmt, ...)
@@ -78,11 +91,12 @@ struct Counters
   uint32_t segment_overflow;
   uint32_t gauss_count;  // NDT: reserved Gaussian-visit record slots
   uint32_t heavy_count;  // NDT: runs set aside for the warp-per-run replay
+  uint32_t new_count;    // regions inserted by this batch (paging: the ones with a chunk in the host store are restored)
   // sticky
   int table_full;
   int overflow_seen;
 };
-constexpr int kPerBatchCounterWords = 10;  // record_count .. heavy_count
+constexpr int kPerBatchCounterWords = 11;  // record_count .. new_count
 
 struct Batch
 {
@@ -715,39 +729,63 @@ struct ClearTable
   int count;
 };
 
+// Resets every layer chunk of one slot to its clear value (one CTA).
+__device__ __forceinline__ void clearSlot(const ClearTable &table, uint32_t slot)
+{
+  for (int l = 0; l < table.count; ++l)
+  {
+    uint32_t *chunk = table.base[l] + (size_t)slot * table.words[l];
+    const uint32_t fill = table.fill[l];
+    if ((table.words[l] & 3u) == 0)
+    {
+      uint4 *chunk4 = reinterpret_cast<uint4 *>(chunk);
+      for (uint32_t w = threadIdx.x; w < (table.words[l] >> 2); w += blockDim.x)
+      {
+        chunk4[w] = make_uint4(fill, fill, fill, fill);
+      }
+    }
+    else
+    {
+      for (uint32_t w = threadIdx.x; w < table.words[l]; w += blockDim.x)
+      {
+        chunk[w] = fill;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) clearLiveRegions(DeviceMap dm, ClearTable table)
 {
   for (uint32_t slot = blockIdx.x; slot < dm.capacity; slot += gridDim.x)
   {
-    if (dm.keys[slot] == kEmptyKey)
+    const unsigned long long key = dm.keys[slot];
+    if (key == kEmptyKey)
     {
       continue;
     }
-    for (int l = 0; l < table.count; ++l)
+    if (key != kTombKey)  // the chunks of an evicted slot were cleared when it was evicted
     {
-      uint32_t *chunk = table.base[l] + (size_t)slot * table.words[l];
-      const uint32_t fill = table.fill[l];
-      if ((table.words[l] & 3u) == 0)
-      {
-        uint4 *chunk4 = reinterpret_cast<uint4 *>(chunk);
-        for (uint32_t w = threadIdx.x; w < (table.words[l] >> 2); w += blockDim.x)
-        {
-          chunk4[w] = make_uint4(fill, fill, fill, fill);
-        }
-      }
-      else
-      {
-        for (uint32_t w = threadIdx.x; w < table.words[l]; w += blockDim.x)
-        {
-          chunk[w] = fill;
-        }
-      }
+      clearSlot(table, slot);
     }
     __syncthreads();  // every thread has read keys[slot] before it is freed
     if (threadIdx.x == 0)
     {
       dm.keys[slot] = kEmptyKey;
       dm.region_stamp[slot] = 0;
+    }
+  }
+}
+
+// Eviction (GpuLayerCache.cpp:536-600): the chunks of the listed slots have been copied to the host store; clear them
+// for their next tenant.  The keys themselves are rewritten by the host (tombstones, see makeRoom).
+__global__ void __launch_bounds__(256) clearEvictedSlots(DeviceMap dm, ClearTable table, const uint32_t *slots, uint32_t count)
+{
+  for (uint32_t i = blockIdx.x; i < count; i += gridDim.x)
+  {
+    clearSlot(table, slots[i]);
+    if (threadIdx.x == 0)
+    {
+      dm.region_stamp[slots[i]] = 0;
     }
   }
 }
@@ -906,6 +944,15 @@ struct ohmb200_map
   void *d_secondary_rays = nullptr;
   size_t secondary_rays_bytes = 0;
   int *d_lookup_missing = nullptr;  // device flag: an asynchronous download named a region that is not resident
+  // Paging (the GpuLayerCache of this build, ohmgpu/GpuLayerCache.cpp:429-633): when the region table runs out of
+  // slots the least recently walked regions are copied to this host store and their slots freed; a region that is
+  // touched again is restored before the batch updates it.  Value = every enabled layer's chunk, in layer order.
+  std::unordered_map<unsigned long long, std::vector<char>> store;
+  size_t store_layer_offset[OHMB200_LAYER_COUNT] = {};
+  size_t store_chunk_bytes = 0;
+  uint64_t regions_bound = 0;  // upper bound of the resident regions, without asking the device
+  uint32_t region_reserve = 0; // free slots a batch may need (ohmb200_set_region_reserve)
+  uint64_t evicted = 0, paged_in = 0;
   // profiling
   bool profiling = false;
   std::vector<cudaEvent_t> event_pool;
@@ -1074,6 +1121,9 @@ int deviceAlloc(T *&ptr, size_t count)
   return OHMB200_OK;
 }
 
+int pageInNewRegions(ohmb200_map *m);
+int ensureRoom(ohmb200_map *m);
+
 int ensureScratch(ohmb200_map *m, size_t n)
 {
   if (n <= m->scratch_rays)
@@ -1209,7 +1259,7 @@ int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_i
   const unsigned blocks = (unsigned)((n + threads - 1) / threads);
   const bool has_samples = m->mode != OHMB200_MODE_TSDF;
 
-  if (m->use_graphs && !m->capturing && m->algo == 1 && has_samples && !m->profiling)
+  if (m->use_graphs && !m->capturing && m->algo == 1 && has_samples && !m->profiling && m->store.empty())
   {
     for (auto &g : m->graphs)
     {
@@ -1318,6 +1368,15 @@ int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_i
     {
       KernelScope scope(m, kKPrepSegments);
       prepSegments<<<blocks, threads, 0, s>>>(m->dm, m->geom, b);
+    }
+    if (!m->store.empty() && !m->capturing)
+    {
+      // every region of the batch exists now: restore the ones that were evicted before anything updates them
+      rc = pageInNewRegions(m);
+      if (rc)
+      {
+        return rc;
+      }
     }
     {
       KernelScope scope(m, kKPlan);
@@ -1499,7 +1558,7 @@ int findSlots(ohmb200_map *m, const int16_t *keys_xyz, size_t count, std::vector
       {
         break;
       }
-      h = (h + 1 == m->dm.capacity) ? 0 : h + 1;
+      h = (h + 1 == m->dm.capacity) ? 0 : h + 1;  // (walks over tombstones)
     }
     if (!found)
     {
@@ -1510,6 +1569,260 @@ int findSlots(ohmb200_map *m, const int16_t *keys_xyz, size_t count, std::vector
   }
   return OHMB200_OK;
 }
+
+// ---- paging -------------------------------------------------------------------------------------------------
+ClearTable makeClearTable(ohmb200_map *m)
+{
+  ClearTable table{};
+  auto add = [&](void *base, size_t bytes_per_region, uint32_t fill) {
+    if (base)
+    {
+      table.base[table.count] = (uint32_t *)base;
+      table.words[table.count] = (uint32_t)(bytes_per_region / 4);
+      table.fill[table.count] = fill;
+      ++table.count;
+    }
+  };
+  for (int l = 0; l < OHMB200_LAYER_COUNT; ++l)
+  {
+    add(m->layer_slab[l], m->region_layer_bytes[l], l == OHMB200_LAYER_OCCUPANCY ? 0x7f800000u : 0u);  // +inf
+  }
+  const size_t bit_bytes = sizeof(uint32_t) * ((m->geom.vpr + 31u) / 32u);
+  add(m->dm.voxel_bits, bit_bytes, 0u);
+  add(m->tsdf_near, bit_bytes, 0u);
+  add(m->dm.pending, sizeof(uint32_t) * m->geom.vpr, 0u);
+  return table;
+}
+
+int ensureGather(ohmb200_map *m, size_t bytes, size_t slots)
+{
+  if (bytes > m->gather_bytes)
+  {
+    cudaFree(m->d_gather);
+    m->gather_bytes = 0;
+    CUDA_TRY(cudaMalloc(&m->d_gather, bytes));
+    m->gather_bytes = bytes;
+  }
+  if (slots > m->gather_slots_cap)
+  {
+    cudaFree(m->d_gather_slots);
+    m->gather_slots_cap = 0;
+    CUDA_TRY(cudaMalloc(&m->d_gather_slots, sizeof(uint32_t) * slots));
+    m->gather_slots_cap = slots;
+  }
+  return OHMB200_OK;
+}
+
+// Copies the chunks of `layer` of the listed slots to dst (host), chunk after chunk.
+int downloadSlots(ohmb200_map *m, int layer, const uint32_t *slots, size_t count, char *dst, size_t dst_stride)
+{
+  const size_t chunk = m->region_layer_bytes[layer];
+  const size_t piece = std::max<size_t>(1, std::min<size_t>(count, (64u << 20) / chunk));
+  std::vector<char> staging(piece * chunk);
+  for (size_t first = 0; first < count; first += piece)
+  {
+    const size_t n = std::min(piece, count - first);
+    int rc = ensureGather(m, chunk * n, n);
+    if (rc)
+    {
+      return rc;
+    }
+    for (size_t i = 0; i < n; ++i)
+    {
+      CUDA_TRY(cudaMemcpyAsync((char *)m->d_gather + i * chunk, (const char *)m->layer_slab[layer] + (size_t)slots[first + i] * chunk,
+                               chunk, cudaMemcpyDeviceToDevice, m->stream));
+    }
+    CUDA_TRY(cudaMemcpyAsync(staging.data(), m->d_gather, chunk * n, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    for (size_t i = 0; i < n; ++i)
+    {
+      memcpy(dst + (first + i) * dst_stride, staging.data() + i * chunk, chunk);
+    }
+  }
+  return OHMB200_OK;
+}
+
+// Frees at least `need` slots of the region table: the least recently walked regions go to the host store
+// (GpuLayerCache evicts its oldest entry the same way, GpuLayerCache.cpp:536-600).  Waits for the queued work.
+int makeRoom(ohmb200_map *m, size_t need)
+{
+  CUDA_TRY(cudaStreamSynchronize(m->copy_stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  const uint32_t capacity = m->dm.capacity;
+  std::vector<unsigned long long> keys(capacity);
+  std::vector<uint32_t> stamps(capacity);
+  CUDA_TRY(cudaMemcpy(keys.data(), m->dm.keys, sizeof(unsigned long long) * capacity, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(stamps.data(), m->dm.region_stamp, sizeof(uint32_t) * capacity, cudaMemcpyDeviceToHost));
+  std::vector<uint32_t> live;
+  for (uint32_t h = 0; h < capacity; ++h)
+  {
+    if (isRegionKey(keys[h]))
+    {
+      live.push_back(h);
+    }
+  }
+  const size_t free_slots = capacity - live.size();
+  PAGING_TRACE("makeRoom: need %zu, live %zu of %u", need, live.size(), capacity);
+  if (free_slots >= need)
+  {
+    m->regions_bound = live.size();
+    return OHMB200_OK;
+  }
+  // oldest first; a little more than asked so that the next batches do not come straight back
+  std::sort(live.begin(), live.end(), [&](uint32_t a, uint32_t b) { return stamps[a] != stamps[b] ? stamps[a] < stamps[b] : a < b; });
+  const size_t count = std::min(live.size(), need - free_slots + capacity / 8u);
+  std::vector<uint32_t> victims(live.begin(), live.begin() + count);
+  PAGING_TRACE("makeRoom: evicting %zu regions, chunk %zu bytes", count, m->store_chunk_bytes);
+  std::vector<std::vector<char> *> chunks(count);
+  for (size_t i = 0; i < count; ++i)
+  {
+    std::vector<char> &chunk = m->store[keys[victims[i]]];
+    chunk.resize(m->store_chunk_bytes);
+    chunks[i] = &chunk;
+  }
+  for (int l = 0; l < OHMB200_LAYER_COUNT; ++l)
+  {
+    if (!m->layer_slab[l])
+    {
+      continue;
+    }
+    // gather the layer of all victims, then hand each region its piece
+    std::vector<char> layer_data(count * m->region_layer_bytes[l]);
+    int rc = downloadSlots(m, l, victims.data(), count, layer_data.data(), m->region_layer_bytes[l]);
+    if (rc)
+    {
+      return rc;
+    }
+    for (size_t i = 0; i < count; ++i)
+    {
+      memcpy(chunks[i]->data() + m->store_layer_offset[l], layer_data.data() + i * m->region_layer_bytes[l], m->region_layer_bytes[l]);
+    }
+  }
+  int rc = ensureGather(m, 16, count);
+  if (rc)
+  {
+    return rc;
+  }
+  CUDA_TRY(cudaMemcpyAsync(m->d_gather_slots, victims.data(), sizeof(uint32_t) * count, cudaMemcpyHostToDevice, m->stream));
+  const ClearTable clear_table = makeClearTable(m);
+  const unsigned clear_grid = (unsigned)std::min<size_t>(count, (size_t)m->sm_count * 16u);
+  clearEvictedSlots<<<clear_grid, 256, 0, m->stream>>>(m->dm, clear_table, m->d_gather_slots, (uint32_t)count);
+  CUDA_TRY(cudaGetLastError());
+  // The new key table: victims become tombstones; a tombstone followed by an empty slot ends no probe sequence and
+  // becomes empty itself (backwards, twice for the wrap-around).
+  for (uint32_t v : victims)
+  {
+    keys[v] = kTombKey;
+  }
+  for (int pass = 0; pass < 2; ++pass)
+  {
+    for (uint32_t h = capacity; h-- > 0;)
+    {
+      if (keys[h] == kTombKey && keys[(h + 1 == capacity) ? 0 : h + 1] == kEmptyKey)
+      {
+        keys[h] = kEmptyKey;
+      }
+    }
+  }
+  CUDA_TRY(cudaMemcpyAsync(m->dm.keys, keys.data(), sizeof(unsigned long long) * capacity, cudaMemcpyHostToDevice, m->stream));
+  const unsigned long long resident = live.size() - count;
+  CUDA_TRY(cudaMemcpyAsync(&m->d_counters->region_count, &resident, sizeof(resident), cudaMemcpyHostToDevice, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  m->evicted += count;
+  m->regions_bound = resident;
+  PAGING_TRACE("makeRoom: done, %llu resident, %zu stored", resident, m->store.size());
+  return OHMB200_OK;
+}
+
+// Restores the chunks of `key` (in the host store) into `slot` and forgets the stored copy.
+int pageIn(ohmb200_map *m, unsigned long long key, uint32_t slot)
+{
+  auto it = m->store.find(key);
+  if (it == m->store.end())
+  {
+    return OHMB200_OK;
+  }
+  PAGING_TRACE("pageIn: key %llx -> slot %u", key, slot);
+  for (int l = 0; l < OHMB200_LAYER_COUNT; ++l)
+  {
+    if (m->layer_slab[l])
+    {
+      CUDA_TRY(cudaMemcpyAsync((char *)m->layer_slab[l] + (size_t)slot * m->region_layer_bytes[l],
+                               it->second.data() + m->store_layer_offset[l], m->region_layer_bytes[l], cudaMemcpyHostToDevice,
+                               m->stream));
+    }
+  }
+  if (m->dm.voxel_bits)
+  {
+    recomputeVoxelBits<<<1, 256, 0, m->stream>>>(m->dm, m->geom, m->mp, m->mode == OHMB200_MODE_TSDF, slot);
+  }
+  CUDA_TRY(cudaStreamSynchronize(m->stream));  // the stored copy is pageable memory: gone only after the copies
+  m->store.erase(it);
+  ++m->paged_in;
+  return OHMB200_OK;
+}
+
+// After the region discovery of a batch (prepRays, prepSegments): the regions it created that have a stored copy.
+int pageInNewRegions(ohmb200_map *m)
+{
+  uint32_t count = 0;
+  CUDA_TRY(cudaMemcpyAsync(&count, &m->d_counters->new_count, sizeof(count), cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  count = std::min(count, m->dm.capacity);
+  PAGING_TRACE("pageInNewRegions: %u new regions, %zu stored", count, m->store.size());
+  if (count == 0)
+  {
+    return OHMB200_OK;
+  }
+  std::vector<uint32_t> slots(count);
+  std::vector<unsigned long long> keys(m->dm.capacity);
+  CUDA_TRY(cudaMemcpyAsync(slots.data(), m->dm.new_slots, sizeof(uint32_t) * count, cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaMemcpyAsync(keys.data(), m->dm.keys, sizeof(unsigned long long) * keys.size(), cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  for (uint32_t slot : slots)
+  {
+    if (slot < m->dm.capacity && isRegionKey(keys[slot]))
+    {
+      int rc = pageIn(m, keys[slot], slot);
+      if (rc)
+      {
+        return rc;
+      }
+    }
+  }
+  return OHMB200_OK;
+}
+
+// Before a batch is queued: make sure the table has room for the regions it may create.  The resident count is only
+// asked of the device (a wait) when the pessimistic bound — every batch so far used its whole reserve — says the
+// table could be full.
+int ensureRoom(ohmb200_map *m)
+{
+  if (m->algo != 1)
+  {
+    return OHMB200_OK;  // the per-ray fallback path updates regions while it discovers them: no paging there
+  }
+  const uint64_t reserve = m->region_reserve;
+  PAGING_TRACE("ensureRoom: bound %llu + reserve %llu, capacity %u", (unsigned long long)m->regions_bound, (unsigned long long)reserve, m->dm.capacity);
+  m->regions_bound += reserve;
+  if (m->regions_bound <= m->dm.capacity)
+  {
+    return OHMB200_OK;
+  }
+  int rc = pullCounters(m);
+  if (rc)
+  {
+    return rc;
+  }
+  m->regions_bound = m->h_counters->region_count + reserve;
+  if (m->regions_bound > m->dm.capacity)
+  {
+    rc = makeRoom(m, reserve);
+    m->regions_bound += reserve;
+  }
+  return rc;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1733,6 +2046,7 @@ ohmb200_map *ohmb200_create(const ohmb200_params *params, int mode, size_t devic
   const size_t voxels = capacity * m->geom.vpr;
   ok = ok && cudaMalloc(&m->dm.keys, sizeof(unsigned long long) * capacity) == cudaSuccess;
   ok = ok && cudaMalloc(&m->dm.region_stamp, sizeof(uint32_t) * capacity) == cudaSuccess;
+  ok = ok && cudaMalloc(&m->dm.new_slots, sizeof(uint32_t) * capacity) == cudaSuccess;
   if (m->algo == 0)
   {
     ok = ok && cudaMalloc(&m->dm.pending, sizeof(uint32_t) * voxels) == cudaSuccess;
@@ -1783,6 +2097,14 @@ ohmb200_map *ohmb200_create(const ohmb200_params *params, int mode, size_t devic
   m->dm.secondary = (uint2 *)m->layer_slab[OHMB200_LAYER_SECONDARY];
   m->dm.region_count = &m->d_counters->region_count;
   m->dm.table_full = &m->d_counters->table_full;
+  m->dm.new_count = &m->d_counters->new_count;
+  for (int l = 0; l < OHMB200_LAYER_COUNT; ++l)
+  {
+    m->store_layer_offset[l] = m->store_chunk_bytes;
+    m->store_chunk_bytes += m->layer_slab[l] ? m->region_layer_bytes[l] : 0;
+  }
+  // free slots a batch may need: half of a small table, 4096 of a large one (a 64x2048 sweep at 0.1 m creates ~1000)
+  m->region_reserve = std::min<uint32_t>(4096u, std::max<uint32_t>(1u, m->dm.capacity / 2u));
   m->dm.part_rank = 0;
   m->dm.part_world = 1;
   if (initialiseSlabs(m) != OHMB200_OK || cudaStreamSynchronize(m->stream) != cudaSuccess)
@@ -1803,7 +2125,7 @@ void ohmb200_destroy(ohmb200_map *m)
   cudaDeviceSynchronize();
   dropBatchGraphs(m);
   Batch &b = m->batch;
-  void *to_free[] = { m->dm.keys,       m->dm.region_stamp, m->dm.pending,      b.touched_list,   m->d_counters,
+  void *to_free[] = { m->dm.keys,       m->dm.region_stamp, m->dm.new_slots,    m->dm.pending,      b.touched_list,   m->d_counters,
                       b.keys_in,        b.keys_out,         b.vals_in,          b.vals_out,       b.run_list,
                       b.run_head,       b.interval_count,   b.interval_offset,  b.sorted_rays,   b.record_ray,     b.record_next,
                       b.last_exit,      m->cub_temp,        m->d_rays[0],       m->d_rays[1],     m->d_intensities[0],
@@ -1948,7 +2270,7 @@ size_t ohmb200_integrate_device(ohmb200_map *m, const double *d_rays, size_t ele
     }
     m->first_ray_time = t0;
   }
-  if (launchBatch(m, d_rays, element_count / 2, d_intensities, d_timestamps, ray_flags) != OHMB200_OK)
+  if (ensureRoom(m) != OHMB200_OK || launchBatch(m, d_rays, element_count / 2, d_intensities, d_timestamps, ray_flags) != OHMB200_OK)
   {
     return 0;
   }
@@ -2019,7 +2341,8 @@ size_t ohmb200_integrate(ohmb200_map *m, const double *rays, size_t element_coun
     setError(OHMB200_E_CUDA, "ray upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     return 0;
   }
-  const int rc = launchBatch(m, m->d_rays[buf], n, intensities ? m->d_intensities[buf] : nullptr,
+  int rc = ensureRoom(m);
+  rc = rc ? rc : launchBatch(m, m->d_rays[buf], n, intensities ? m->d_intensities[buf] : nullptr,
                              timestamps ? m->d_timestamps[buf] : nullptr, ray_flags);
   cudaEventRecord(m->in_free[buf], m->stream);
   // The caller's arrays are only guaranteed to be read during the call (GpuMap.cpp:843-862).
@@ -2057,7 +2380,7 @@ size_t ohmb200_region_count(ohmb200_map *m)
   {
     return 0;
   }
-  return (size_t)m->h_counters->region_count;
+  return (size_t)m->h_counters->region_count + m->store.size();
 }
 
 size_t ohmb200_enumerate_regions(ohmb200_map *m, int16_t *keys_xyz, size_t capacity)
@@ -2082,10 +2405,15 @@ size_t ohmb200_enumerate_regions(ohmb200_map *m, int16_t *keys_xyz, size_t capac
   std::vector<R> regions;
   for (unsigned long long k : table)
   {
-    if (k != kEmptyKey)
+    if (isRegionKey(k))
     {
       regions.push_back({ (int16_t)(k & 0xffff), (int16_t)((k >> 16) & 0xffff), (int16_t)((k >> 32) & 0xffff) });
     }
+  }
+  for (const auto &kv : m->store)
+  {
+    const unsigned long long k = kv.first;
+    regions.push_back({ (int16_t)(k & 0xffff), (int16_t)((k >> 16) & 0xffff), (int16_t)((k >> 32) & 0xffff) });
   }
   std::sort(regions.begin(), regions.end(), [](const R &a, const R &b) {
     if (a.z != b.z)
@@ -2132,6 +2460,28 @@ int ohmb200_read_regions(ohmb200_map *m, int layer, const int16_t *keys_xyz, siz
     return OHMB200_OK;
   }
   cudaSetDevice(m->device);
+  if (!m->store.empty())
+  {
+    // some regions live in the host store (paging): those are copied from there, the others read one by one
+    for (size_t i = 0; i < count; ++i)
+    {
+      const int16_t *k = keys_xyz + 3 * i;
+      const auto it = m->store.find(packRegion(k[0], k[1], k[2]));
+      if (it != m->store.end())
+      {
+        memcpy((char *)dst + i * chunk, it->second.data() + m->store_layer_offset[layer], chunk);
+        continue;
+      }
+      std::vector<uint32_t> slot;
+      int rc1 = findSlots(m, k, 1, slot);
+      rc1 = rc1 ? rc1 : downloadSlots(m, layer, slot.data(), 1, (char *)dst + i * chunk, chunk);
+      if (rc1)
+      {
+        return rc1;
+      }
+    }
+    return OHMB200_OK;
+  }
   std::vector<uint32_t> slots;
   int rc = findSlots(m, keys_xyz, count, slots);
   if (rc)
@@ -2191,7 +2541,7 @@ size_t ohmb200_integrate_secondary_device(ohmb200_map *m, const double *d_rays, 
   }
   cudaSetDevice(m->device);
   const size_t n = element_count / 2;
-  if (ensureScratch(m, n) != OHMB200_OK)
+  if (ensureScratch(m, n) != OHMB200_OK || ensureRoom(m) != OHMB200_OK)
   {
     return 0;
   }
@@ -2218,6 +2568,10 @@ size_t ohmb200_integrate_secondary_device(ohmb200_map *m, const double *d_rays, 
   {
     KernelScope scope(m, kKPrepRays);
     prepSecondary<<<blocks, 128, 0, s>>>(m->dm, m->geom, b, m->d_secondary_ranges);
+  }
+  if (!m->store.empty() && pageInNewRegions(m) != OHMB200_OK)  // the sample regions exist now; none is updated yet
+  {
+    return 0;
   }
   {
     KernelScope scope(m, kKSort);
@@ -2426,6 +2780,10 @@ int ohmb200_read_regions_async(ohmb200_map *m, int layer, const int16_t *keys_xy
   {
     return setError(OHMB200_E_INVALID, "asynchronous download needs 16-byte multiple chunks");
   }
+  if (!m->store.empty())
+  {
+    return ohmb200_read_regions(m, layer, keys_xyz, count, dst, bytes);  // part of the map is in the host store
+  }
   if (count == 0)
   {
     return OHMB200_OK;
@@ -2536,6 +2894,14 @@ int ohmb200_write_region(ohmb200_map *m, const int16_t key_xyz[3], int layer, co
   cudaSetDevice(m->device);
   const unsigned long long key = (unsigned long long)(uint16_t)key_xyz[0] | ((unsigned long long)(uint16_t)key_xyz[1] << 16) |
                                  ((unsigned long long)(uint16_t)key_xyz[2] << 32);
+  if (pullCounters(m) == OHMB200_OK && m->h_counters->region_count >= m->dm.capacity && m->algo == 1)
+  {
+    int rc_room = makeRoom(m, 1);
+    if (rc_room)
+    {
+      return rc_room;
+    }
+  }
   int *d_slot = (int *)&m->d_counters->record_count;  // scratch word, reset before every batch
   insertRegion<<<1, 1, 0, m->stream>>>(m->dm, key, d_slot);
   int slot = -1;
@@ -2544,6 +2910,11 @@ int ohmb200_write_region(ohmb200_map *m, const int16_t key_xyz[3], int layer, co
   if (slot < 0)
   {
     return setError(OHMB200_E_CACHE_FULL, "region table full");
+  }
+  int rc_page = pageIn(m, key, (uint32_t)slot);  // its other layers, if the region was evicted
+  if (rc_page)
+  {
+    return rc_page;
   }
   CUDA_TRY(cudaMemcpyAsync((char *)m->layer_slab[layer] + (size_t)slot * chunk, src, chunk, cudaMemcpyHostToDevice,
                            m->stream));
@@ -2563,24 +2934,9 @@ int ohmb200_clear(ohmb200_map *m)
   }
   cudaSetDevice(m->device);
   CUDA_TRY(cudaStreamSynchronize(m->copy_stream));
-  ClearTable table{};
-  auto add = [&](void *base, size_t bytes_per_region, uint32_t fill) {
-    if (base)
-    {
-      table.base[table.count] = (uint32_t *)base;
-      table.words[table.count] = (uint32_t)(bytes_per_region / 4);
-      table.fill[table.count] = fill;
-      ++table.count;
-    }
-  };
-  for (int l = 0; l < OHMB200_LAYER_COUNT; ++l)
-  {
-    add(m->layer_slab[l], m->region_layer_bytes[l], l == OHMB200_LAYER_OCCUPANCY ? 0x7f800000u : 0u);  // +inf
-  }
-  const size_t bit_bytes = sizeof(uint32_t) * ((m->geom.vpr + 31u) / 32u);
-  add(m->dm.voxel_bits, bit_bytes, 0u);
-  add(m->tsdf_near, bit_bytes, 0u);
-  add(m->dm.pending, sizeof(uint32_t) * m->geom.vpr, 0u);
+  const ClearTable table = makeClearTable(m);
+  m->store.clear();
+  m->regions_bound = 0;
   clearLiveRegions<<<std::min<unsigned>(m->dm.capacity, (unsigned)m->sm_count * 16u), 256, 0, m->stream>>>(m->dm, table);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemsetAsync(m->d_counters, 0, sizeof(Counters), m->stream));
@@ -2620,10 +2976,51 @@ int ohmb200_get_stats(ohmb200_map *m, ohmb200_stats *stats)
   stats->voxel_visits = m->h_counters->voxel_visits;
   stats->sample_updates = m->h_counters->sample_updates;
   stats->ordered_records = m->h_counters->ordered_records;
-  stats->regions = m->h_counters->region_count;
+  stats->regions = m->h_counters->region_count + m->store.size();
   stats->region_capacity = m->dm.capacity;
   stats->batches = m->batches;
   stats->kernel_launches = m->launches;
+  return OHMB200_OK;
+}
+
+int ohmb200_set_region_reserve(ohmb200_map *m, uint32_t free_slots)
+{
+  if (!m || free_slots == 0 || free_slots > m->dm.capacity)
+  {
+    return setError(OHMB200_E_INVALID, "ohmb200_set_region_reserve: 1 .. region capacity");
+  }
+  m->region_reserve = free_slots;
+  return OHMB200_OK;
+}
+
+int ohmb200_paging_stats(ohmb200_map *m, uint64_t *resident, uint64_t *stored, uint64_t *evicted, uint64_t *paged_in)
+{
+  if (!m)
+  {
+    return setError(OHMB200_E_INVALID, "null map");
+  }
+  cudaSetDevice(m->device);
+  int rc = pullCounters(m);
+  if (rc)
+  {
+    return rc;
+  }
+  if (resident)
+  {
+    *resident = m->h_counters->region_count;
+  }
+  if (stored)
+  {
+    *stored = m->store.size();
+  }
+  if (evicted)
+  {
+    *evicted = m->evicted;
+  }
+  if (paged_in)
+  {
+    *paged_in = m->paged_in;
+  }
   return OHMB200_OK;
 }
 

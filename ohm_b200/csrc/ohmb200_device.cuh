@@ -23,6 +23,13 @@
 namespace ohmb200
 {
 constexpr uint64_t kEmptyKey = ~0ull;
+// A slot whose region was evicted to the host store (GpuLayerCache's eviction, ohmgpu/GpuLayerCache.cpp:429-633):
+// probes walk over it, an insert may take it.
+constexpr uint64_t kTombKey = ~0ull - 1ull;
+OHMB200_HD __forceinline__ bool isRegionKey(unsigned long long k)
+{
+  return k < kTombKey;
+}
 constexpr uint32_t kHitFlag = 0x80000000u;   // pending word: voxel has sample updates in this batch
 constexpr uint32_t kInvalidVoxel = 0xFFFFFFFFu;
 
@@ -74,6 +81,8 @@ struct DeviceMap
   uint32_t *voxel_bits;      // [capacity][(vpr + 31) / 32] persistent bit per voxel (NDT / TSDF maps), else nullptr
   unsigned long long *region_count;  // device counter of occupied slots
   int *table_full;                   // set when an insert found no free slot
+  uint32_t *new_slots;               // slots of the regions inserted since new_count was reset (paging), or nullptr
+  uint32_t *new_count;
   int part_rank;                     // this GPU's index among `part_world` region owners (multi-GPU sharding)
   int part_world;                    // 1 = the map owns every region
 };
@@ -112,31 +121,74 @@ __device__ __forceinline__ bool ownsRegion(const DeviceMap &m, const int r[3])
   return m.part_world <= 1 || regionOwner(r[0], r[1], r[2], m.part_world) == m.part_rank;
 }
 
-// Find or insert a region; returns its slot, or -1 when the table is full.
+// Find or insert a region; returns its slot, or -1 when the table is full.  Open addressing, linear probing; the slot
+// of an evicted region (kTombKey) is taken by the first insert whose probe sequence passes it and ends on an empty
+// slot — every inserter of one key picks its slot by the same rule from the same table, so two of them meet on the
+// same compare-and-swap; the loser of any CAS simply probes again.
 __device__ inline int regionSlot(const DeviceMap &m, unsigned long long key)
 {
-  uint32_t h = hashRegion(key) % m.capacity;
-  for (uint32_t probe = 0; probe < m.capacity; ++probe)
+  for (int attempt = 0; attempt < 64; ++attempt)
   {
-    unsigned long long k = m.keys[h];
-    if (k == key)
+    uint32_t h = hashRegion(key) % m.capacity;
+    int tomb = -1;
+    bool retry = false;
+    for (uint32_t probe = 0; probe < m.capacity; ++probe)
     {
-      return (int)h;
-    }
-    if (k == kEmptyKey)
-    {
-      const unsigned long long old = atomicCAS(&m.keys[h], kEmptyKey, key);
-      if (old == kEmptyKey)
-      {
-        atomicAdd(m.region_count, 1ull);
-        return (int)h;
-      }
-      if (old == key)
+      const unsigned long long k = m.keys[h];
+      if (k == key)
       {
         return (int)h;
       }
+      if (k == kTombKey && tomb < 0)
+      {
+        tomb = (int)h;
+      }
+      if (k == kEmptyKey)
+      {
+        const uint32_t target = tomb >= 0 ? (uint32_t)tomb : h;
+        const unsigned long long expected = tomb >= 0 ? kTombKey : kEmptyKey;
+        const unsigned long long old = atomicCAS(&m.keys[target], expected, key);
+        if (old == expected)
+        {
+          atomicAdd(m.region_count, 1ull);
+          if (m.new_slots)
+          {
+            m.new_slots[atomicAdd(m.new_count, 1u)] = target;
+          }
+          return (int)target;
+        }
+        if (old == key)
+        {
+          return (int)target;
+        }
+        retry = true;  // somebody else took the slot for another region
+        break;
+      }
+      h = (h + 1 == m.capacity) ? 0 : h + 1;
     }
-    h = (h + 1 == m.capacity) ? 0 : h + 1;
+    if (!retry)
+    {
+      if (tomb >= 0)
+      {
+        // no empty slot on the way, but a free one: take it (the probe went all the way round, the key is absent)
+        const unsigned long long old = atomicCAS(&m.keys[tomb], kTombKey, key);
+        if (old == kTombKey)
+        {
+          atomicAdd(m.region_count, 1ull);
+          if (m.new_slots)
+          {
+            m.new_slots[atomicAdd(m.new_count, 1u)] = (uint32_t)tomb;
+          }
+          return tomb;
+        }
+        if (old == key)
+        {
+          return tomb;
+        }
+        continue;
+      }
+      break;
+    }
   }
   *m.table_full = 1;
   return -1;

@@ -89,6 +89,10 @@ __global__ void __launch_bounds__(128) prepRays(DeviceMap dm, Geom g, MapParams 
         if (slot >= 0)
         {
           vid = (uint32_t)slot * g.vpr + voxelIndex(g, ekey);
+          if (__ldcg(&dm.region_stamp[slot]) != b.stamp)
+          {
+            dm.region_stamp[slot] = b.stamp;  // sampled by this batch: the age paging evicts by
+          }
         }
       }
       unsigned walk_flags = 0;
@@ -234,6 +238,7 @@ __global__ void __launch_bounds__(1024) planRegions(DeviceMap dm, Batch b, uint3
     if (t < touched)
     {
       b.seg_offset[slot] = carry + offset;
+      dm.region_stamp[slot] = b.stamp;  // walked by this batch: the age paging evicts by
     }
     __syncthreads();
     if (threadIdx.x == 0)

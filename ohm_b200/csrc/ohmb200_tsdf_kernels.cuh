@@ -434,7 +434,7 @@ __global__ void clearTouchedBits(Batch b, uint32_t *bits, uint32_t words_per_reg
 __global__ void recomputeVoxelBits(DeviceMap dm, Geom g, MapParams mp, int tsdf_mode, uint32_t first)
 {
   const uint32_t slot = first + blockIdx.x;
-  if (slot >= dm.capacity || dm.keys[slot] == kEmptyKey)
+  if (slot >= dm.capacity || !isRegionKey(dm.keys[slot]))
   {
     return;
   }

@@ -294,6 +294,17 @@ class GpuMap:
         self._check(self.L.ohmb200_get_stats(self.h, C.byref(s)))
         return {k: int(getattr(s, k)) for k, _ in Stats._fields_}
 
+    # -- paging (GpuLayerCache) -----------------------------------------------------------------------------
+    def set_region_reserve(self, free_slots):
+        """Free region slots guaranteed before every batch (include/ohmb200.h: ohmb200_set_region_reserve)."""
+        self._check(self.L.ohmb200_set_region_reserve(self.h, int(free_slots)))
+
+    def paging_stats(self):
+        """{resident, stored, evicted, paged_in}: regions in device memory / in the host store, totals so far."""
+        v = [C.c_uint64() for _ in range(4)]
+        self._check(self.L.ohmb200_paging_stats(self.h, *[C.byref(x) for x in v]))
+        return dict(zip(("resident", "stored", "evicted", "paged_in"), (int(x.value) for x in v)))
+
     # -- multi-GPU sharding ----------------------------------------------------------------------------------
     def set_partition(self, rank, world):
         """Keep only the regions owned by `rank` of `world` GPUs (include/ohmb200.h: ohmb200_set_partition)."""
