@@ -208,8 +208,12 @@ def run_gpu(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
     torch.cuda.set_device(local_rank)
+    # stdout carries the one JSON line and nothing else: whatever a library prints there (NCCL's version banner, for
+    # one) is sent to stderr from here on; the line itself is written to the saved descriptor.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     # One sweep per rank: the step's batch is the concatenation of the N sweeps, in sweep order.
@@ -423,7 +427,8 @@ def run_gpu(args):
         }
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     gpu.close()
     if world > 1:
         dist.destroy_process_group()

@@ -951,6 +951,13 @@ struct ohmb200_map
   size_t store_layer_offset[OHMB200_LAYER_COUNT] = {};
   size_t store_chunk_bytes = 0;
   uint64_t regions_bound = 0;  // upper bound of the resident regions, without asking the device
+  // ... kept tight by a copy of the device's region counter queued behind every batch and read once it has landed
+  unsigned long long *h_region_snap = nullptr;  // pinned
+  cudaEvent_t snap_event = nullptr;
+  bool snap_pending = false;
+  uint64_t snap_batch = 0;     // batches queued when the pending snapshot was taken
+  uint64_t known_regions = 0;  // the last snapshot that landed, and the batch count it belongs to
+  uint64_t known_batch = 0;
   uint32_t region_reserve = 0; // free slots a batch may need (ohmb200_set_region_reserve)
   uint64_t evicted = 0, paged_in = 0;
   // profiling
@@ -1803,24 +1810,51 @@ int ensureRoom(ohmb200_map *m)
     return OHMB200_OK;  // the per-ray fallback path updates regions while it discovers them: no paging there
   }
   const uint64_t reserve = m->region_reserve;
-  PAGING_TRACE("ensureRoom: bound %llu + reserve %llu, capacity %u", (unsigned long long)m->regions_bound, (unsigned long long)reserve, m->dm.capacity);
-  m->regions_bound += reserve;
+  if (m->snap_pending && cudaEventQuery(m->snap_event) == cudaSuccess)
+  {
+    m->known_regions = *m->h_region_snap;
+    m->known_batch = m->snap_batch;
+    m->snap_pending = false;
+  }
+  // every batch since the last known count may have used its whole reserve, and so may this one
+  m->regions_bound = m->known_regions + reserve * (m->batches - m->known_batch + 1);
+  PAGING_TRACE("ensureRoom: %llu regions after batch %llu, now batch %llu, reserve %llu, capacity %u",
+               (unsigned long long)m->known_regions, (unsigned long long)m->known_batch, (unsigned long long)m->batches,
+               (unsigned long long)reserve, m->dm.capacity);
   if (m->regions_bound <= m->dm.capacity)
   {
     return OHMB200_OK;
   }
-  int rc = pullCounters(m);
+  int rc = pullCounters(m);  // waits for the queued batches
   if (rc)
   {
     return rc;
   }
-  m->regions_bound = m->h_counters->region_count + reserve;
-  if (m->regions_bound > m->dm.capacity)
+  m->known_regions = m->h_counters->region_count;
+  m->known_batch = m->batches;
+  m->snap_pending = false;
+  if (m->known_regions + reserve > m->dm.capacity)
   {
     rc = makeRoom(m, reserve);
-    m->regions_bound += reserve;
+    m->known_regions = m->regions_bound;  // makeRoom leaves the resident count there
   }
   return rc;
+}
+
+// Behind a batch: a copy of the region counter for ensureRoom (no wait, read when it has landed).
+void snapshotRegionCount(ohmb200_map *m)
+{
+  if (m->algo != 1 || m->snap_pending || !m->h_region_snap)
+  {
+    return;
+  }
+  if (cudaMemcpyAsync(m->h_region_snap, &m->d_counters->region_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                      m->stream) == cudaSuccess &&
+      cudaEventRecord(m->snap_event, m->stream) == cudaSuccess)
+  {
+    m->snap_pending = true;
+    m->snap_batch = m->batches;
+  }
 }
 
 }  // namespace
@@ -2103,6 +2137,8 @@ ohmb200_map *ohmb200_create(const ohmb200_params *params, int mode, size_t devic
     m->store_layer_offset[l] = m->store_chunk_bytes;
     m->store_chunk_bytes += m->layer_slab[l] ? m->region_layer_bytes[l] : 0;
   }
+  cudaMallocHost(&m->h_region_snap, sizeof(unsigned long long));
+  cudaEventCreateWithFlags(&m->snap_event, cudaEventDisableTiming);
   // free slots a batch may need: half of a small table, 4096 of a large one (a 64x2048 sweep at 0.1 m creates ~1000)
   m->region_reserve = std::min<uint32_t>(4096u, std::max<uint32_t>(1u, m->dm.capacity / 2u));
   m->dm.part_rank = 0;
@@ -2150,6 +2186,11 @@ void ohmb200_destroy(ohmb200_map *m)
   if (m->h_counters)
   {
     cudaFreeHost(m->h_counters);
+    cudaFreeHost(m->h_region_snap);
+    if (m->snap_event)
+    {
+      cudaEventDestroy(m->snap_event);
+    }
   }
   for (cudaEvent_t e : m->event_pool)
   {
@@ -2274,6 +2315,7 @@ size_t ohmb200_integrate_device(ohmb200_map *m, const double *d_rays, size_t ele
   {
     return 0;
   }
+  snapshotRegionCount(m);
   return element_count;
 }
 
@@ -2345,6 +2387,7 @@ size_t ohmb200_integrate(ohmb200_map *m, const double *rays, size_t element_coun
   rc = rc ? rc : launchBatch(m, m->d_rays[buf], n, intensities ? m->d_intensities[buf] : nullptr,
                              timestamps ? m->d_timestamps[buf] : nullptr, ray_flags);
   cudaEventRecord(m->in_free[buf], m->stream);
+  snapshotRegionCount(m);
   // The caller's arrays are only guaranteed to be read during the call (GpuMap.cpp:843-862).
   cudaEventSynchronize(m->in_ready[buf]);
   return rc == OHMB200_OK ? element_count : 0;
@@ -2911,6 +2954,7 @@ int ohmb200_write_region(ohmb200_map *m, const int16_t key_xyz[3], int layer, co
   {
     return setError(OHMB200_E_CACHE_FULL, "region table full");
   }
+  ++m->known_regions;  // (at most) one more resident region than ensureRoom knows of
   int rc_page = pageIn(m, key, (uint32_t)slot);  // its other layers, if the region was evicted
   if (rc_page)
   {
@@ -2937,6 +2981,9 @@ int ohmb200_clear(ohmb200_map *m)
   const ClearTable table = makeClearTable(m);
   m->store.clear();
   m->regions_bound = 0;
+  m->known_regions = 0;
+  m->known_batch = m->batches;
+  m->snap_pending = false;
   clearLiveRegions<<<std::min<unsigned>(m->dm.capacity, (unsigned)m->sm_count * 16u), 256, 0, m->stream>>>(m->dm, table);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemsetAsync(m->d_counters, 0, sizeof(Counters), m->stream));

@@ -89,10 +89,6 @@ __global__ void __launch_bounds__(128) prepRays(DeviceMap dm, Geom g, MapParams 
         if (slot >= 0)
         {
           vid = (uint32_t)slot * g.vpr + voxelIndex(g, ekey);
-          if (__ldcg(&dm.region_stamp[slot]) != b.stamp)
-          {
-            dm.region_stamp[slot] = b.stamp;  // sampled by this batch: the age paging evicts by
-          }
         }
       }
       unsigned walk_flags = 0;
@@ -591,21 +587,29 @@ __device__ __forceinline__ void foldGroups(const uint32_t *tile, const TileLayou
 // counts(position, counters, cnt[8]) fills the counts to apply and returns whether any is non-zero;
 // apply(voxel &, count) updates one voxel.
 template <int kGroups, typename Voxel, typename Counts, typename Apply>
-__device__ __forceinline__ void foldGroupsSole(const uint32_t *tile, const TileLayout &tl, Voxel *slab, Counts &&counts,
-                                               Apply &&apply)
+__device__ __forceinline__ void foldGroupsSole(const uint32_t *tile, const TileLayout &tl, Voxel *slab, uint32_t *ticket,
+                                               Counts &&counts, Apply &&apply)
 {
   constexpr int kChunks = (int)sizeof(Voxel) * 8 / 16;  // 16-byte chunks per group
   const uint4 *tile4 = reinterpret_cast<const uint4 *>(tile);
   const uint32_t groups = ((uint32_t)tl.dxy * (uint32_t)tl.dz) >> 3;
-  // Round i of warp w takes the block of 32 groups ((w + 5 i) mod warps) of the round's span, not block w every time: the
-  // voxels a batch touches sit in a few bands of y or z of the region, and a fixed assignment leaves a quarter of
-  // the warps with all the work (measured: warps waited 10 k cycles per item at the barrier after the fold).
-  const uint32_t span = kGroups * blockDim.x;
-  uint32_t turn = threadIdx.x;
-  for (uint32_t base = 0; base < groups; base += span, turn += 5u * 32u)
+  // Warps take blocks of 32 x kGroups groups from a ticket counter in shared memory (zeroed before the barrier that
+  // precedes the fold): the voxels a batch touches sit in a few bands of y or z of the region, and a fixed assignment
+  // leaves a quarter of the warps with all the work (measured: the others waited 10 k cycles per item at the barrier).
+  const uint32_t lane = threadIdx.x & 31u;
+  for (;;)
   {
-    turn = (turn >= blockDim.x) ? turn - blockDim.x : turn;
-    const uint32_t c0 = base + turn;
+    uint32_t base = 0;
+    if (lane == 0)
+    {
+      base = atomicAdd(ticket, 1u) * (32u * kGroups);
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= groups)
+    {
+      break;
+    }
+    const uint32_t c0 = base + lane;
     uint32_t cnt[kGroups][8];
     bool any[kGroups];
     union
@@ -616,7 +620,7 @@ __device__ __forceinline__ void foldGroupsSole(const uint32_t *tile, const TileL
 #pragma unroll
     for (int u = 0; u < kGroups; ++u)
     {
-      const uint32_t c = c0 + (uint32_t)u * blockDim.x;
+      const uint32_t c = c0 + (uint32_t)u * 32u;
       any[u] = false;
       if (c < groups)
       {
@@ -630,7 +634,7 @@ __device__ __forceinline__ void foldGroupsSole(const uint32_t *tile, const TileL
     {
       if (any[u])
       {
-        const uint4 *src = reinterpret_cast<const uint4 *>(slab + 8u * (c0 + (uint32_t)u * blockDim.x));
+        const uint4 *src = reinterpret_cast<const uint4 *>(slab + 8u * (c0 + (uint32_t)u * 32u));
 #pragma unroll
         for (int k = 0; k < kChunks; ++k)
         {
@@ -648,7 +652,7 @@ __device__ __forceinline__ void foldGroupsSole(const uint32_t *tile, const TileL
         {
           apply(value[u].voxel[k], cnt[u][k]);
         }
-        uint4 *dst = reinterpret_cast<uint4 *>(slab + 8u * (c0 + (uint32_t)u * blockDim.x));
+        uint4 *dst = reinterpret_cast<uint4 *>(slab + 8u * (c0 + (uint32_t)u * 32u));
 #pragma unroll
         for (int k = 0; k < kChunks; ++k)
         {
@@ -677,16 +681,6 @@ __device__ __forceinline__ void foldUnitShared(unsigned long long *unit, unsigne
       return;
     }
     seen = got;
-  }
-}
-
-// Pulls a region's slab of one layer towards the L2 while the work item is walked (the fold reads it afterwards).
-__device__ __forceinline__ void prefetchSlab(const void *slab, size_t bytes)
-{
-  const char *p = static_cast<const char *>(slab);
-  for (size_t at = (size_t)threadIdx.x * 128u; at < bytes; at += (size_t)blockDim.x * 128u)
-  {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + at));
   }
 }
 
@@ -757,7 +751,7 @@ __device__ __forceinline__ void foldLogOdds(float *occ, uint32_t v, uint32_t cou
 // `hit_miss` (NDT-TM; else null) counts every plain miss.  Flagged voxels are replayed with their samples.
 __device__ __forceinline__ void foldLogOddsTile(const uint32_t *tile, const uint32_t *kind, const TileLayout &layout,
                                                 float *occ, uint2 *hit_miss, const MapParams &mp, unsigned ray_flags,
-                                                const MissLadder &ladder, uint32_t shared)
+                                                const MissLadder &ladder, uint32_t *ticket, uint32_t shared)
 {
   const TileLayout tl = foldLayout(layout);
   const auto misses = [&](float v, uint32_t count) { return missRepeatLadder(ladder, v, count, mp, ray_flags); };
@@ -810,7 +804,7 @@ __device__ __forceinline__ void foldLogOddsTile(const uint32_t *tile, const uint
   if (!shared)
   {
     // sole writer of the region's log-odds until this kernel ends
-    foldGroupsSole<2>(tile, tl, occ, counts, [&](float &v, uint32_t count) {
+    foldGroupsSole<2>(tile, tl, occ, ticket, counts, [&](float &v, uint32_t count) {
       bool ok;
       const float after = missLadderLookup(ladder, v, count, ok);
       v = ok ? after : missRepeat(v, count, mp, ray_flags);
@@ -872,6 +866,7 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegions(cons
   __shared__ unsigned long long record_chunk[kWalkThreads / 32];
   __shared__ SegmentQueue queue;
   __shared__ MissLadder ladder;
+  __shared__ uint32_t fold_ticket;  // next block of the fold (foldGroupsSole)
   const uint32_t words = tl.words;
   const uint32_t tile_base = (uint32_t)__cvta_generic_to_shared(tile);
   const uint32_t tid = threadIdx.x;
@@ -932,7 +927,6 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegions(cons
         tile[w] = 0;
       }
     }
-    prefetchSlab(dm.occupancy + (size_t)vbase, sizeof(float) * g.vpr);
     __syncthreads();
     PHASE(1);
     if (has_samples)
@@ -1009,12 +1003,13 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegions(cons
     if (tid == 0)
     {
       loadWorkItem(b, next_work, &items2[parity ^ 1u]);
+      fold_ticket = 0;
     }
     __syncthreads();
     PHASE(4);
 
     // Fold the miss counts into the occupancy slab.  k identical misses commute, so the count is all that matters.
-    foldLogOddsTile(tile, nullptr, tl, dm.occupancy + (size_t)vbase, nullptr, mp, b.ray_flags, ladder, item.shared);
+    foldLogOddsTile(tile, nullptr, tl, dm.occupancy + (size_t)vbase, nullptr, mp, b.ray_flags, ladder, &fold_ticket, item.shared);
 #ifdef OHMB200_PHASE_CLOCKS
     PHASE(5);
     ph[0] += tc[0] - tc[6];
@@ -1189,6 +1184,7 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegionsNdt(c
   __shared__ unsigned long long gauss_chunk[kWalkThreads / 32];
   __shared__ SegmentQueue queue;
   __shared__ MissLadder ladder;
+  __shared__ uint32_t fold_ticket;  // next block of the fold (foldGroupsSole)
   const uint32_t words = tl.words;
   const uint32_t tile_base = (uint32_t)__cvta_generic_to_shared(tile);
   const uint32_t bit_words = (g.vpr + 31u) >> 5;  // the persistent bits of a region, indexed by voxel
@@ -1341,13 +1337,14 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegionsNdt(c
     if (tid == 0)
     {
       loadWorkItem(b, next_work, &items2[parity ^ 1u]);
+      fold_ticket = 0;
     }
     __syncthreads();
 
     // Fold.  Plain voxels: k identical misses (RayMapperNdt applies no exclusion flags).  Gaussian voxels: the
     // adjustments are already in the slab; apply occupancyAdjustDown's clamp.
     foldLogOddsTile(tile, kind, tl, dm.occupancy + (size_t)vbase, dm.hit_miss ? dm.hit_miss + (size_t)vbase : nullptr, mp, 0u,
-                    ladder, item.shared);
+                    ladder, &fold_ticket, item.shared);
   }
 }
 
