@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(128) prepSegments(DeviceMap dm, Geom g, Batch 
   if (i < b.n)
   {
     RayRec rec;
-    loadRec(rec, b.recs + i);
+    loadRec(rec, b.recs + rayOfThread(i, b.n));  // (the staged segments are indexed by thread, emitSegments maps back)
     uint32_t staged = 0;
     if (rec.flags & kRecValid)
     {
@@ -299,6 +299,7 @@ __global__ void __launch_bounds__(128) emitSegments(DeviceMap dm, Geom g, Batch 
     return;
   }
   const uint32_t staged = b.stage_count[i];
+  const uint32_t ray = rayOfThread(i, b.n);
   if (staged <= kStageSegments)
   {
     // Pass B, common case: scatter the segments pass A staged (plane k holds the k-th segment of every ray).
@@ -309,14 +310,14 @@ __global__ void __launch_bounds__(128) emitSegments(DeviceMap dm, Geom g, Batch 
       const uint32_t at = b.seg_offset[slot] + slotAggregatedInc(b.seg_cursor, slot);
       if (at < b.seg_capacity)
       {
-        raw.x = i;
+        raw.x = ray;
         reinterpret_cast<uint4 *>(b.segments)[at] = raw;
       }
     }
     return;
   }
   RayRec rec;
-  loadRec(rec, b.recs + i);
+  loadRec(rec, b.recs + ray);
   enumerateSegments(rec, g, [&](const int r[3], const int st[3], const int entry[3], int n) {
     if (!ownsRegion(dm, r))
     {
@@ -331,7 +332,7 @@ __global__ void __launch_bounds__(128) emitSegments(DeviceMap dm, Geom g, Batch 
     if (at < b.seg_capacity)
     {
       uint4 raw;
-      raw.x = i;
+      raw.x = ray;
       raw.y = (uint32_t)st[0] | ((uint32_t)st[1] << 16);
       raw.z = (uint32_t)st[2] | ((uint32_t)n << 16);
       raw.w = (uint32_t)entry[0] | ((uint32_t)entry[1] << 8) | ((uint32_t)entry[2] << 16);

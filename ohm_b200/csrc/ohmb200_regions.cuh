@@ -120,6 +120,24 @@ struct WorkItem
   uint32_t shared;  // region split over several items: fold with CAS
 };
 
+// The ray a thread of the per-ray segment kernels (prepSegments, emitSegments, markTsdfNear) works on.  Lidar data comes
+// in firing order — the beams of one azimuth, then the next azimuth — so 32 consecutive rays span the whole elevation
+// fan: 4 m rays into the floor next to 40 m rays to the far wall, and a warp of them runs as long as its longest ray
+// with a third of its lanes busy (ncu: 13.7 of 32 in prepSegments).  Inside blocks of 2048 rays the lanes of a warp
+// take rays 64 apart instead — the same beam of neighbouring azimuths for any sensor of up to 64 beams (two beams for
+// 128), rays of nearly equal length.  Everything indexed by THREAD (the staged segments) stays coalesced; the ray
+// records are 64-byte reads either way.  Unordered input loses nothing.
+OHMB200_HD __forceinline__ uint32_t rayOfThread(uint32_t i, uint32_t n)
+{
+  const uint32_t base = i & ~2047u;
+  if (base + 2048u > n)
+  {
+    return i;
+  }
+  const uint32_t j = i & 2047u;
+  return base + (j & 31u) * 64u + (j >> 5);
+}
+
 OHMB200_HD __forceinline__ double stepTime(double initial, double delta, int m)
 {
   return m == 0 ? initial : initial + delta * m;

@@ -94,8 +94,9 @@ __global__ void __launch_bounds__(128) markTsdfNear(const __grid_constant__ Devi
   {
     return;
   }
+  const uint32_t ray = rayOfThread(i, b.n);  // staged segments are indexed by thread (prepSegments)
   RayRec rec;
-  loadRec(rec, b.recs + i);
+  loadRec(rec, b.recs + ray);
   const float far_threshold = tsdfFarThreshold(mp);
   const int near_steps = tsdfNearSteps(mp, g);
   const uint32_t flag_words = (g.vpr + 31u) >> 5;
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(128) markTsdfNear(const __grid_constant__ Devi
   const int steps_total = total[0] + total[1] + total[2];
   const int dx = g.dim[0], dxy = g.dim[0] * g.dim[1];
   TsdfRayGeometry geo;
-  tsdfLoadRay(b, i, geo);
+  tsdfLoadRay(b, ray, geo);
   // returns false when the segment (and so every earlier one) ends too far from the end of the walk
   auto mark_segment = [&](uint32_t slot, const int st[3], int visits) -> bool {
     const int q_entry = st[0] + st[1] + st[2];
