@@ -276,6 +276,9 @@ OHMB200_API int ohmb200_kernel_times(ohmb200_map *map, ohmb200_kernel_time *out,
  * ohmb200_set_region_reserve: free slots to guarantee before every batch (default min(4096, capacity / 2)); a single
  * batch that creates more regions than that can still fill the table (ohmb200_sync -> OHMB200_E_CACHE_FULL). */
 OHMB200_API int ohmb200_set_region_reserve(ohmb200_map *map, uint32_t free_slots);
+/* MapRegionCache::remove (ohm/MapRegionCache.h:52, called by OccupancyMap::cullRegions... OccupancyMap.cpp:678): drops one
+ * region — resident or stored — with all its layers.  OHMB200_E_NOT_FOUND if the map does not hold it. */
+OHMB200_API int ohmb200_remove_region(ohmb200_map *map, const int16_t key_xyz[3]);
 /* resident = regions in device memory, stored = regions in the host store, evicted / paged_in = totals so far. */
 OHMB200_API int ohmb200_paging_stats(ohmb200_map *map, uint64_t *resident, uint64_t *stored, uint64_t *evicted,
                                      uint64_t *paged_in);

@@ -267,6 +267,11 @@ public:
     }
     return s;
   }
+  /// MapRegionCache::remove (ohm/MapRegionCache.h:52)
+  bool removeRegion(const glm::i16vec3 &key)
+  {
+    return map_ && ohmb200_remove_region(map_, reinterpret_cast<const int16_t *>(&key)) == OHMB200_OK;
+  }
   /// Free region slots guaranteed before every batch (the gpu_mem_size counterpart for regions created per batch).
   bool setRegionReserve(uint32_t free_slots) { return map_ && ohmb200_set_region_reserve(map_, free_slots) == OHMB200_OK; }
   /// GpuCache::clear + OccupancyMap::clear

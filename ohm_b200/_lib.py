@@ -90,6 +90,7 @@ SYMBOLS = [
     ("ohmb200_set_profiling", C.c_int, [_vp, C.c_int]),
     ("ohmb200_kernel_times", C.c_int, [_vp, C.POINTER(KernelTime), C.c_int, C.c_int]),
     ("ohmb200_set_region_reserve", C.c_int, [_vp, C.c_uint32]),
+    ("ohmb200_remove_region", C.c_int, [_vp, _kp]),
     ("ohmb200_paging_stats", C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                        C.POINTER(C.c_uint64)]),
     ("ohmb200_last_error", C.c_char_p, []),

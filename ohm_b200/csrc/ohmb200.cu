@@ -3030,6 +3030,47 @@ int ohmb200_get_stats(ohmb200_map *m, ohmb200_stats *stats)
   return OHMB200_OK;
 }
 
+int ohmb200_remove_region(ohmb200_map *m, const int16_t key_xyz[3])
+{
+  if (!m || !key_xyz)
+  {
+    return setError(OHMB200_E_INVALID, "ohmb200_remove_region: bad arguments");
+  }
+  cudaSetDevice(m->device);
+  const unsigned long long key = packRegion(key_xyz[0], key_xyz[1], key_xyz[2]);
+  if (m->store.erase(key))
+  {
+    return OHMB200_OK;  // it lived in the host store
+  }
+  CUDA_TRY(cudaStreamSynchronize(m->copy_stream));
+  std::vector<uint32_t> slot;
+  int rc = findSlots(m, key_xyz, 1, slot);  // waits for the queued batches
+  if (rc)
+  {
+    return rc;
+  }
+  rc = ensureGather(m, 16, 1);
+  if (rc)
+  {
+    return rc;
+  }
+  // the slot is cleared for its next tenant and becomes a tombstone (probe sequences that pass it stay intact)
+  CUDA_TRY(cudaMemcpyAsync(m->d_gather_slots, slot.data(), sizeof(uint32_t), cudaMemcpyHostToDevice, m->stream));
+  clearEvictedSlots<<<1, 256, 0, m->stream>>>(m->dm, makeClearTable(m), m->d_gather_slots, 1u);
+  CUDA_TRY(cudaGetLastError());
+  const unsigned long long tomb = kTombKey;
+  CUDA_TRY(cudaMemcpyAsync(m->dm.keys + slot[0], &tomb, sizeof(tomb), cudaMemcpyHostToDevice, m->stream));
+  rc = pullCounters(m);
+  if (rc)
+  {
+    return rc;
+  }
+  const unsigned long long resident = m->h_counters->region_count ? m->h_counters->region_count - 1 : 0;
+  CUDA_TRY(cudaMemcpyAsync(&m->d_counters->region_count, &resident, sizeof(resident), cudaMemcpyHostToDevice, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  return OHMB200_OK;
+}
+
 int ohmb200_set_region_reserve(ohmb200_map *m, uint32_t free_slots)
 {
   if (!m || free_slots == 0 || free_slots > m->dm.capacity)

@@ -664,6 +664,107 @@ __device__ __forceinline__ void foldGroupsSole(const uint32_t *tile, const TileL
   }
 }
 
+// The fold of a work item that shares its region with other items (a hot region is cut into several), fast layouts:
+// the same scan, the slab updated by 64-bit compare-and-swap — a unit is two 4-byte voxels or one 8-byte voxel — with
+// all the swaps of a group in flight together; a swap that lost against another item's fold (rare) is repeated on
+// the value it returned.
+template <typename Voxel, typename Counts, typename Apply>
+__device__ __forceinline__ void foldGroupsShared(const uint32_t *tile, const TileLayout &tl, Voxel *slab, uint32_t *ticket,
+                                                 Counts &&counts, Apply &&apply)
+{
+  constexpr int kUnits = (int)sizeof(Voxel);  // 64-bit units per group of eight voxels
+  constexpr int kPerUnit = 8 / kUnits;        // voxels per unit
+  const uint4 *tile4 = reinterpret_cast<const uint4 *>(tile);
+  const uint32_t groups = ((uint32_t)tl.dxy * (uint32_t)tl.dz) >> 3;
+  const uint32_t lane = threadIdx.x & 31u;
+  for (;;)
+  {
+    uint32_t base = 0;
+    if (lane == 0)
+    {
+      base = atomicAdd(ticket, 1u) * 32u;
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= groups)
+    {
+      break;
+    }
+    const uint32_t c = base + lane;
+    uint32_t cnt[8];
+    bool any = false;
+    if (c < groups)
+    {
+      const uint32_t position = groupPosition(tl, c);
+      const uint4 t = tile4[position >> 3];
+      any = (t.x | t.y | t.z | t.w) != 0 && counts(position, t, cnt);
+    }
+    if (!any)
+    {
+      continue;
+    }
+    unsigned long long *units = reinterpret_cast<unsigned long long *>(slab + 8u * c);
+    union
+    {
+      unsigned long long unit[kUnits];
+      Voxel voxel[8];
+    } old, now;
+#pragma unroll
+    for (int k = 0; k < kUnits; ++k)
+    {
+      const uint32_t wanted = (kPerUnit == 2) ? (cnt[2 * k] | cnt[2 * k + 1]) : cnt[k];
+      old.unit[k] = wanted ? __ldcg(units + k) : 0ull;
+    }
+#pragma unroll
+    for (int k = 0; k < kUnits; ++k)
+    {
+      now.unit[k] = old.unit[k];
+    }
+#pragma unroll
+    for (int v = 0; v < 8; ++v)
+    {
+      apply(now.voxel[v], cnt[v]);
+    }
+    uint32_t lost = 0;
+#pragma unroll
+    for (int k = 0; k < kUnits; ++k)
+    {
+      const uint32_t wanted = (kPerUnit == 2) ? (cnt[2 * k] | cnt[2 * k + 1]) : cnt[k];
+      if (wanted && now.unit[k] != old.unit[k])
+      {
+        const unsigned long long got = atomicCAS(units + k, old.unit[k], now.unit[k]);
+        lost |= (got != old.unit[k]) ? (1u << k) : 0u;
+        old.unit[k] = got;
+      }
+    }
+    if (lost)
+    {
+#pragma unroll
+      for (int k = 0; k < kUnits; ++k)
+      {
+        while (lost & (1u << k))
+        {
+          now.unit[k] = old.unit[k];
+#pragma unroll
+          for (int j = 0; j < kPerUnit; ++j)
+          {
+            apply(now.voxel[kPerUnit * k + j], cnt[kPerUnit * k + j]);
+          }
+          if (now.unit[k] == old.unit[k])
+          {
+            break;
+          }
+          const unsigned long long got = atomicCAS(units + k, old.unit[k], now.unit[k]);
+          if (got == old.unit[k])
+          {
+            break;
+          }
+          old.unit[k] = got;
+        }
+      }
+    }
+  }
+}
+
 // The update of one 64-bit unit of a slab by a work item that shares its region with other items (a hot region is
 // cut into several): compare-and-swap, repeated on the value it returned when another item's fold got in between.
 template <typename Update>
@@ -787,6 +888,11 @@ __device__ __forceinline__ void foldLogOddsTile(const uint32_t *tile, const uint
     }
     return any != 0;
   };
+  const auto log_odds_after = [&](float &v, uint32_t count) {
+    bool ok;
+    const float after = missLadderLookup(ladder, v, count, ok);
+    v = ok ? after : missRepeat(v, count, mp, ray_flags);
+  };
   if (hit_miss)
   {
     foldGroups(tile, tl, [&](uint32_t c, uint32_t position, const uint4 &t) {
@@ -805,40 +911,10 @@ __device__ __forceinline__ void foldLogOddsTile(const uint32_t *tile, const uint
   if (!shared)
   {
     // sole writer of the region's log-odds until this kernel ends
-    foldGroupsSole<2>(tile, tl, occ, ticket, counts, [&](float &v, uint32_t count) {
-      bool ok;
-      const float after = missLadderLookup(ladder, v, count, ok);
-      v = ok ? after : missRepeat(v, count, mp, ray_flags);
-    });
+    foldGroupsSole<2>(tile, tl, occ, ticket, counts, log_odds_after);
     return;
   }
-  foldGroups(tile, tl, [&](uint32_t c, uint32_t position, const uint4 &t) {
-    uint32_t cnt[8];
-    if (!counts(position, t, cnt))
-    {
-      return;
-    }
-    // shared region: a compare-and-swap per pair of voxels, the four reads in flight together
-    unsigned long long *units = reinterpret_cast<unsigned long long *>(occ) + 4u * c;
-    unsigned long long seen[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-    {
-      seen[k] = (cnt[2 * k] | cnt[2 * k + 1]) ? __ldcg(units + k) : 0ull;
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-    {
-      if (cnt[2 * k] | cnt[2 * k + 1])
-      {
-        foldUnitShared(units + k, seen[k], [&](unsigned long long old) {
-          const float x = misses(__uint_as_float((uint32_t)old), cnt[2 * k]);
-          const float y = misses(__uint_as_float((uint32_t)(old >> 32)), cnt[2 * k + 1]);
-          return (unsigned long long)__float_as_uint(x) | ((unsigned long long)__float_as_uint(y) << 32);
-        });
-      }
-    }
-  });
+  foldGroupsShared(tile, tl, occ, ticket, counts, log_odds_after);
 }
 
 // Work item w of the batch, or the "no more work" marker.

@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(128) markTsdfNear(const __grid_constant__ Devi
 
 // The fold of walkRegionsTsdf: k commuting far visits of a voxel -> (trunc, min(w + 1, max) k times).
 __device__ __forceinline__ void foldTsdfTile(const uint32_t *tile, const TileLayout &layout, float2 *slab,
-                                             const MapParams &mp, uint32_t shared)
+                                             const MapParams &mp, uint32_t *ticket, uint32_t shared)
 {
   const TileLayout tl = foldLayout(layout);
   auto far_visits = [&](float w, uint32_t k) {
@@ -208,9 +208,9 @@ __device__ __forceinline__ void foldTsdfTile(const uint32_t *tile, const TileLay
     });
     return;
   }
-  foldGroups(tile, tl, [&](uint32_t c, uint32_t, const uint4 &t) {
+  const auto counts = [&](uint32_t, const uint4 &t, uint32_t cnt[8]) {
     const uint32_t w4[4] = { t.x, t.y, t.z, t.w };
-    uint32_t cnt[8], any = 0;
+    uint32_t any = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k)
     {
@@ -218,53 +218,24 @@ __device__ __forceinline__ void foldTsdfTile(const uint32_t *tile, const TileLay
       cnt[k] = (half & kTileFlag) ? 0u : half;
       any |= cnt[k];
     }
-    if (!any)
+    return any != 0;
+  };
+  const auto far_voxel = [&](float2 &v, uint32_t count) {
+    if (count)
     {
-      return;
+      v.x = far_visits(v.x, count);
+      v.y = mp.tsdf_trunc;
     }
-    if (!shared)
-    {
-      // sole writer of the region in this batch: 64-byte read-modify-write of eight voxels at a time
-      float4 *slab4 = reinterpret_cast<float4 *>(slab) + 4u * c;
-      float4 v[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-      {
-        v[k] = slab4[k];
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-      {
-        if (cnt[2 * k])
-        {
-          v[k].x = far_visits(v[k].x, cnt[2 * k]);
-          v[k].y = mp.tsdf_trunc;
-        }
-        if (cnt[2 * k + 1])
-        {
-          v[k].z = far_visits(v[k].z, cnt[2 * k + 1]);
-          v[k].w = mp.tsdf_trunc;
-        }
-        slab4[k] = v[k];
-      }
-      return;
-    }
-    unsigned long long *units = reinterpret_cast<unsigned long long *>(slab) + 8u * c;
-    unsigned long long seen[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-    {
-      seen[k] = cnt[k] ? __ldcg(units + k) : 0ull;
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-    {
-      if (cnt[k])
-      {
-        foldUnitShared(units + k, seen[k], [&](unsigned long long old) { return voxel_after(old, cnt[k]); });
-      }
-    }
-  });
+  };
+  if (!shared)
+  {
+    // sole writer of the region in this batch: 64-byte read-modify-write of eight voxels at a time
+    foldGroupsSole<1>(tile, tl, slab, ticket, counts, far_voxel);
+  }
+  else
+  {
+    foldGroupsShared(tile, tl, slab, ticket, counts, far_voxel);
+  }
 }
 
 // Pass 2: count far visits of unflagged voxels in the tile, record every visit of flagged voxels (stored state not
@@ -280,6 +251,7 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegionsTsdf(
   uint32_t parity = 1;
   __shared__ unsigned long long record_chunk[kWalkThreads / 32];
   __shared__ SegmentQueue queue;
+  __shared__ uint32_t fold_ticket;  // next block of the fold (foldGroupsSole / foldGroupsShared)
   const uint32_t words = tl.words;
   const uint32_t tile_base = (uint32_t)__cvta_generic_to_shared(tile);
   const uint32_t flag_words = (g.vpr + 31u) >> 5;
@@ -370,10 +342,11 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegionsTsdf(
     if (tid == 0)
     {
       loadWorkItem(b, next_work, &items2[parity ^ 1u]);
+      fold_ticket = 0;
     }
     __syncthreads();
 
-    foldTsdfTile(tile, tl, dm.tsdf + (size_t)vbase, mp, item.shared);
+    foldTsdfTile(tile, tl, dm.tsdf + (size_t)vbase, mp, &fold_ticket, item.shared);
   }
 }
 

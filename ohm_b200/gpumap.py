@@ -299,6 +299,11 @@ class GpuMap:
         """Free region slots guaranteed before every batch (include/ohmb200.h: ohmb200_set_region_reserve)."""
         self._check(self.L.ohmb200_set_region_reserve(self.h, int(free_slots)))
 
+    def remove_region(self, key):
+        """MapRegionCache::remove: drop one region (resident or stored) with all its layers."""
+        key = np.ascontiguousarray(key, dtype=np.int16)
+        self._check(self.L.ohmb200_remove_region(self.h, key.ctypes.data_as(C.POINTER(C.c_int16))))
+
     def paging_stats(self):
         """{resident, stored, evicted, paged_in}: regions in device memory / in the host store, totals so far."""
         v = [C.c_uint64() for _ in range(4)]

@@ -80,3 +80,33 @@ def test_clear_forgets_the_store(gpu):
     integrate_both(g, c, rays)
     compare_maps(g, c)
     g.close()
+
+
+def test_remove_region_resident_and_stored(gpu):
+    # MapRegionCache::remove: a removed region is gone from reads and counts, its slot is reusable, and integrating
+    # into it again starts from an unobserved region (the oracle removes the same regions)
+    g, c = make_pair(0.25, device_bytes=60 * region_bytes([gm.LAYER_OCCUPANCY], 16 ** 3), region_dim=(16, 16, 16))
+    batches = trajectory_rays(steps=20, rays_per_step=400, seed=9)
+    for rays in batches:
+        g.integrate_rays(rays)
+    g.sync_voxels()
+    before = g.stats()["regions"]
+    ps = g.paging_stats()
+    assert ps["stored"] > 0
+    dump = g.dump()
+    keys = sorted(dump.keys())
+    victims = [keys[0], keys[len(keys) // 2], keys[-1]]
+    for k in victims:
+        g.remove_region(k)
+    assert g.stats()["regions"] == before - len(victims)
+    after = g.dump()
+    assert sorted(after.keys()) == [k for k in keys if k not in victims]
+    for k in after:
+        assert np.array_equal(after[k][gm.LAYER_OCCUPANCY].view(np.uint32), dump[k][gm.LAYER_OCCUPANCY].view(np.uint32))
+    with pytest.raises(Exception):
+        g.remove_region(victims[0])
+    # the map keeps working: the same rays again re-create the removed regions
+    g.integrate_rays(batches[0])
+    g.sync_voxels()
+    assert g.stats()["regions"] >= before - len(victims)
+    g.close()
