@@ -551,7 +551,7 @@ OHMB200_HD inline unsigned walkLine(const Geom &g, const double start[3], const 
 
 // One miss applied to `v` with the CPU mapper's flag logic (RayMapperOccupancy.cpp:150-166 +
 // VoxelOccupancyCompute.h:110-120).  A pure function of v, so k identical misses commute with each other.
-__device__ __forceinline__ float missOnce(float v, const MapParams &p, unsigned ray_flags)
+OHMB200_HD __forceinline__ float missOnce(float v, const MapParams &p, unsigned ray_flags)
 {
   const float uninit = INFINITY;
   const bool unobserved = v == uninit;
@@ -571,12 +571,12 @@ __device__ __forceinline__ float missOnce(float v, const MapParams &p, unsigned 
 // has turned "unobserved" into 0 + miss: a four-instruction step instead of missOnce's flag logic, and when the count
 // is so large that the walk down certainly ends on the clamp (with room for the rounding of every add) the answer is
 // min itself.  (A fold that ran missOnce ten times per voxel of a fresh map was 60 % of walkRegions.)
-__device__ __forceinline__ bool missIsPlain(const MapParams &p, unsigned ray_flags)
+OHMB200_HD __forceinline__ bool missIsPlain(const MapParams &p, unsigned ray_flags)
 {
   return (ray_flags & 0xE0u) == 0 && p.sat_min == -FLT_MAX && p.sat_max == FLT_MAX;
 }
 
-__device__ __forceinline__ float missRepeatPlain(float v, uint32_t count, float miss_value, float min_value)
+OHMB200_HD __forceinline__ float missRepeatPlain(float v, uint32_t count, float miss_value, float min_value)
 {
   if (count == 0)
   {
@@ -609,7 +609,7 @@ __device__ __forceinline__ float missRepeatPlain(float v, uint32_t count, float 
   return v;
 }
 
-__device__ __forceinline__ float missRepeat(float v, uint32_t count, const MapParams &p, unsigned ray_flags)
+OHMB200_HD __forceinline__ float missRepeat(float v, uint32_t count, const MapParams &p, unsigned ray_flags)
 {
   if (missIsPlain(p, ray_flags))
   {
@@ -642,7 +642,7 @@ struct MissLadder
   uint32_t fix;    // value[fix] is a fixed point of the miss rule; kMissLadder if the table ends before one
 };
 
-__device__ __forceinline__ void buildMissLadder(MissLadder &ladder, const MapParams &p, unsigned ray_flags)
+OHMB200_HD __forceinline__ void buildMissLadder(MissLadder &ladder, const MapParams &p, unsigned ray_flags)
 {
   float v = INFINITY;
   ladder.fix = kMissLadder;
@@ -662,7 +662,7 @@ __device__ __forceinline__ void buildMissLadder(MissLadder &ladder, const MapPar
 // Branch-free lookup: the value after `count` misses when v is on the ladder (ok = true), so that the lookups of the
 // eight voxels of a group overlap; off the ladder (a voxel with hits in its history, a table without a fixed point)
 // ok = false and the caller runs missRepeat.
-__device__ __forceinline__ float missLadderLookup(const MissLadder &ladder, float v, uint32_t count, bool &ok)
+OHMB200_HD __forceinline__ float missLadderLookup(const MissLadder &ladder, float v, uint32_t count, bool &ok)
 {
   const uint32_t fix = ladder.fix;
   const bool has_fix = fix < (uint32_t)kMissLadder;
@@ -678,7 +678,7 @@ __device__ __forceinline__ float missLadderLookup(const MissLadder &ladder, floa
   return (count == 0 || at_fix) ? v : after;
 }
 
-__device__ __forceinline__ float missRepeatLadder(const MissLadder &ladder, float v, uint32_t count, const MapParams &p,
+OHMB200_HD __forceinline__ float missRepeatLadder(const MissLadder &ladder, float v, uint32_t count, const MapParams &p,
                                                   unsigned ray_flags)
 {
   bool ok;
@@ -687,7 +687,7 @@ __device__ __forceinline__ float missRepeatLadder(const MissLadder &ladder, floa
 }
 
 // RayMapperOccupancy.cpp:262-279 + VoxelOccupancyCompute.h:44-54
-__device__ __forceinline__ float hitOnce(float v, const MapParams &p, unsigned ray_flags)
+OHMB200_HD __forceinline__ float hitOnce(float v, const MapParams &p, unsigned ray_flags)
 {
   const float uninit = INFINITY;
   const bool unobserved = v == uninit;

@@ -126,9 +126,146 @@ static bool checkRay(const Geom &g, const double start[3], const double end[3], 
   return ok;
 }
 
+// The layout of the shared-memory counter tile and the thread -> ray mapping of the per-ray kernels: pure index maths,
+// checked exhaustively.
+static int checkLayouts()
+{
+  int bad = 0;
+  const int dims[][3] = { { 32, 32, 32 }, { 16, 16, 16 }, { 16, 24, 8 }, { 8, 5, 3 }, { 12, 10, 6 }, { 5, 7, 3 },
+                          { 9, 32, 4 }, { 64, 2, 2 }, { 255, 3, 1 }, { 1, 1, 1 }, { 2, 255, 2 } };
+  for (const auto &d : dims)
+  {
+    for (int variant = 0; variant < 3; ++variant)
+    {
+      const Geom g = makeGeom(0.1, d[0], d[1], d[2], 0, 0, 0);
+      const TileLayout tl = variant == 0 ? makeTileLayout(g) : (variant == 1 ? makeTileLayout(g, 1, 5) : makeTileLayout(g, 0, -1));
+      bad += (tl.row & 1) || (tl.slab & 1) || tl.row < d[0] || tl.slab < tl.row * d[1] || (tl.words & 31u);
+      bad += (uint32_t)tl.slab * (uint32_t)d[2] > 2u * tl.words;
+      std::vector<char> used((size_t)2 * tl.words, 0);
+      for (uint32_t v = 0; v < g.vpr; ++v)
+      {
+        const uint32_t half = tileHalf(tl, v);
+        const uint32_t x = v % (uint32_t)d[0], y = (v / (uint32_t)d[0]) % (uint32_t)d[1], z = v / (uint32_t)(d[0] * d[1]);
+        bad += half != x + (uint32_t)tl.row * y + (uint32_t)tl.slab * z;  // linear in the coordinates
+        bad += half >= used.size() || used[half]++ != 0 || tileVoxel(tl, half) != v;
+      }
+      // rows -> (y, z) and groups -> rows by multiply-high, as foldTile / groupPosition do on the device
+      for (uint32_t r = 0; r < (uint32_t)(d[1] * d[2]); ++r)
+      {
+        const uint32_t z = (d[1] > 1) ? (uint32_t)(((unsigned long long)r * tl.inv_dy) >> 32) : r;
+        bad += z != r / (uint32_t)d[1];
+      }
+      if (tl.fast)
+      {
+        bad += (d[0] % 8) != 0 || tl.row_groups != (uint32_t)d[0] / 8u;
+        for (uint32_t c = 0; c < g.vpr / 8u; ++c)
+        {
+          const uint32_t r = (tl.row_groups > 1) ? (uint32_t)(((unsigned long long)c * tl.inv_row_groups) >> 32) : c;
+          bad += r != c / tl.row_groups;
+          bad += (tileHalf(tl, 8u * c) & 7u) != 0;  // groups of eight voxels are aligned 16-byte groups of the tile
+          bad += tileHalf(tl, 8u * c + 7u) != tileHalf(tl, 8u * c) + 7u;
+        }
+      }
+    }
+  }
+  const uint32_t counts[] = { 0, 1, 31, 2047, 2048, 2049, 4096, 5000, 131072, 131072 + 777 };
+  for (uint32_t n : counts)
+  {
+    std::vector<char> seen(n, 0);
+    for (uint32_t i = 0; i < n; ++i)
+    {
+      const uint32_t ray = rayOfThread(i, n);
+      bad += ray >= n || seen[ray]++ != 0;  // a permutation of the rays
+    }
+  }
+  return bad;
+}
+
+// The miss ladder of the fold (MissLadder, ohmb200_device.cuh) against the definition — missOnce applied `count` times —
+// for every miss rule the mapper has: plain, saturation, each exclusion flag, odd parameters; values on the ladder, off it
+// (voxels with hits in their history), unobserved, the clamp, NaN; counts from 0 to the tile counter's maximum.
+static int checkMissLadder()
+{
+  int bad = 0;
+  struct Rule
+  {
+    float miss, min, max, threshold;
+    bool sat_min, sat_max;
+    unsigned flags;
+  };
+  const Rule rules[] = {
+    { -0.2006707f, -2.0f, 3.511f, 0.0f, false, false, 0u },   { -0.2006707f, -2.0f, 3.511f, 0.0f, true, true, 0u },
+    { -0.2006707f, -2.0f, 3.511f, 0.0f, false, false, 1u << 5 }, { -0.2006707f, -2.0f, 3.511f, 0.0f, false, false, 1u << 6 },
+    { -0.2006707f, -2.0f, 3.511f, 0.0f, false, false, 1u << 7 }, { -0.4f, -1.9f, 2.0f, 0.0f, false, false, 0u },
+    { -0.01f, -2.0f, 3.5f, 0.0f, false, false, 0u },          { 0.3f, -2.0f, 3.5f, 0.0f, false, false, 0u },
+    { -2.4079456f, -2.0f, 3.511f, 0.0f, true, false, 0u },    { -1e-9f, -2.0f, 3.5f, 0.5f, false, false, 0u },
+  };
+  const uint32_t counts[] = { 0, 1, 2, 3, 5, 9, 10, 11, 12, 31, 63, 64, 65, 200, 1000, 32767 };
+  std::mt19937 rng(5489u);
+  std::uniform_real_distribution<float> any_value(-2.5f, 4.0f);
+  for (const Rule &r : rules)
+  {
+    MapParams p{};
+    p.miss_value = r.miss;
+    p.hit_value = 2.1972246f;
+    p.min_value = r.min;
+    p.max_value = r.max;
+    p.threshold_value = r.threshold;
+    p.sat_min = r.sat_min ? r.min : -FLT_MAX;
+    p.sat_max = r.sat_max ? r.max : FLT_MAX;
+    MissLadder ladder;
+    buildMissLadder(ladder, p, r.flags);
+    std::vector<float> values = { INFINITY, r.min, r.max, 0.0f, -0.0f, NAN, r.min + 1e-6f, 2.1972246f };
+    for (int k = 0; k < kMissLadder; ++k)
+    {
+      values.push_back(ladder.value[k]);
+      values.push_back(hitOnce(ladder.value[k], p, 0u));              // a voxel that took a hit after k misses
+      values.push_back(missOnce(hitOnce(ladder.value[k], p, 0u), p, r.flags));
+    }
+    for (int k = 0; k < 300; ++k)
+    {
+      values.push_back(any_value(rng));
+    }
+    for (float v : values)
+    {
+      for (uint32_t count : counts)
+      {
+        float want = v;
+        for (uint32_t n = 0; n < count; ++n)
+        {
+          const float next = missOnce(want, p, r.flags);
+          if (memcmp(&next, &want, sizeof(float)) == 0)
+          {
+            break;
+          }
+          want = next;
+        }
+        const float got = missRepeatLadder(ladder, v, count, p, r.flags);
+        const float plain = missRepeat(v, count, p, r.flags);
+        const bool same = memcmp(&got, &want, sizeof(float)) == 0 || (got == want && got == 0.0f) || (got != got && want != want);
+        const bool same_plain = memcmp(&plain, &want, sizeof(float)) == 0 || (plain == want && plain == 0.0f) || (plain != plain && want != want);
+        if (!same || !same_plain)
+        {
+          if (bad < 10)
+          {
+            fprintf(stderr, "miss ladder: rule miss %g min %g flags %u: v %.9g count %u -> ladder %.9g, missRepeat %.9g, want %.9g\n",
+                    r.miss, r.min, r.flags, v, count, got, plain, want);
+          }
+          ++bad;
+        }
+      }
+    }
+  }
+  return bad;
+}
+
 int main()
 {
-  int failures = 0;
+  int failures = checkLayouts() + checkMissLadder();
+  if (failures)
+  {
+    fprintf(stderr, "layout checks: %d failures\n", failures);
+  }
   std::mt19937_64 rng(1153297050u);
   const Geom geoms[] = {
     makeGeom(0.1, 32, 32, 32, 0, 0, 0),       makeGeom(0.1, 32, 32, 32, 0.05, 0.05, 0.05),

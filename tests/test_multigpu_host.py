@@ -61,6 +61,48 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
+def _weak_worker(rank, world, port, out_dir):
+    """bench.py's N>1 arm: rank r brings its own batch (sweep r; ragged sizes), padded with NaN rays to the longest;
+    the all-gather in rank order is the batch every rank integrates."""
+    sys.path.insert(0, ROOT)
+    from ohm_b200.lidar import cube_rays
+    from oracle import pyoracle as po
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sweeps = [cube_rays(700 + 150 * r, half_extent=12.0, origin=(0.05 + 0.5 * r, 0.05, 0.05), seed=11 + r)
+              for r in range(world)]
+    per = max(s.shape[0] // 2 for s in sweeps)
+    mine = np.full((2 * per, 3), np.nan)
+    mine[:sweeps[rank].shape[0]] = sweeps[rank]
+    full = torch.empty((2 * per * world, 3), dtype=torch.float64)
+    dist.all_gather_into_tensor(full, torch.from_numpy(mine))
+    full = full.numpy()
+    for r in range(world):
+        got = full[2 * per * r:2 * per * (r + 1)]
+        n_r = sweeps[r].shape[0]
+        assert np.array_equal(got[:n_r], sweeps[r]) and np.all(np.isnan(got[n_r:]))
+    # the padded, gathered batch and the plain concatenation of the sweeps are the same batch to the mapper
+    a, b = po.OracleMap(0.25), po.OracleMap(0.25)
+    a.integrate_rays(full)
+    b.integrate_rays(np.concatenate(sweeps))
+    assert a.stats()["rays_accepted"] == b.stats()["rays_accepted"] == sum(s.shape[0] // 2 for s in sweeps)
+    da, db = a.dump(), b.dump()
+    assert sorted(da) == sorted(db)
+    for key in da:
+        for layer in da[key]:
+            assert np.array_equal(np.ascontiguousarray(da[key][layer]).view(np.uint8),
+                                  np.ascontiguousarray(db[key][layer]).view(np.uint8))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_one_sweep_per_rank(tmp_path):
+    world = 2
+    mp.spawn(_weak_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+
+
 def test_two_rank_gloo_gather_and_partition(tmp_path):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
