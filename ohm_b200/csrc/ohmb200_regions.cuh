@@ -19,7 +19,7 @@ namespace ohmb200
 {
 constexpr unsigned kRecValid = 1u << 3, kRecExcludeStart = 1u << 4, kRecExcludeEnd = 1u << 5;
 constexpr uint32_t kMaxSegmentsPerItem = 2048;  // < 32768: tile counters are 15 bit + flag
-constexpr uint32_t kRecordChunk = 256;
+constexpr uint32_t kRecordChunk = 256;  // ordered-miss records are reserved per warp in chunks
 // Counter tile addressing.  One u16 counter per voxel (15-bit count + flag bit), two per 32-bit word.  The tile is a
 // padded copy of the region, the position of a voxel LINEAR in its coordinates:
 //        position(x, y, z) = x + row * y + slab * z          (counters; row and slab are even)
@@ -87,7 +87,7 @@ OHMB200_HD __forceinline__ uint32_t tileVoxel(const TileLayout &t, uint32_t half
   const uint32_t y = r / (uint32_t)t.row;
   return (r - y * (uint32_t)t.row) + y * (uint32_t)t.dx + z * (uint32_t)t.dxy;
 }
-constexpr uint32_t kStageSegments = 96;  // segments per ray that pass A hands to pass B without a second enumeration         // ordered-miss records are reserved per warp in chunks
+constexpr uint32_t kStageSegments = 96;  // segments per ray that pass A hands to pass B without a second enumeration
 constexpr uint32_t kTileFlag = 0x8000u;
 
 // Walk constants of one ray (64 bytes).
@@ -338,6 +338,78 @@ OHMB200_HD inline void enumerateSegments(const RayRec &rec, const Geom &g, Emit 
   }
 }
 
+// ---- one crossing at a time (groundwork for a producer with one thread per crossing; not yet used by the kernels) ----
+// enumerateSegments walks a ray's region crossings in order, each found from the one before.  They do not depend on
+// each other: crossing j of axis a IS step k1_a + j dim_a of that axis (k1_a = steps until the local coordinate first
+// wraps), taken at time T_a(k1_a + j dim_a - 1); the steps of another axis b that precede it are counted by the same
+// estimate-and-check search enumerateSegments uses; and the number of crossings of axis b among those steps is a
+// closed form of that count — so the crossing's rank in the merged order of all crossings, the walk position right
+// after it and the state of the walk there follow without looking at any other crossing.  A segment is what lies
+// between two crossings of consecutive rank: with one thread per crossing writing (position, steps) at its rank and a
+// second pass taking differences, the ~1 M segments of a sweep become ~1 M balanced threads instead of 131 k threads
+// that loop over 4 to 60 segments each.  tests/cpp/segments_host_test.cu proves the equivalence on the host.
+struct Crossing
+{
+  int rank;         // 1-based position among the ray's crossings in walk order (rank 0 = the start of the ray)
+  int position;     // walk position (steps taken) of the first voxel after the crossing
+  int stepped[3];   // per-axis steps taken at that position
+};
+
+// steps on `axis` until the local coordinate wraps for the first time
+OHMB200_HD __forceinline__ int firstCrossingStep(const RayRec &rec, const Geom &g, int axis)
+{
+  return (rec.flags & (1u << axis)) ? (int)rec.local[axis] + 1 : g.dim[axis] - (int)rec.local[axis];
+}
+
+// crossings of `axis` among its first `steps` steps
+OHMB200_HD __forceinline__ int crossingsWithin(const RayRec &rec, const Geom &g, int axis, int steps)
+{
+  const int first = firstCrossingStep(rec, g, axis);
+  return steps >= first ? 1 + (steps - first) / g.dim[axis] : 0;
+}
+
+// Crossing j (0-based) of `axis`; false when the ray has no such crossing.
+OHMB200_HD inline bool crossingOf(const RayRec &rec, const Geom &g, int axis, int j, Crossing &out)
+{
+  const int step = firstCrossingStep(rec, g, axis) + j * g.dim[axis];  // its number among the steps of the axis
+  if (j < 0 || step > (int)rec.total[axis])
+  {
+    return false;
+  }
+  const double ct = stepTime(rec.initial[axis], rec.delta[axis], step - 1);
+  out.rank = 1 + j;
+  out.position = 0;
+#pragma unroll
+  for (int b = 0; b < 3; ++b)
+  {
+    int n = step;
+    if (b != axis)
+    {
+      // the largest n in [0, total_b] whose step n (taken at T_b(n - 1)) precedes the crossing; "precedes" is monotone
+      const int hi = (int)rec.total[b];
+      n = 0;
+      if (hi > 0)
+      {
+        const double guess = (ct - rec.initial[b]) / rec.delta[b];  // an estimate only
+        n = (guess >= (double)hi) ? hi : ((guess > 0.0) ? (int)guess + 1 : 0);  // NaN -> 0
+        n = min(max(n, 0), hi);
+        while (n > 0 && !stepPrecedes(stepTime(rec.initial[b], rec.delta[b], n - 1), b, ct, axis))
+        {
+          --n;
+        }
+        while (n < hi && stepPrecedes(stepTime(rec.initial[b], rec.delta[b], n), b, ct, axis))
+        {
+          ++n;
+        }
+      }
+      out.rank += crossingsWithin(rec, g, b, n);
+    }
+    out.stepped[b] = n;
+    out.position += n;
+  }
+  return true;
+}
+
 // Resume a segment's walk from its per-axis step counts and call visit(l, enter, exit, last_of_ray) for each of
 // its `visits` voxels (l = local voxel coordinates inside the segment's region).  kTimes: also track the
 // enter/exit ranges (traversal layer); `length` is the walk's length (exit range of the end voxel).
@@ -395,9 +467,10 @@ OHMB200_HD inline void resumeSegment(const double init[3], const double delta[3]
   }
 }
 
-// The hot-path variant of resumeSegment: no ranges, a running linear voxel index instead of coordinates, fp64 step
-// counters (no int->double conversion in the loop) and a branch per stepped axis instead of predicating all three.
-// visit(idx) receives the voxel index inside the region.  Same arithmetic, same order of comparisons.
+// resumeSegment without ranges: a running linear voxel index instead of coordinates, fp64 step counters (no int->double
+// conversion in the loop) and a branch per stepped axis.  visit(idx) receives the voxel index inside the region.
+// Same arithmetic, same order of comparisons.  The kernels use resumeSegmentTile (below), which addresses the counter
+// tile directly; this form stays as its reference in tests/cpp/segments_host_test.cu.
 template <typename Visit>
 OHMB200_HD __forceinline__ void resumeSegmentFast(const double init[3], const double delta[3], const int entry[3],
                                                   const int total[3], uint32_t flags, const int st_in[3], int visits,

@@ -34,7 +34,108 @@ static Geom makeGeom(double res, int dx, int dy, int dz, double ox, double oy, d
   return g;
 }
 
-static long long g_rays = 0, g_visits = 0, g_segments = 0;
+static long long g_rays = 0, g_visits = 0, g_segments = 0, g_crossings = 0;
+
+struct SegmentTuple
+{
+  int r[3], st[3], entry[3], n;
+  bool operator==(const SegmentTuple &o) const
+  {
+    return memcmp(r, o.r, sizeof(r)) == 0 && memcmp(st, o.st, sizeof(st)) == 0 && memcmp(entry, o.entry, sizeof(entry)) == 0 &&
+           n == o.n;
+  }
+};
+
+// The segments of a ray rebuilt from its crossings taken ONE AT A TIME (crossingOf): each crossing yields its rank in
+// walk order, the walk position after it and the per-axis step counts there, without reference to any other crossing;
+// a segment is what lies between two crossings of consecutive rank.  Must equal enumerateSegments' output exactly.
+static bool segmentsFromCrossings(const RayRec &rec, const Geom &g, std::vector<SegmentTuple> &out)
+{
+  const int total[3] = { rec.total[0], rec.total[1], rec.total[2] };
+  const int T = total[0] + total[1] + total[2];
+  const bool exclude_start = (rec.flags & kRecExcludeStart) != 0, exclude_end = (rec.flags & kRecExcludeEnd) != 0;
+  auto state_at = [&](const int st[3], SegmentTuple &t) {
+    for (int a = 0; a < 3; ++a)
+    {
+      const int dir = (rec.flags & (1u << a)) ? -1 : 1;
+      t.st[a] = st[a];
+      const int pos = ((int)rec.local[a] + dir * st[a]) % g.dim[a];
+      t.entry[a] = pos < 0 ? pos + g.dim[a] : pos;
+      t.r[a] = (int)(int16_t)((int)rec.region[a] + dir * crossingsWithin(rec, g, a, st[a]));
+    }
+  };
+  if (T == 0)
+  {
+    if (!exclude_end)
+    {
+      SegmentTuple t;
+      const int zero[3] = { 0, 0, 0 };
+      state_at(zero, t);
+      t.n = 1;
+      out.push_back(t);
+    }
+    return true;
+  }
+  int count = 0;
+  for (int a = 0; a < 3; ++a)
+  {
+    count += crossingsWithin(rec, g, a, total[a]);
+  }
+  std::vector<Crossing> by_rank((size_t)count + 1);
+  std::vector<char> have((size_t)count + 1, 0);
+  by_rank[0].rank = 0;
+  by_rank[0].position = 0;
+  by_rank[0].stepped[0] = by_rank[0].stepped[1] = by_rank[0].stepped[2] = 0;
+  have[0] = 1;
+  for (int a = 0; a < 3; ++a)
+  {
+    Crossing c;
+    for (int j = 0; crossingOf(rec, g, a, j, c); ++j)
+    {
+      ++g_crossings;
+      if (c.rank < 1 || c.rank > count || have[c.rank])
+      {
+        return false;  // the ranks must be a permutation of 1 .. count
+      }
+      have[c.rank] = 1;
+      by_rank[c.rank] = c;
+    }
+  }
+  const int q_first = exclude_start ? 1 : 0, q_last = exclude_end ? T - 1 : T;
+  for (int i = 0; i <= count; ++i)
+  {
+    if (!have[i] || (i > 0 && by_rank[i].position <= by_rank[i - 1].position))
+    {
+      return false;
+    }
+    const int begin = by_rank[i].position, end = (i < count) ? by_rank[i + 1].position - 1 : T;
+    const int lo = begin > q_first ? begin : q_first, hi = end < q_last ? end : q_last;
+    if (hi < lo)
+    {
+      continue;
+    }
+    SegmentTuple t;
+    if (lo == begin)
+    {
+      state_at(by_rank[i].stepped, t);
+    }
+    else
+    {
+      // the excluded start voxel: the segment begins one step into the ray (the first step: the earliest exit time)
+      double t0[3];
+      for (int a = 0; a < 3; ++a)
+      {
+        t0[a] = total[a] ? rec.initial[a] : (double)INFINITY;
+      }
+      int st[3] = { 0, 0, 0 };
+      st[selectNextAxis(t0)] = 1;
+      state_at(st, t);
+    }
+    t.n = hi - lo + 1;
+    out.push_back(t);
+  }
+  return true;
+}
 
 static bool checkRay(const Geom &g, const double start[3], const double end[3], unsigned walk_flags)
 {
@@ -65,8 +166,15 @@ static bool checkRay(const Geom &g, const double start[3], const double end[3], 
   const TileLayout tl = makeTileLayout(g);
   bool tile_ok = true;
   int last_flags = 0;
+  std::vector<SegmentTuple> enumerated, rebuilt;
   enumerateSegments(rec, g, [&](const int r[3], const int st[3], const int entry[3], int n) {
     ++g_segments;
+    SegmentTuple tuple;
+    memcpy(tuple.r, r, sizeof(tuple.r));
+    memcpy(tuple.st, st, sizeof(tuple.st));
+    memcpy(tuple.entry, entry, sizeof(tuple.entry));
+    tuple.n = n;
+    enumerated.push_back(tuple);
     const int total[3] = { rec.total[0], rec.total[1], rec.total[2] };
     const int local0[3] = { rec.local[0], rec.local[1], rec.local[2] };
     resumeSegment<true>(rec.initial, rec.delta, local0, total, rec.flags, st, n, length, g,
@@ -103,6 +211,12 @@ static bool checkRay(const Geom &g, const double start[3], const double end[3], 
   }
   ok = ok && (seq.empty() || last_flags == 1);
   ok = ok && fast_idx.size() == seg.size() && tile_ok && tile_idx == fast_idx;
+  const bool crossings_ok = segmentsFromCrossings(rec, g, rebuilt) && rebuilt == enumerated;
+  if (!crossings_ok)
+  {
+    fprintf(stderr, "crossings: %zu segments rebuilt, %zu enumerated\n", rebuilt.size(), enumerated.size());
+  }
+  ok = ok && crossings_ok;
   for (size_t i = 0; ok && i < seg.size(); ++i)
   {
     ok = fast_idx[i] == (uint32_t)(seg[i].l[0] + seg[i].l[1] * g.dim[0] + seg[i].l[2] * g.dim[0] * g.dim[1]);
@@ -325,6 +439,6 @@ int main()
       failures += !checkRay(g, p, q, flags);
     }
   }
-  printf("rays %lld visits %lld segments %lld failures %d\n", g_rays, g_visits, g_segments, failures);
+  printf("rays %lld visits %lld segments %lld crossings %lld failures %d\n", g_rays, g_visits, g_segments, g_crossings, failures);
   return failures ? 1 : 0;
 }
