@@ -137,6 +137,8 @@ struct Batch
   uint4 *stage;            // [kStageSegments][stage_stride] segments found by pass A, plane k = k-th segment of each ray
   uint32_t *stage_count;   // [n] segments pass A found for the ray (> kStageSegments: pass B enumerates again)
   uint32_t stage_stride;
+  uint32_t *cross_pos;     // [kStageSegments][stage_stride] per-crossing producer: walk position after the crossing of rank k
+  uint32_t stage_by_ray;   // the staged planes are indexed by ray (per-crossing producer), not by thread (prepSegments)
   WorkItem *items;         // (region, segment range) work list
   uint32_t item_capacity;
   unsigned long long *gauss_keys;          // NDT: (voxel id << 32 | ray) of visits to voxels with an established Gaussian
@@ -868,6 +870,7 @@ struct ohmb200_map
   TileLayout tile;        // layout of the shared-memory counter tile
   int walk_ctas_per_sm = 1;
   uint32_t heavy_run = 16;
+  int producer = 1;  // 1 = prepSegments (one thread per ray); 2 = one thread per crossing (OHMB200_PRODUCER=2, experimental)
   uint32_t *tsdf_near = nullptr;  // TSDF: per-batch bit per voxel, "visited near a sample in this batch"
   size_t voxel_bit_bytes = 0;     // size of dm.voxel_bits (and of tsdf_near)
   ohmb200_params params{};
@@ -1184,6 +1187,8 @@ int ensureScratch(ohmb200_map *m, size_t n)
     cudaFree(b.items);
     cudaFree(b.stage);
     cudaFree(b.stage_count);
+    cudaFree(b.cross_pos);
+    b.cross_pos = nullptr;
     b.ray_length = nullptr;
     rc |= deviceAlloc(b.recs, cap);
     if (m->dm.traversal)
@@ -1196,6 +1201,10 @@ int ensureScratch(ohmb200_map *m, size_t n)
     b.stage_stride = (uint32_t)cap;
     rc |= deviceAlloc(b.stage, (size_t)kStageSegments * cap);
     rc |= deviceAlloc(b.stage_count, cap);
+    if (m->producer == 2)
+    {
+      rc |= deviceAlloc(b.cross_pos, (size_t)kStageSegments * cap);
+    }
     b.item_capacity = m->dm.capacity + b.seg_capacity / 512 + 16;
     rc |= deviceAlloc(b.items, b.item_capacity);
     if (m->mode == OHMB200_MODE_NDT || m->mode == OHMB200_MODE_NDT_TM)
@@ -1372,8 +1381,19 @@ int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_i
         markRuns<<<blocks, threads, 0, sample_stream>>>(m->dm, b, m->geom.vpr);
       }
     }
+    if (m->producer == 2 && m->mode != OHMB200_MODE_TSDF && b.cross_pos)
+    {
+      // experimental (OHMB200_PRODUCER=2): one thread per region crossing; markTsdfNear still reads prepSegments' layout
+      KernelScope scope(m, kKPrepSegments);
+      const unsigned producer_blocks = (unsigned)((n + kProducerRays - 1) / kProducerRays);
+      b.stage_by_ray = 1;
+      crossPositions<<<producer_blocks, kProducerRays, 0, s>>>(m->geom, b);
+      finishSlots<<<producer_blocks, kProducerRays, 0, s>>>(m->dm, m->geom, b);
+    }
+    else
     {
       KernelScope scope(m, kKPrepSegments);
+      b.stage_by_ray = 0;
       prepSegments<<<blocks, threads, 0, s>>>(m->dm, m->geom, b);
     }
     if (!m->store.empty() && !m->capturing)
@@ -2002,6 +2022,10 @@ ohmb200_map *ohmb200_create(const ohmb200_params *params, int mode, size_t devic
   {
     m->use_graphs = atoi(env) != 0;
   }
+  if (const char *env = getenv("OHMB200_PRODUCER"))
+  {
+    m->producer = atoi(env) == 2 ? 2 : 1;
+  }
   if (const char *env = getenv("OHMB200_HEAVY_RUN"))
   {
     m->heavy_run = (uint32_t)std::max(1, atoi(env));
@@ -2168,7 +2192,7 @@ void ohmb200_destroy(ohmb200_map *m)
                       m->d_intensities[1], m->d_timestamps[0], m->d_timestamps[1], m->d_gather,    m->d_gather_slots,
                       b.recs,           b.ray_length,       b.record_vid,       b.seg_count,      b.seg_offset,
                       b.seg_cursor,     b.sample_begin,     b.segments,         b.items,            b.record_keys,    b.record_keys_sorted, b.gauss_keys,
-                      b.stage,          b.stage_count,      m->tsdf_near,       m->dm.voxel_bits };
+                      b.stage,          b.stage_count,      m->tsdf_near,       m->dm.voxel_bits,   b.cross_pos };
   for (void *p : to_free)
   {
     if (p)
