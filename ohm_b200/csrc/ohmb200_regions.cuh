@@ -355,23 +355,32 @@ struct Crossing
   int stepped[3];   // per-axis steps taken at that position
 };
 
-// steps on `axis` until the local coordinate wraps for the first time
-OHMB200_HD __forceinline__ int firstCrossingStep(const RayRec &rec, const Geom &g, int axis)
+// steps on `axis` until the local coordinate first passes a multiple of `cut` (cut = the region dimension: until it wraps)
+OHMB200_HD __forceinline__ int firstCutStep(const RayRec &rec, int axis, int cut)
 {
-  return (rec.flags & (1u << axis)) ? (int)rec.local[axis] + 1 : g.dim[axis] - (int)rec.local[axis];
+  const int within = (int)rec.local[axis] % cut;
+  return (rec.flags & (1u << axis)) ? within + 1 : cut - within;
 }
 
-// crossings of `axis` among its first `steps` steps
+// cuts of `axis` among its first `steps` steps
+OHMB200_HD __forceinline__ int cutsWithin(const RayRec &rec, int axis, int cut, int steps)
+{
+  const int first = firstCutStep(rec, axis, cut);
+  return steps >= first ? 1 + (steps - first) / cut : 0;
+}
+
+// region crossings of `axis` among its first `steps` steps
 OHMB200_HD __forceinline__ int crossingsWithin(const RayRec &rec, const Geom &g, int axis, int steps)
 {
-  const int first = firstCrossingStep(rec, g, axis);
-  return steps >= first ? 1 + (steps - first) / g.dim[axis] : 0;
+  return cutsWithin(rec, axis, g.dim[axis], steps);
 }
 
-// Crossing j (0-based) of `axis`; false when the ray has no such crossing.
-OHMB200_HD inline bool crossingOf(const RayRec &rec, const Geom &g, int axis, int j, Crossing &out)
+// Cut j (0-based) of `axis`, the walk being cut wherever a local coordinate passes a multiple of cut[axis]; false when
+// the ray has no such cut.  cut = the region dimensions gives the region crossings; a divisor of them cuts the segments
+// shorter (every region crossing is still a cut), which bounds the serial length of a lane's walk.
+OHMB200_HD inline bool cutOf(const RayRec &rec, const int cut[3], int axis, int j, Crossing &out)
 {
-  const int step = firstCrossingStep(rec, g, axis) + j * g.dim[axis];  // its number among the steps of the axis
+  const int step = firstCutStep(rec, axis, cut[axis]) + j * cut[axis];  // its number among the steps of the axis
   if (j < 0 || step > (int)rec.total[axis])
   {
     return false;
@@ -385,7 +394,7 @@ OHMB200_HD inline bool crossingOf(const RayRec &rec, const Geom &g, int axis, in
     int n = step;
     if (b != axis)
     {
-      // the largest n in [0, total_b] whose step n (taken at T_b(n - 1)) precedes the crossing; "precedes" is monotone
+      // the largest n in [0, total_b] whose step n (taken at T_b(n - 1)) precedes the cut; "precedes" is monotone
       const int hi = (int)rec.total[b];
       n = 0;
       if (hi > 0)
@@ -402,12 +411,18 @@ OHMB200_HD inline bool crossingOf(const RayRec &rec, const Geom &g, int axis, in
           ++n;
         }
       }
-      out.rank += crossingsWithin(rec, g, b, n);
+      out.rank += cutsWithin(rec, b, cut[b], n);
     }
     out.stepped[b] = n;
     out.position += n;
   }
   return true;
+}
+
+// Crossing j (0-based) of `axis`; false when the ray has no such crossing.
+OHMB200_HD inline bool crossingOf(const RayRec &rec, const Geom &g, int axis, int j, Crossing &out)
+{
+  return cutOf(rec, g.dim, axis, j, out);
 }
 
 // Resume a segment's walk from its per-axis step counts and call visit(l, enter, exit, last_of_ray) for each of

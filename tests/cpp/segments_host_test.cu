@@ -49,7 +49,14 @@ struct SegmentTuple
 // The segments of a ray rebuilt from its crossings taken ONE AT A TIME (crossingOf): each crossing yields its rank in
 // walk order, the walk position after it and the per-axis step counts there, without reference to any other crossing;
 // a segment is what lies between two crossings of consecutive rank.  Must equal enumerateSegments' output exactly.
+static bool segmentsFromCuts(const RayRec &rec, const Geom &g, const int cut[3], std::vector<SegmentTuple> &out);
 static bool segmentsFromCrossings(const RayRec &rec, const Geom &g, std::vector<SegmentTuple> &out)
+{
+  return segmentsFromCuts(rec, g, g.dim, out);
+}
+
+// ... and cut finer: wherever a local coordinate passes a multiple of cut[axis] (a divisor of the region dimension).
+static bool segmentsFromCuts(const RayRec &rec, const Geom &g, const int cut[3], std::vector<SegmentTuple> &out)
 {
   const int total[3] = { rec.total[0], rec.total[1], rec.total[2] };
   const int T = total[0] + total[1] + total[2];
@@ -79,7 +86,7 @@ static bool segmentsFromCrossings(const RayRec &rec, const Geom &g, std::vector<
   int count = 0;
   for (int a = 0; a < 3; ++a)
   {
-    count += crossingsWithin(rec, g, a, total[a]);
+    count += cutsWithin(rec, a, cut[a], total[a]);
   }
   std::vector<Crossing> by_rank((size_t)count + 1);
   std::vector<char> have((size_t)count + 1, 0);
@@ -90,7 +97,7 @@ static bool segmentsFromCrossings(const RayRec &rec, const Geom &g, std::vector<
   for (int a = 0; a < 3; ++a)
   {
     Crossing c;
-    for (int j = 0; crossingOf(rec, g, a, j, c); ++j)
+    for (int j = 0; cutOf(rec, cut, a, j, c); ++j)
     {
       ++g_crossings;
       if (c.rank < 1 || c.rank > count || have[c.rank])
@@ -217,6 +224,31 @@ static bool checkRay(const Geom &g, const double start[3], const double end[3], 
     fprintf(stderr, "crossings: %zu segments rebuilt, %zu enumerated\n", rebuilt.size(), enumerated.size());
   }
   ok = ok && crossings_ok;
+  // Cut at half regions: every piece stays inside one region, and walking the pieces one after the other visits the
+  // voxels of the sequential walk.
+  if ((g.dim[0] % 2) == 0 && (g.dim[1] % 2) == 0 && (g.dim[2] % 2) == 0)
+  {
+    const int half[3] = { g.dim[0] / 2, g.dim[1] / 2, g.dim[2] / 2 };
+    std::vector<SegmentTuple> pieces;
+    bool halves_ok = segmentsFromCuts(rec, g, half, pieces);
+    size_t at = 0;
+    const int total[3] = { rec.total[0], rec.total[1], rec.total[2] };
+    for (const SegmentTuple &p : pieces)
+    {
+      halves_ok = halves_ok && p.n <= half[0] + half[1] + half[2];
+      resumeSegmentFast(rec.initial, rec.delta, p.entry, total, rec.flags, p.st, p.n, g, [&](uint32_t idx) {
+        halves_ok = halves_ok && at < seq.size() && memcmp(seq[at].r, p.r, sizeof(p.r)) == 0 &&
+                    idx == (uint32_t)(seq[at].l[0] + seq[at].l[1] * g.dim[0] + seq[at].l[2] * g.dim[0] * g.dim[1]);
+        ++at;
+      });
+    }
+    halves_ok = halves_ok && at == seq.size();
+    if (!halves_ok)
+    {
+      fprintf(stderr, "half-region cuts: %zu pieces, %zu of %zu visits matched\n", pieces.size(), at, seq.size());
+    }
+    ok = ok && halves_ok;
+  }
   for (size_t i = 0; ok && i < seg.size(); ++i)
   {
     ok = fast_idx[i] == (uint32_t)(seg[i].l[0] + seg[i].l[1] * g.dim[0] + seg[i].l[2] * g.dim[0] * g.dim[1]);
