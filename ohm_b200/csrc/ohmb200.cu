@@ -94,7 +94,8 @@ struct Counters
   uint32_t new_count;    // regions inserted by this batch (paging: the ones with a chunk in the host store are restored)
   // sticky
   int table_full;
-  int overflow_seen;
+  int overflow_seen;  // bit 0: an ordered-record list overflowed (results incomplete); bit 1: the segment list did (batch dropped)
+  uint32_t batch_stamp;  // stamp of the last batch planRegions saw (read on the device: a replayed graph bakes no stamp)
 };
 constexpr int kPerBatchCounterWords = 11;  // record_count .. new_count
 
@@ -165,6 +166,23 @@ __device__ __forceinline__ uint32_t warpAggregatedInc(uint32_t *counter)
   base = __shfl_sync(mask, base, leader);
   return base + __popc(mask & ((1u << lane) - 1u));
 }
+
+// b.last_exit[] after carryLastExit: the exit range of the last voxel the ray walked, or that of the nearest earlier ray
+// of the batch that walked one — the reference's last_exit_range is a variable of the whole integrateRays call and a
+// ray that visits no voxel (start and sample in one voxel) finds the previous ray's value in it
+// (ohm/RayMapperOccupancy.cpp:79,190,309).  NaN = no ray before it walked anything: the initial 0.
+__device__ __forceinline__ double staleExit(double v)
+{
+  return isnan(v) ? 0.0 : v;
+}
+
+struct CarryValid
+{
+  __device__ __forceinline__ double operator()(double before, double here) const
+  {
+    return isnan(here) ? before : here;
+  }
+};
 
 __device__ __forceinline__ void loadRay(const Batch &b, uint32_t i, double start[3], double end[3])
 {
@@ -271,6 +289,7 @@ __global__ void __launch_bounds__(128) walkRays(DeviceMap dm, Geom g, MapParams 
     unsigned filter_flags = 0;
     Key skey, ekey;
     double last_exit = 0;
+    bool walked_any = false;
     if (applyRayFilter(mp, start, end, filter_flags) && !(b.ray_flags & OHMB200_RF_EXCLUDE_RAY) &&
         voxelKey(g, start, skey) && voxelKey(g, end, ekey))
     {
@@ -297,6 +316,7 @@ __global__ void __launch_bounds__(128) walkRays(DeviceMap dm, Geom g, MapParams 
           }
         }
         last_exit = exit;
+        walked_any = true;
         if (slot < 0)
         {
           visits += (slot == -1) ? 1u : 0u;
@@ -333,7 +353,7 @@ __global__ void __launch_bounds__(128) walkRays(DeviceMap dm, Geom g, MapParams 
     }
     if (b.last_exit)
     {
-      b.last_exit[i] = last_exit;
+      b.last_exit[i] = walked_any ? last_exit : nan("");  // NaN: "the previous ray's" (carryLastExit)
     }
   }
   __syncwarp();
@@ -356,7 +376,7 @@ __global__ void __launch_bounds__(128) applySamples(DeviceMap dm, Geom g, MapPar
 {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned samples = 0, ordered = 0;
-  if (t < b.counters->run_count)
+  if (t < b.counters->run_count && !b.counters->segment_overflow)  // (a batch whose segment list overflowed is dropped whole)
   {
     const uint32_t head = b.run_list[t];
     const uint32_t vid = b.keys_out[head];
@@ -433,7 +453,7 @@ __global__ void __launch_bounds__(128) applySamples(DeviceMap dm, Geom g, MapPar
       {
         const double d[3] = { end[0] - start[0], end[1] - start[1], end[2] - start[2] };
         const double len = sqrt((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]);
-        traversal_add += (float)(len - b.last_exit[ray]);
+        traversal_add += (float)(len - staleExit(b.last_exit[ray]));
       }
       if (dm.touch_time && b.timestamps)
       {
@@ -485,6 +505,109 @@ __global__ void __launch_bounds__(128) applySamples(DeviceMap dm, Geom g, MapPar
       atomicAdd(&b.counters->ordered_records, (unsigned long long)o);
     }
   }
+}
+
+// kRfStopOnFirstOccupied (ohm/RayMapperOccupancy.cpp:183,234): a ray stops adjusting voxels — and loses its sample — once
+// it has passed a voxel that was occupied WHEN THE RAY GOT THERE.  That makes every ray depend on the voxels as the rays
+// before it left them, so the batch is integrated the way the CPU mapper does it: one ray after the other, each voxel
+// read, adjusted and written in walk order, by ONE thread.  Exact and slow by construction; the flag belongs to
+// ohm::ClearingPattern (ohm/ClearingPattern.h:45), whose batches are a few hundred rays.  Occupancy mode only
+// (RayMapperNdt never raises stop_adjustments, RayMapperNdt.cpp:230; RayMapperTsdf ignores ray flags).
+__global__ void __launch_bounds__(32) integrateOrdered(DeviceMap dm, Geom g, MapParams mp, Batch b)
+{
+  if (blockIdx.x != 0 || threadIdx.x != 0)
+  {
+    return;
+  }
+  unsigned long long accepted = 0, visits = 0, samples = 0;
+  const float uninit = INFINITY;
+  double last_exit = 0;  // per call, NOT per ray: a ray that visits no voxel leaves the previous ray's (RayMapperOccupancy.cpp:79,190)
+  for (uint32_t i = 0; i < b.n; ++i)
+  {
+    double start[3], end[3];
+    loadRay(b, i, start, end);
+    unsigned filter_flags = 0;
+    if (!applyRayFilter(mp, start, end, filter_flags))
+    {
+      continue;
+    }
+    ++accepted;
+    const bool include_sample_in_ray = (filter_flags & kRffClippedEnd) || (b.ray_flags & OHMB200_RF_END_POINT_AS_FREE);
+    unsigned walk_flags = (!include_sample_in_ray) ? kExcludeEndVoxel : 0u;
+    walk_flags |= (b.ray_flags & OHMB200_RF_EXCLUDE_ORIGIN) ? kExcludeStartVoxel : 0u;
+    bool stop = false;
+    Key skey, ekey;
+    if (!(b.ray_flags & OHMB200_RF_EXCLUDE_RAY) && voxelKey(g, start, skey) && voxelKey(g, end, ekey))
+    {
+      unsigned long long last_region = kEmptyKey;
+      int slot = -1;
+      walkLine(g, start, end, skey, ekey, walk_flags, [&](const Key &k, double enter, double exit) {
+        const unsigned long long rk = packRegion(k.r[0], k.r[1], k.r[2]);
+        if (rk != last_region)
+        {
+          last_region = rk;
+          slot = regionSlot(dm, rk);
+        }
+        last_exit = exit;
+        ++visits;
+        if (slot < 0)
+        {
+          return;
+        }
+        const size_t vid = (size_t)slot * g.vpr + voxelIndex(g, k);
+        const float v = dm.occupancy[vid];
+        const bool occupied = v != uninit && v >= mp.threshold_value;
+        // occupancyAdjustMiss with null_update = stop (VoxelOccupancyCompute.h:110-120)
+        dm.occupancy[vid] = stop ? ((v != uninit) ? fmaxf(mp.min_value, v + 0.0f) : v) : missOnce(v, mp, b.ray_flags);
+        if (dm.traversal)
+        {
+          dm.traversal[vid] += (float)(exit - enter);
+        }
+        stop = stop || ((b.ray_flags & OHMB200_RF_STOP_ON_FIRST_OCCUPIED) && occupied);
+      });
+    }
+    if (stop || include_sample_in_ray || (b.ray_flags & OHMB200_RF_EXCLUDE_SAMPLE) || !voxelKey(g, end, ekey))
+    {
+      continue;
+    }
+    const int slot = regionSlot(dm, packRegion(ekey.r[0], ekey.r[1], ekey.r[2]));
+    if (slot < 0)
+    {
+      continue;
+    }
+    const size_t vid = (size_t)slot * g.vpr + voxelIndex(g, ekey);
+    dm.occupancy[vid] = hitOnce(dm.occupancy[vid], mp, b.ray_flags);
+    uint32_t sample_count = 0;
+    if (dm.mean)
+    {
+      uint2 mean = dm.mean[vid];
+      const double local_pt[3] = { end[0] - voxelCentreAxis(g, ekey.r[0], ekey.l[0], 0),
+                                   end[1] - voxelCentreAxis(g, ekey.r[1], ekey.l[1], 1),
+                                   end[2] - voxelCentreAxis(g, ekey.r[2], ekey.l[2], 2) };
+      mean.x = subVoxelUpdate(mean.x, mean.y, local_pt, g.res);
+      sample_count = mean.y;
+      ++mean.y;
+      dm.mean[vid] = mean;
+    }
+    if (dm.traversal)
+    {
+      const double d[3] = { end[0] - start[0], end[1] - start[1], end[2] - start[2] };
+      dm.traversal[vid] += (float)(sqrt((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]) - last_exit);
+    }
+    if (dm.touch_time && b.timestamps)
+    {
+      dm.touch_time[vid] = encodeTouchTime(b.time_base, b.timestamps[i]);
+    }
+    if (dm.incident)
+    {
+      dm.incident[vid] = updateIncidentNormal(dm.incident[vid], (float)(start[0] - end[0]), (float)(start[1] - end[1]),
+                                              (float)(start[2] - end[2]), sample_count);
+    }
+    ++samples;
+  }
+  atomicAdd(&b.counters->rays_accepted, accepted);
+  atomicAdd(&b.counters->voxel_visits, visits);
+  atomicAdd(&b.counters->sample_updates, samples);
 }
 
 // Fold the per-voxel miss counts of every region walked this batch into the occupancy layer.
@@ -851,13 +974,14 @@ enum KernelId
   kKTsdfReplay,
   kKNdtGauss,
   kKNdtClamp,
+  kKOrdered,
   kKernelCount
 };
 static const char *kKernelNames[kKernelCount] = { "prepSamples",  "radixSort",     "markRuns",      "walkRays",
                                                   "applySamples", "resolveMisses", "gatherRegions", "fillFloat",
                                                   "prepRays",     "prepSegments",  "planRegions",   "emitSegments",  "walkRegions",
                                                   "linkRecords",  "scatterRecords", "markTsdfNear",  "clearTouchedBits", "replayTsdf",
-                                                  "ndtGaussianMisses", "ndtClampGaussians" };
+                                                  "ndtGaussianMisses", "ndtClampGaussians", "integrateOrdered" };
 static_assert(kKernelCount <= OHMB200_KERNEL_SLOTS, "raise OHMB200_KERNEL_SLOTS");
 
 struct ohmb200_map
@@ -870,6 +994,8 @@ struct ohmb200_map
   TileLayout tile;        // layout of the shared-memory counter tile
   int walk_ctas_per_sm = 1;
   uint32_t heavy_run = 16;
+  uint32_t seg_factor = 96;     // segments per ray the batch's segment list is sized for (doubled after an overflow)
+  uint32_t record_factor = 24;  // ordered-miss records per ray, likewise
   int producer = 1;  // 1 = prepSegments (one thread per ray); 2 = one thread per crossing (OHMB200_PRODUCER=2, experimental)
   uint32_t *tsdf_near = nullptr;  // TSDF: per-batch bit per voxel, "visited near a sample in this batch"
   size_t voxel_bit_bytes = 0;     // size of dm.voxel_bits (and of tsdf_near)
@@ -912,6 +1038,8 @@ struct ohmb200_map
   size_t scratch_rays = 0;
   void *cub_temp = nullptr;
   size_t cub_temp_bytes = 0;
+  void *carry_temp = nullptr;  // scan storage of carryLastExit (traversal layer)
+  size_t carry_temp_bytes = 0;
   int sort_bits = 32;
   // host -> device input staging (double buffered)
   double *d_rays[2] = {};
@@ -1171,12 +1299,17 @@ int ensureScratch(ohmb200_map *m, size_t n)
   rc |= deviceAlloc(b.run_head, cap);
   rc |= deviceAlloc(b.interval_count, 2 * cap + 1);
   b.tail_overflow = b.interval_count + cap;  // re-pointed at interval_count + n by every batch
-  b.record_capacity = (uint32_t)std::min<size_t>(std::max<size_t>(cap * 24, 1u << 20), 1u << 28);
+  b.record_capacity = (uint32_t)std::min<size_t>(std::max<size_t>(cap * m->record_factor, 1u << 20), 1u << 28);
   rc |= deviceAlloc(b.record_ray, b.record_capacity);
   rc |= deviceAlloc(b.record_next, b.record_capacity);
   if (m->dm.traversal)
   {
     rc |= deviceAlloc(b.last_exit, cap);
+    cudaFree(m->carry_temp);
+    m->carry_temp = nullptr;
+    m->carry_temp_bytes = 0;
+    cub::DeviceScan::InclusiveScan(nullptr, m->carry_temp_bytes, b.last_exit, b.last_exit, CarryValid(), (int)cap, m->stream);
+    rc |= cudaMalloc(&m->carry_temp, std::max<size_t>(m->carry_temp_bytes, 16)) == cudaSuccess ? 0 : 1;
   }
   if (m->algo == 1)
   {
@@ -1196,7 +1329,7 @@ int ensureScratch(ohmb200_map *m, size_t n)
       rc |= deviceAlloc(b.ray_length, cap);
     }
     rc |= deviceAlloc(b.record_vid, b.record_capacity);
-    b.seg_capacity = (uint32_t)std::min<size_t>(cap * 96, 0xFFFFFFF0u);
+    b.seg_capacity = (uint32_t)std::min<size_t>(cap * m->seg_factor, 0xFFFFFFF0u);
     rc |= deviceAlloc(b.segments, b.seg_capacity);
     b.stage_stride = (uint32_t)cap;
     rc |= deviceAlloc(b.stage, (size_t)kStageSegments * cap);
@@ -1248,6 +1381,15 @@ int ensureScratch(ohmb200_map *m, size_t n)
   return OHMB200_OK;
 }
 
+// Rays that walked no voxel take the exit range of the nearest earlier ray that did (see staleExit).
+int carryLastExit(ohmb200_map *m, size_t n, cudaStream_t s)
+{
+  size_t temp = m->carry_temp_bytes;
+  CUDA_TRY(cub::DeviceScan::InclusiveScan(m->carry_temp, temp, m->batch.last_exit, m->batch.last_exit, CarryValid(), (int)n, s));
+  ++m->launches;
+  return OHMB200_OK;
+}
+
 int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_intensities, const double *d_timestamps,
                 unsigned ray_flags)
 {
@@ -1274,6 +1416,29 @@ int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_i
   const unsigned threads = 128;
   const unsigned blocks = (unsigned)((n + threads - 1) / threads);
   const bool has_samples = m->mode != OHMB200_MODE_TSDF;
+
+  if ((ray_flags & OHMB200_RF_STOP_ON_FIRST_OCCUPIED) && m->mode == OHMB200_MODE_OCCUPANCY)
+  {
+    // order-dependent across rays: the exact, sequential path (see integrateOrdered)
+    if (m->dm.part_world > 1)
+    {
+      return setError(OHMB200_E_INVALID, "kRfStopOnFirstOccupied needs the whole map on one GPU: a ray's stop depends on "
+                                         "voxels of every region it crosses");
+    }
+    if (!m->store.empty())
+    {
+      return setError(OHMB200_E_INVALID, "kRfStopOnFirstOccupied is not available while part of the map is paged out");
+    }
+    CUDA_TRY(cudaMemsetAsync(&m->d_counters->record_count, 0, sizeof(uint32_t) * kPerBatchCounterWords, s));
+    {
+      KernelScope scope(m, kKOrdered);
+      integrateOrdered<<<1, 32, 0, s>>>(m->dm, m->geom, m->mp, b);
+    }
+    CUDA_TRY(cudaGetLastError());
+    m->rays_in += n;
+    ++m->batches;
+    return OHMB200_OK;
+  }
 
   if (m->use_graphs && !m->capturing && m->algo == 1 && has_samples && !m->profiling && m->store.empty())
   {
@@ -1358,6 +1523,14 @@ int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_i
     {
       KernelScope scope(m, kKPrepRays);
       prepRays<<<blocks, threads, 0, s>>>(m->dm, m->geom, m->mp, b, m->mode);
+    }
+    if (b.last_exit)
+    {
+      rc = carryLastExit(m, n, s);
+      if (rc)
+      {
+        return rc;
+      }
     }
     // The sample path (sort -> run heads) and the segment path (plan -> scatter) only meet at walkRegions: run them
     // on two streams.  (With per-kernel profiling on they are serialised so that the event pairs stay meaningful.)
@@ -1537,6 +1710,14 @@ int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_i
   {
     KernelScope scope(m, kKWalk);
     walkRays<<<blocks, threads, 0, s>>>(m->dm, m->geom, m->mp, b);
+  }
+  if (b.last_exit)
+  {
+    rc = carryLastExit(m, n, s);
+    if (rc)
+    {
+      return rc;
+    }
   }
   if (has_samples)
   {
@@ -2188,7 +2369,7 @@ void ohmb200_destroy(ohmb200_map *m)
   void *to_free[] = { m->dm.keys,       m->dm.region_stamp, m->dm.new_slots,    m->dm.pending,      b.touched_list,   m->d_counters,
                       b.keys_in,        b.keys_out,         b.vals_in,          b.vals_out,       b.run_list,
                       b.run_head,       b.interval_count,   b.interval_offset,  b.sorted_rays,   b.record_ray,     b.record_next,
-                      b.last_exit,      m->cub_temp,        m->d_rays[0],       m->d_rays[1],     m->d_intensities[0],
+                      b.last_exit,      m->carry_temp,      m->cub_temp,        m->d_rays[0],       m->d_rays[1],     m->d_intensities[0],
                       m->d_intensities[1], m->d_timestamps[0], m->d_timestamps[1], m->d_gather,    m->d_gather_slots,
                       b.recs,           b.ray_length,       b.record_vid,       b.seg_count,      b.seg_offset,
                       b.seg_cursor,     b.sample_begin,     b.segments,         b.items,            b.record_keys,    b.record_keys_sorted, b.gauss_keys,
@@ -2434,9 +2615,27 @@ int ohmb200_sync(ohmb200_map *m)
   {
     return setError(OHMB200_E_CACHE_FULL, "region table full (%u slots): raise device_bytes", m->dm.capacity);
   }
-  if (m->h_counters->overflow_seen)
+  if (const int seen = m->h_counters->overflow_seen)
   {
-    return setError(OHMB200_E_OVERFLOW, "a per-batch segment/record list overflowed: results are incomplete; use smaller batches");
+    // reported once; the lists are grown for the batches that follow
+    CUDA_TRY(cudaMemsetAsync(&m->d_counters->overflow_seen, 0, sizeof(int), m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    if (seen & 2)
+    {
+      m->seg_factor = std::min<uint32_t>(m->seg_factor * 2u, 4096u);
+    }
+    if (seen & 1)
+    {
+      m->record_factor = std::min<uint32_t>(m->record_factor * 2u, 1024u);
+    }
+    m->scratch_rays = 0;  // the next batch reallocates its scratch with the new factors
+    if (seen & 1)
+    {
+      return setError(OHMB200_E_OVERFLOW, "a per-batch list of ordered records overflowed: the results of that batch are "
+                                          "incomplete (the list has been enlarged; use smaller batches)");
+    }
+    return setError(OHMB200_E_OVERFLOW, "a batch cut into more region segments than its list holds was dropped whole: "
+                                        "integrate it again (the list has been enlarged to %u segments per ray)", m->seg_factor);
   }
   return OHMB200_OK;
 }
@@ -2970,7 +3169,9 @@ int ohmb200_write_region(ohmb200_map *m, const int16_t key_xyz[3], int layer, co
     }
   }
   int *d_slot = (int *)&m->d_counters->record_count;  // scratch word, reset before every batch
-  insertRegion<<<1, 1, 0, m->stream>>>(m->dm, key, d_slot);
+  DeviceMap dm_insert = m->dm;
+  dm_insert.new_slots = nullptr;  // the per-batch list of new regions is not this call's business (and is not reset here)
+  insertRegion<<<1, 1, 0, m->stream>>>(dm_insert, key, d_slot);
   int slot = -1;
   CUDA_TRY(cudaMemcpyAsync(&slot, d_slot, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
   CUDA_TRY(cudaStreamSynchronize(m->stream));

@@ -153,7 +153,11 @@ __device__ inline int regionSlot(const DeviceMap &m, unsigned long long key)
           atomicAdd(m.region_count, 1ull);
           if (m.new_slots)
           {
-            m.new_slots[atomicAdd(m.new_count, 1u)] = target;
+            const uint32_t at = atomicAdd(m.new_count, 1u);
+            if (at < m.capacity)
+            {
+              m.new_slots[at] = target;
+            }
           }
           return (int)target;
         }
@@ -177,7 +181,11 @@ __device__ inline int regionSlot(const DeviceMap &m, unsigned long long key)
           atomicAdd(m.region_count, 1ull);
           if (m.new_slots)
           {
-            m.new_slots[atomicAdd(m.new_count, 1u)] = (uint32_t)tomb;
+            const uint32_t at = atomicAdd(m.new_count, 1u);
+            if (at < m.capacity)
+            {
+              m.new_slots[at] = (uint32_t)tomb;
+            }
           }
           return tomb;
         }

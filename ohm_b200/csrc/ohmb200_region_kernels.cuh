@@ -117,7 +117,33 @@ __global__ void __launch_bounds__(128) prepRays(DeviceMap dm, Geom g, MapParams 
     }
     if (b.last_exit)
     {
-      b.last_exit[i] = 0;
+      // Exit range of the last voxel the walk visits, in closed form (the sample's owner need not have walked it):
+      // the end voxel's exit is the walk's length; with the end voxel excluded the last visit ends on the walk's final
+      // step, the latest of the per-axis last-step times.  NaN = the ray visits nothing (see staleExit).
+      double last = nan("");
+      if (rec.flags & kRecValid)
+      {
+        const int steps = (int)rec.total[0] + (int)rec.total[1] + (int)rec.total[2];
+        if (!(rec.flags & kRecExcludeEnd))
+        {
+          const double d[3] = { end[0] - start[0], end[1] - start[1], end[2] - start[2] };
+          const double len2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+          last = (len2 > 1e-6) ? sqrt(len2) : 0;
+        }
+        else if (steps - ((rec.flags & kRecExcludeStart) ? 1 : 0) > 0)
+        {
+          last = -INFINITY;
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+          {
+            if (rec.total[a])
+            {
+              last = fmax(last, stepTime(rec.initial[a], rec.delta[a], (int)rec.total[a] - 1));
+            }
+          }
+        }
+      }
+      b.last_exit[i] = last;
     }
   }
   __syncwarp();
@@ -447,6 +473,8 @@ __global__ void __launch_bounds__(1024) planRegions(DeviceMap dm, Batch b, uint3
   __shared__ typename Scan::TempStorage scan_storage;
   __shared__ uint32_t carry;
   const uint32_t touched = b.counters->touched_count;
+  // the batch's age for paging, counted on the device (a replayed batch graph carries no host-side stamp)
+  const uint32_t stamp = b.counters->batch_stamp + 1u;
   if (threadIdx.x == 0)
   {
     carry = 0;
@@ -462,7 +490,7 @@ __global__ void __launch_bounds__(1024) planRegions(DeviceMap dm, Batch b, uint3
     if (t < touched)
     {
       b.seg_offset[slot] = carry + offset;
-      dm.region_stamp[slot] = b.stamp;  // walked by this batch: the age paging evicts by
+      dm.region_stamp[slot] = stamp;  // walked by this batch: the age paging evicts by
     }
     __syncthreads();
     if (threadIdx.x == 0)
@@ -474,11 +502,19 @@ __global__ void __launch_bounds__(1024) planRegions(DeviceMap dm, Batch b, uint3
   if (threadIdx.x == 0)
   {
     b.counters->segment_total = carry;
+    b.counters->batch_stamp = stamp;
     if (carry > b.seg_capacity)
     {
       b.counters->segment_overflow = 1;
-      b.counters->overflow_seen = 1;
+      atomicOr(&b.counters->overflow_seen, 2);
     }
+  }
+  if (carry > b.seg_capacity)
+  {
+    // More segments than the batch's list holds: no work items are made, so no walk kernel reads past the list, and
+    // the sample replay kernels skip the batch too (they test segment_overflow) — the batch is dropped WHOLE and
+    // ohmb200_sync reports OHMB200_E_OVERFLOW (the list is grown for the batches that follow).
+    return;
   }
   // Work items in decreasing size classes so that the long items start first and the tail is made of small ones.
   // Item size: kMaxSegmentsPerItem, unless that leaves fewer than two items per persistent CTA (a small batch, or one
@@ -1282,7 +1318,7 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegions(cons
             else
             {
               b.counters->record_overflow = 1;
-              b.counters->overflow_seen = 1;
+              atomicOr(&b.counters->overflow_seen, 1);
             }
           }
         };
@@ -1295,10 +1331,6 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegions(cons
                                 count_visit(tile_base + 2u * (uint32_t)(l[0] + l[1] * tl.row + l[2] * tl.slab),
                                             (l[0] & 1) ? 0x10000u : 1u);
                                 atomicAdd(&dm.traversal[vbase + idx], (float)(t_exit - t_enter));
-                                if (last_of_ray)
-                                {
-                                  b.last_exit[ray] = t_exit;
-                                }
                               });
         }
         else
@@ -1603,7 +1635,7 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegionsNdt(c
             else
             {
               b.counters->record_overflow = 1;
-              b.counters->overflow_seen = 1;
+              atomicOr(&b.counters->overflow_seen, 1);
             }
           }
           else if ((kind[(offset - tile_base) >> 6] >> (((offset - tile_base) >> 1) & 31u)) & 1u)
@@ -1617,7 +1649,7 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegionsNdt(c
             else
             {
               b.counters->record_overflow = 1;
-              b.counters->overflow_seen = 1;
+              atomicOr(&b.counters->overflow_seen, 1);
             }
           }
         };
@@ -1630,10 +1662,6 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegionsNdt(c
                                 count_visit(tile_base + 2u * (uint32_t)(l[0] + l[1] * tl.row + l[2] * tl.slab),
                                             (l[0] & 1) ? 0x10000u : 1u);
                                 atomicAdd(&dm.traversal[vbase + idx], (float)(t_exit - t_enter));
-                                if (last_of_ray)
-                                {
-                                  b.last_exit[ray] = t_exit;
-                                }
                               });
         }
         else
@@ -1850,7 +1878,7 @@ __device__ __forceinline__ unsigned replayNdtRun(const DeviceMap &dm, const Geom
     {
       const double d[3] = { end[0] - start[0], end[1] - start[1], end[2] - start[2] };
       const double len = sqrt((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]);
-      traversal_add += (float)(len - b.last_exit[ray]);
+      traversal_add += (float)(len - staleExit(b.last_exit[ray]));
     }
     if (dm.touch_time && b.timestamps)
     {
@@ -1901,7 +1929,7 @@ __global__ void __launch_bounds__(128) applySamplesNdt(DeviceMap dm, Geom g, Map
 {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned samples = 0;
-  if (t < b.counters->run_count)
+  if (t < b.counters->run_count && !b.counters->segment_overflow)
   {
     const uint32_t head = b.run_list[t];
     const uint32_t vid = b.keys_out[head];

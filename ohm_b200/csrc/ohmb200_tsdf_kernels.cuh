@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegionsTsdf(
             else
             {
               b.counters->record_overflow = 1;
-              b.counters->overflow_seen = 1;
+              atomicOr(&b.counters->overflow_seen, 1);
             }
           }
         });

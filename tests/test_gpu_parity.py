@@ -109,6 +109,10 @@ def test_region_dimensions_and_origin(gpu, dims):
     gm.RF_END_POINT_AS_FREE, gm.RF_EXCLUDE_ORIGIN, gm.RF_EXCLUDE_SAMPLE, gm.RF_EXCLUDE_RAY,
     gm.RF_EXCLUDE_UNOBSERVED, gm.RF_EXCLUDE_FREE, gm.RF_EXCLUDE_OCCUPIED, gm.RF_REVERSE_WALK,
     gm.RF_EXCLUDE_ORIGIN | gm.RF_END_POINT_AS_FREE,
+    # kRfStopOnFirstOccupied: order-dependent across rays, integrated by the exact sequential kernel (integrateOrdered)
+    gm.RF_STOP_ON_FIRST_OCCUPIED, gm.RF_STOP_ON_FIRST_OCCUPIED | gm.RF_END_POINT_AS_FREE,
+    # ohm::ClearingPattern::kDefaultRayFlags (ohm/ClearingPattern.h:45)
+    gm.RF_END_POINT_AS_FREE | gm.RF_STOP_ON_FIRST_OCCUPIED | gm.RF_EXCLUDE_FREE | gm.RF_EXCLUDE_UNOBSERVED,
 ])
 def test_ray_flags(gpu, flags):
     g, c = make_pair(0.25)
@@ -359,3 +363,78 @@ def test_secondary_sample_mapper(gpu):
     plain, _ = make_pair(0.25)
     with pytest.raises(ohm_b200.OhmB200Error):
         plain.integrate_secondary(rays[:10])
+
+
+def test_stop_on_first_occupied_all_layers(gpu):
+    """kRfStopOnFirstOccupied with every sample layer: a stopped ray loses its sample — mean, touch time, incident normal
+    and the sample's traversal share included (ohm/RayMapperOccupancy.cpp:183,234); traversal still accumulates along
+    the stopped part of the walk.  The ordered kernel keeps the reference's per-call last_exit_range, so traversal is
+    bit-exact here."""
+    layers = [gm.LAYER_OCCUPANCY, gm.LAYER_MEAN, gm.LAYER_TRAVERSAL, gm.LAYER_TOUCH_TIME, gm.LAYER_INCIDENT]
+    g, c = make_pair(0.25, layers=layers)
+    n = 3000
+    rays = random_rays(n, 8.0, seed=31)
+    ts = 5.0 + np.arange(n) * 1e-3
+    integrate_both(g, c, rays[:2 * 1500], timestamps=ts[:1500])
+    for lo, hi in ((1500, 2400), (2400, 3000), (0, 1500)):
+        g.integrate_rays(rays[2 * lo:2 * hi], timestamps=ts[lo:hi], ray_flags=gm.RF_STOP_ON_FIRST_OCCUPIED)
+        c.integrate_rays(rays[2 * lo:2 * hi], timestamps=ts[lo:hi], ray_flags=gm.RF_STOP_ON_FIRST_OCCUPIED)
+    g.sync_voxels()
+    compare_maps(g, c, tol_layers={gm.LAYER_TRAVERSAL: (2e-5, 1e-6)})
+    st = check_counts(g, c)
+    assert st["sample_updates"] < 1500 + 3000      # some rays did stop
+    # sharded maps cannot honour the flag (a ray's stop depends on regions of other owners): refused, not ignored
+    p = ohm_b200.GpuMap(0.25, device_bytes=1 << 28)
+    p.set_partition(0, 2)
+    with pytest.raises(ohm_b200.OhmB200Error):
+        p.integrate_rays(rays[:64], ray_flags=gm.RF_STOP_ON_FIRST_OCCUPIED)
+
+
+def test_traversal_of_rays_that_walk_no_voxel(gpu):
+    """A ray whose sensor and sample share a voxel walks nothing; the reference then subtracts the exit range the
+    PREVIOUS ray of the call left behind from the sample's traversal share (last_exit_range is a variable of the
+    whole integrateRays call, ohm/RayMapperOccupancy.cpp:79,190,309).  Reproduced: closed-form exit ranges in prepRays
+    + one carry-forward scan."""
+    layers = [gm.LAYER_OCCUPANCY, gm.LAYER_TRAVERSAL]
+    g, c = make_pair(0.25, layers=layers)
+    rng = np.random.RandomState(77)
+    n = 4000
+    rays = random_rays(n, 6.0, seed=41)
+    inside = rng.choice(n, size=1200, replace=False)          # these rays stay inside one voxel
+    centres = (np.floor(rng.uniform(-5, 5, size=(1200, 3)) / 0.25) + 0.5) * 0.25
+    rays[2 * inside] = centres + rng.uniform(-0.1, 0.1, size=(1200, 3))
+    rays[2 * inside + 1] = centres + rng.uniform(-0.1, 0.1, size=(1200, 3))
+    rays[0] = rays[1] = centres[0]                            # the first ray of the call: nothing before it
+    # one call on both sides: the carried value is per call
+    g.integrate_rays(rays)
+    c.integrate_rays(rays)
+    g.integrate_rays(rays[::-1].copy())
+    c.integrate_rays(rays[::-1].copy())
+    g.sync_voxels()
+    compare_maps(g, c, tol_layers={gm.LAYER_TRAVERSAL: (2e-5, 1e-6)})
+    check_counts(g, c)
+
+
+def test_segment_list_overflow_drops_the_batch_and_recovers(gpu):
+    """Tiny regions and long rays cut into more segments than the batch's list holds (96 per ray): the batch is
+    dropped WHOLE — no out-of-bounds access, no partial update — ohmb200_sync reports OHMB200_E_OVERFLOW once, the list
+    is enlarged, and the same batch integrated again gives the oracle's map."""
+    dims = (2, 2, 2)
+    g, c = make_pair(0.1, region_dim=dims, device_bytes=256 << 20)
+    rays = random_rays(7000, 40.0, seed=51)   # ~300 region crossings per ray: 2.1 M segments > 16384 x 96
+    g.integrate_rays(rays)
+    with pytest.raises(ohm_b200.OhmB200Error, match="segment"):
+        g.sync_voxels()
+    g.sync_voxels()                       # reported once
+    occ = g.dump()
+    assert all(np.all(np.isinf(v[gm.LAYER_OCCUPANCY])) for v in occ.values())   # nothing was applied
+    g.clear()
+    for _ in range(4):                    # the list doubles per overflow: 96 -> 192 -> 384 segments per ray
+        g.integrate_rays(rays)
+        try:
+            g.sync_voxels()
+            break
+        except ohm_b200.OhmB200Error:
+            g.clear()
+    c.integrate_rays(rays)
+    compare_maps(g, c)

@@ -55,7 +55,9 @@ def test_all_sample_layers_with_timestamps():
     assert o.first_ray_time() == r.first_ray_time() == 100.0
 
 
-@pytest.mark.parametrize("flags", [0, 1 << 0, 1 << 2, 1 << 3, 1 << 4, 1 << 5, 1 << 6, 1 << 7, (1 << 2) | (1 << 0)])
+# bit 1 = kRfStopOnFirstOccupied; 0x63 = ohm::ClearingPattern::kDefaultRayFlags (ohm/ClearingPattern.h:45)
+@pytest.mark.parametrize("flags", [0, 1 << 0, 1 << 1, 1 << 2, 1 << 3, 1 << 4, 1 << 5, 1 << 6, 1 << 7, (1 << 2) | (1 << 0),
+                                   (1 << 1) | (1 << 0), 0x63])
 def test_ray_flags(flags):
     o, r = po.OracleMap(0.25), pr.ReferenceMap(0.25)
     rays = random_rays(4096, 12.0, 7)
