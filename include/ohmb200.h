@@ -65,7 +65,9 @@ enum ohmb200_ray_flag
 {
   OHMB200_RF_DEFAULT = 0,
   OHMB200_RF_END_POINT_AS_FREE = 1u << 0,
-  OHMB200_RF_STOP_ON_FIRST_OCCUPIED = 1u << 1,
+  OHMB200_RF_STOP_ON_FIRST_OCCUPIED = 1u << 1, /* order-dependent across rays: integrated by one thread, ray after ray,
+                                                * exactly as RayMapperOccupancy.cpp:183,234 (ClearingPattern-sized batches);
+                                                * refused (OHMB200_E_INVALID) on a sharded or paged-out map */
   OHMB200_RF_EXCLUDE_ORIGIN = 1u << 2,
   OHMB200_RF_EXCLUDE_SAMPLE = 1u << 3,
   OHMB200_RF_EXCLUDE_RAY = 1u << 4,
@@ -83,7 +85,11 @@ enum ohmb200_error
   OHMB200_E_NO_DEVICE = -3,   /* no sm_100 device: gpuOk() == false, calls are no-ops (GpuMap.cpp:548-551) */
   OHMB200_E_CACHE_FULL = -4,  /* region table full (GpuLayerCache kCacheFull, GpuMap.cpp:935-975) */
   OHMB200_E_NOT_FOUND = -5,   /* region/layer absent */
-  OHMB200_E_OVERFLOW = -6     /* an internal per-batch list overflowed; batch was split and retried */
+  OHMB200_E_OVERFLOW = -6     /* reported once by ohmb200_sync.  "segment list": a batch cut into more region segments than
+                               * its list holds (tiny regions, very long rays) was dropped WHOLE - nothing of it was applied -
+                               * and the list has been doubled: integrate that batch again.  "ordered records": too many
+                               * misses on voxels that are also hit in the same batch; that batch's results are incomplete,
+                               * the list has been doubled for the batches that follow */
 };
 
 /* Map + mapper parameters.  Mirrors OccupancyMapDetail (ohm/private/OccupancyMapDetail.h:47-84),
@@ -158,8 +164,10 @@ OHMB200_API int ohmb200_get_params(const ohmb200_map *map, ohmb200_params *param
 /* ohm::RayMapper::integrateRays (ohm/RayMapper.h:57-58) as implemented by GpuMap::integrateRays
  * (ohmgpu/GpuMap.cpp:540-875).  `rays` = interleaved (origin, sample) f64 xyz triples in HOST memory,
  * `element_count` = 2 x ray count; `intensities` / `timestamps` are per ray and nullable.  Asynchronous with
- * respect to the device: inputs are copied to pinned staging before return.  Returns the number of points
- * integrated (2 x accepted rays, GpuMap.cpp:874) or 0 on failure. */
+ * respect to the device: inputs are copied to device staging before return.  Returns element_count (what the CPU
+ * mappers return, RayMapperOccupancy.cpp:338) or 0 on failure; the reference's GpuMap returns 2 x the rays its host-side
+ * filter accepted (GpuMap.cpp:874) - here the filter runs on the device after the call has returned, and callers only
+ * test for zero; the accepted count is ohmb200_stats.rays_accepted. */
 OHMB200_API size_t ohmb200_integrate(ohmb200_map *map, const double *rays, size_t element_count,
                                      const float *intensities, const double *timestamps, unsigned ray_flags);
 
@@ -255,9 +263,48 @@ OHMB200_API int ohmb200_set_stream(ohmb200_map *map, void *cuda_stream);
 OHMB200_API int ohmb200_set_partition(ohmb200_map *map, int rank, int world);
 OHMB200_API int ohmb200_region_owner(const int16_t key_xyz[3], int world);
 
+/* ---- multi-GPU: the routed exchange (new capability; SURVEY §8e second option: "all-to-all of pre-cut segments") --------
+ * ohmb200_set_partition above shards the MAP but hands every GPU every ray.  The exchange shards the WORK too: each rank
+ * filters and cuts only ITS OWN rays and stores every region segment and every sample straight into the inbox of the GPU
+ * that owns the region (peer stores over NVLink into one device allocation per rank, exported as a CUDA IPC handle; the
+ * per-ray walk constants follow by copy engine).  The owner bins what it received and runs the single-GPU walk and
+ * replay kernels.  The cut is the exact region-boundary cut of the single-GPU path — the exact counterpart of the
+ * reference's clipped-end ray segments (ohmgpu/GpuMap.cpp:747-795, ohmgpu/gpu/AdjustOccupancy.cl:13-18) — so the union
+ * of the per-GPU maps equals one GPU, or the CPU mapper, integrating rank 0's rays, then rank 1's, ... bit for bit.
+ *
+ *   every rank:  ohmb200_exchange_open(map, rank, world, max_rays_per_rank, &mine)
+ *                all-gather the handles (any transport: torch.distributed, MPI, a pipe), in rank order
+ *                ohmb200_exchange_connect(map, handles, world)
+ *   every step:  ohmb200_exchange_send(map, own rays ...)    filter, cut, route; returns after queueing
+ *                ohmb200_exchange_integrate(map)             waits ON THE DEVICE for every rank's records of the step
+ *                                                            (a bounded spin: a missing peer cannot hang the GPU), then
+ *                                                            integrates them; returns after queueing
+ * Every rank must make the same sequence of steps (a rank with no rays sends an empty batch) with the same ray flags and
+ * the same presence of timestamps / intensities.  Occupancy and NDT maps (a TSDF map is sharded with ohmb200_set_partition).
+ * With timestamps, set the time base on every rank first (ohmb200_set_first_ray_time).  A single process may drive
+ * several maps (same or different devices): call send on all of them, then integrate on all of them.  While the exchange
+ * is open the plain integrate calls are refused; ohmb200_exchange_close (or ohmb200_destroy) releases it.
+ * world = 1 is valid (the exchange pipeline on one GPU). */
+#define OHMB200_EXCHANGE_HANDLE_BYTES 128
+typedef struct ohmb200_exchange_handle
+{
+  unsigned char bytes[OHMB200_EXCHANGE_HANDLE_BYTES];
+} ohmb200_exchange_handle;
+OHMB200_API int ohmb200_exchange_open(ohmb200_map *map, int rank, int world, size_t max_rays_per_rank,
+                                      ohmb200_exchange_handle *handle);
+OHMB200_API int ohmb200_exchange_connect(ohmb200_map *map, const ohmb200_exchange_handle *handles, int count);
+/* rays etc. in HOST memory (staged like ohmb200_integrate) / already in device memory */
+OHMB200_API size_t ohmb200_exchange_send(ohmb200_map *map, const double *rays, size_t element_count,
+                                         const float *intensities, const double *timestamps, unsigned ray_flags);
+OHMB200_API size_t ohmb200_exchange_send_device(ohmb200_map *map, const double *d_rays, size_t element_count,
+                                                const float *d_intensities, const double *d_timestamps,
+                                                unsigned ray_flags);
+OHMB200_API int ohmb200_exchange_integrate(ohmb200_map *map);
+OHMB200_API int ohmb200_exchange_close(ohmb200_map *map);
+
 /* Per-kernel CUDA-event timing on the map's stream (bench.py's roofline numbers).  When enabled every launch is
  * bracketed by events; ohmb200_kernel_times drains {name -> accumulated ms, launches}. */
-#define OHMB200_KERNEL_SLOTS 24
+#define OHMB200_KERNEL_SLOTS 40
 typedef struct ohmb200_kernel_time
 {
   char name[32];

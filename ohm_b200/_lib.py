@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("OHMB200_LIB") or os.path.join(HERE, "libohmb200.so")  # OHMB200_LIB: instrumented builds
 
-LAYER_COUNT = 9
+LAYER_COUNT = 10
 
 
 class Params(C.Structure):
@@ -46,6 +46,10 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "rays_in", "rays_accepted", "voxel_visits", "sample_updates", "ordered_records", "regions",
         "region_capacity", "batches", "kernel_launches")]
+
+
+class ExchangeHandle(C.Structure):
+    _fields_ = [("bytes", C.c_ubyte * 128)]
 
 
 class KernelTime(C.Structure):
@@ -93,6 +97,12 @@ SYMBOLS = [
     ("ohmb200_remove_region", C.c_int, [_vp, _kp]),
     ("ohmb200_paging_stats", C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                        C.POINTER(C.c_uint64)]),
+    ("ohmb200_exchange_open", C.c_int, [_vp, C.c_int, C.c_int, C.c_size_t, C.POINTER(ExchangeHandle)]),
+    ("ohmb200_exchange_connect", C.c_int, [_vp, C.POINTER(ExchangeHandle), C.c_int]),
+    ("ohmb200_exchange_send", C.c_size_t, [_vp, _vp, C.c_size_t, _vp, _vp, C.c_uint]),
+    ("ohmb200_exchange_send_device", C.c_size_t, [_vp, _vp, C.c_size_t, _vp, _vp, C.c_uint]),
+    ("ohmb200_exchange_integrate", C.c_int, [_vp]),
+    ("ohmb200_exchange_close", C.c_int, [_vp]),
     ("ohmb200_last_error", C.c_char_p, []),
     ("ohmb200_version", C.c_char_p, []),
 ]

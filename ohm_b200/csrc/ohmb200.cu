@@ -22,6 +22,8 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <unistd.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -631,6 +633,7 @@ __global__ void __launch_bounds__(256) resolveMisses(DeviceMap dm, Geom g, MapPa
 
 #include "ohmb200_region_kernels.cuh"
 #include "ohmb200_tsdf_kernels.cuh"
+#include "ohmb200_exchange.cuh"
 
 __global__ void fillFloat(float *dst, size_t n, float value)
 {
@@ -975,13 +978,20 @@ enum KernelId
   kKNdtGauss,
   kKNdtClamp,
   kKOrdered,
+  kKExPrepRays,
+  kKExRoute,
+  kKExSegments,
+  kKExWait,
+  kKExBin,
+  kKExEmit,
   kKernelCount
 };
 static const char *kKernelNames[kKernelCount] = { "prepSamples",  "radixSort",     "markRuns",      "walkRays",
                                                   "applySamples", "resolveMisses", "gatherRegions", "fillFloat",
                                                   "prepRays",     "prepSegments",  "planRegions",   "emitSegments",  "walkRegions",
                                                   "linkRecords",  "scatterRecords", "markTsdfNear",  "clearTouchedBits", "replayTsdf",
-                                                  "ndtGaussianMisses", "ndtClampGaussians", "integrateOrdered" };
+                                                  "ndtGaussianMisses", "ndtClampGaussians", "integrateOrdered",
+                                                  "exPrepRays", "exRouteSamples", "exPrepSegments", "exWait", "exBin", "exEmit" };
 static_assert(kKernelCount <= OHMB200_KERNEL_SLOTS, "raise OHMB200_KERNEL_SLOTS");
 
 struct ohmb200_map
@@ -1091,6 +1101,25 @@ struct ohmb200_map
   uint64_t known_batch = 0;
   uint32_t region_reserve = 0; // free slots a batch may need (ohmb200_set_region_reserve)
   uint64_t evicted = 0, paged_in = 0;
+  // Multi-GPU routed exchange (ohmb200_exchange.cuh)
+  struct Exchange
+  {
+    bool open = false, connected = false, pending = false;
+    int rank = 0, world = 1;
+    uint32_t per = 0, seg_cap = 0, step = 0;
+    char *arena = nullptr;
+    size_t arena_bytes = 0, parity_bytes = 0;
+    char *peer_base[kMaxWorld] = {};
+    bool peer_mapped[kMaxWorld] = {};  // opened with cudaIpcOpenMemHandle (to be closed)
+    uint32_t *out_counts = nullptr;    // [2 * kMaxWorld] segments / samples sent to each owner this step
+    unsigned long long *smp_key = nullptr;
+    int *abort = nullptr;
+    cudaStream_t stream = nullptr;     // the per-ray broadcast (copy engines) runs here, beside the cut
+    cudaEvent_t prepped = nullptr;
+    size_t n_own = 0;
+    unsigned ray_flags = 0;
+    bool has_timestamps = false, has_intensities = false;
+  } ex;
   // profiling
   bool profiling = false;
   std::vector<cudaEvent_t> event_pool;
@@ -1323,20 +1352,35 @@ int ensureScratch(ohmb200_map *m, size_t n)
     cudaFree(b.cross_pos);
     b.cross_pos = nullptr;
     b.ray_length = nullptr;
-    rc |= deviceAlloc(b.recs, cap);
-    if (m->dm.traversal)
+    b.recs = nullptr;
+    b.stage = nullptr;
+    b.stage_count = nullptr;
+    if (!m->ex.open)
     {
-      rc |= deviceAlloc(b.ray_length, cap);
+      rc |= deviceAlloc(b.recs, cap);
+      if (m->dm.traversal)
+      {
+        rc |= deviceAlloc(b.ray_length, cap);
+      }
     }
     rc |= deviceAlloc(b.record_vid, b.record_capacity);
     b.seg_capacity = (uint32_t)std::min<size_t>(cap * m->seg_factor, 0xFFFFFFF0u);
+    if (m->ex.open)
+    {
+      // an exchange map bins what its inboxes hold; the per-ray arrays (walk constants, lengths) live in the arena and
+      // the segments arrive cut: no staging planes
+      b.seg_capacity = (uint32_t)std::min<size_t>((size_t)m->ex.world * m->ex.seg_cap, 0xFFFFFFF0u);
+    }
     rc |= deviceAlloc(b.segments, b.seg_capacity);
     b.stage_stride = (uint32_t)cap;
-    rc |= deviceAlloc(b.stage, (size_t)kStageSegments * cap);
-    rc |= deviceAlloc(b.stage_count, cap);
-    if (m->producer == 2)
+    if (!m->ex.open)
     {
-      rc |= deviceAlloc(b.cross_pos, (size_t)kStageSegments * cap);
+      rc |= deviceAlloc(b.stage, (size_t)kStageSegments * cap);
+      rc |= deviceAlloc(b.stage_count, cap);
+      if (m->producer == 2)
+      {
+        rc |= deviceAlloc(b.cross_pos, (size_t)kStageSegments * cap);
+      }
     }
     b.item_capacity = m->dm.capacity + b.seg_capacity / 512 + 16;
     rc |= deviceAlloc(b.items, b.item_capacity);
@@ -1390,12 +1434,80 @@ int carryLastExit(ohmb200_map *m, size_t n, cudaStream_t s)
   return OHMB200_OK;
 }
 
+// The second half of an occupancy / NDT batch on the region-binned path: the segments are binned by region, the sample
+// pairs sorted (both streams joined).  Walk -> (NDT: Gaussian misses) -> link records -> sample replay.
+int launchWalkAndReplay(ohmb200_map *m, const Batch &b, cudaStream_t s, size_t n, bool has_samples)
+{
+  const unsigned threads = 128;
+  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  {
+    KernelScope scope(m, kKWalkRegions);
+    if ((m->mode == OHMB200_MODE_NDT || m->mode == OHMB200_MODE_NDT_TM))
+    {
+      CUDA_TRY(cudaMemsetAsync(b.gauss_keys, 0xFF, sizeof(unsigned long long) * b.gauss_capacity, s));
+      const auto kernel = m->dm.traversal ? walkRegionsNdt<true> : walkRegionsNdt<false>;
+      kernel<<<m->sm_count * m->walk_ctas_per_sm, kWalkThreads, m->tile_bytes, s>>>(m->dm, m->geom, m->mp, b, m->tile);
+    }
+    else
+    {
+      const auto kernel = m->dm.traversal ? walkRegions<true> : walkRegions<false>;
+      kernel<<<m->sm_count * m->walk_ctas_per_sm, kWalkThreads, m->tile_bytes, s>>>(m->dm, m->geom, m->mp, b, m->tile,
+                                                                                 has_samples ? 1 : 0);
+    }
+  }
+  if (m->mode == OHMB200_MODE_NDT || m->mode == OHMB200_MODE_NDT_TM)
+  {
+    {
+      KernelScope scope(m, kKNdtGauss);
+      ndtGaussianMisses<<<m->sm_count * 8, 128, 0, s>>>(m->dm, m->geom, m->mp, b);
+    }
+    {
+      KernelScope scope(m, kKNdtClamp);
+      ndtClampGaussians<<<m->sm_count * 4, 256, 0, s>>>(m->dm, m->mp, b);
+    }
+  }
+  if (has_samples)
+  {
+    const bool ndt_mode = m->mode == OHMB200_MODE_NDT || m->mode == OHMB200_MODE_NDT_TM;
+    {
+      KernelScope scope(m, kKLink);
+      linkRecords<<<m->sm_count * 4, 256, 0, s>>>(b, ndt_mode ? 1 : 0, m->geom.vpr);
+    }
+    if (ndt_mode)
+    {
+      // group the records by interval: exclusive scan of the interval counts, then one scatter
+      KernelScope scope(m, kKScatter);
+      size_t temp = m->cub_temp_bytes;
+      cub::DeviceScan::ExclusiveSum(m->cub_temp, temp, b.interval_count, b.interval_offset, (int)(2 * n + 1), s);
+      scatterRecords<<<m->sm_count * 4, 256, 0, s>>>(b);
+    }
+    {
+      KernelScope scope(m, kKSamples);
+      if ((m->mode == OHMB200_MODE_NDT || m->mode == OHMB200_MODE_NDT_TM))
+      {
+        applySamplesNdt<<<blocks, threads, 0, s>>>(m->dm, m->geom, m->mp, b);
+        applySamplesNdtHeavy<<<m->sm_count * 8, 128, 0, s>>>(m->dm, m->geom, m->mp, b);
+      }
+      else
+      {
+        applySamples<<<blocks, threads, 0, s>>>(m->dm, m->geom, m->mp, b);
+      }
+    }
+  }
+  return OHMB200_OK;
+}
+
 int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_intensities, const double *d_timestamps,
                 unsigned ray_flags)
 {
   if (n == 0)
   {
     return OHMB200_OK;
+  }
+  if (m->ex.open)
+  {
+    return setError(OHMB200_E_INVALID, "the map has an open exchange: integrate through ohmb200_exchange_send / "
+                                       "ohmb200_exchange_integrate (or ohmb200_exchange_close first)");
   }
   int rc = ensureScratch(m, n);
   if (rc)
@@ -1628,59 +1740,10 @@ int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_i
       ++m->batches;
       return OHMB200_OK;
     }
+    rc = launchWalkAndReplay(m, b, s, n, has_samples);
+    if (rc)
     {
-      KernelScope scope(m, kKWalkRegions);
-      if ((m->mode == OHMB200_MODE_NDT || m->mode == OHMB200_MODE_NDT_TM))
-      {
-        CUDA_TRY(cudaMemsetAsync(b.gauss_keys, 0xFF, sizeof(unsigned long long) * b.gauss_capacity, s));
-        const auto kernel = m->dm.traversal ? walkRegionsNdt<true> : walkRegionsNdt<false>;
-        kernel<<<m->sm_count * m->walk_ctas_per_sm, kWalkThreads, m->tile_bytes, s>>>(m->dm, m->geom, m->mp, b, m->tile);
-      }
-      else
-      {
-        const auto kernel = m->dm.traversal ? walkRegions<true> : walkRegions<false>;
-        kernel<<<m->sm_count * m->walk_ctas_per_sm, kWalkThreads, m->tile_bytes, s>>>(m->dm, m->geom, m->mp, b, m->tile,
-                                                                                   has_samples ? 1 : 0);
-      }
-    }
-    if (m->mode == OHMB200_MODE_NDT || m->mode == OHMB200_MODE_NDT_TM)
-    {
-      {
-        KernelScope scope(m, kKNdtGauss);
-        ndtGaussianMisses<<<m->sm_count * 8, 128, 0, s>>>(m->dm, m->geom, m->mp, b);
-      }
-      {
-        KernelScope scope(m, kKNdtClamp);
-        ndtClampGaussians<<<m->sm_count * 4, 256, 0, s>>>(m->dm, m->mp, b);
-      }
-    }
-    if (has_samples)
-    {
-      const bool ndt_mode = m->mode == OHMB200_MODE_NDT || m->mode == OHMB200_MODE_NDT_TM;
-      {
-        KernelScope scope(m, kKLink);
-        linkRecords<<<m->sm_count * 4, 256, 0, s>>>(b, ndt_mode ? 1 : 0, m->geom.vpr);
-      }
-      if (ndt_mode)
-      {
-        // group the records by interval: exclusive scan of the interval counts, then one scatter
-        KernelScope scope(m, kKScatter);
-        size_t temp = m->cub_temp_bytes;
-        cub::DeviceScan::ExclusiveSum(m->cub_temp, temp, b.interval_count, b.interval_offset, (int)(2 * n + 1), s);
-        scatterRecords<<<m->sm_count * 4, 256, 0, s>>>(b);
-      }
-      {
-        KernelScope scope(m, kKSamples);
-        if ((m->mode == OHMB200_MODE_NDT || m->mode == OHMB200_MODE_NDT_TM))
-        {
-          applySamplesNdt<<<blocks, threads, 0, s>>>(m->dm, m->geom, m->mp, b);
-          applySamplesNdtHeavy<<<m->sm_count * 8, 128, 0, s>>>(m->dm, m->geom, m->mp, b);
-        }
-        else
-        {
-          applySamples<<<blocks, threads, 0, s>>>(m->dm, m->geom, m->mp, b);
-        }
-      }
+      return rc;
     }
     CUDA_TRY(cudaGetLastError());
     m->rays_in += n;
@@ -2058,6 +2121,8 @@ void snapshotRegionCount(ohmb200_map *m)
   }
 }
 
+#include "ohmb200_exchange_host.inl"
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------
@@ -2364,6 +2429,7 @@ void ohmb200_destroy(ohmb200_map *m)
   }
   cudaSetDevice(m->device);
   cudaDeviceSynchronize();
+  exchangeClose(m);
   dropBatchGraphs(m);
   Batch &b = m->batch;
   void *to_free[] = { m->dm.keys,       m->dm.region_stamp, m->dm.new_slots,    m->dm.pending,      b.touched_list,   m->d_counters,
@@ -2614,6 +2680,17 @@ int ohmb200_sync(ohmb200_map *m)
   if (m->h_counters->table_full)
   {
     return setError(OHMB200_E_CACHE_FULL, "region table full (%u slots): raise device_bytes", m->dm.capacity);
+  }
+  if (m->ex.open)
+  {
+    int aborted = 0;
+    CUDA_TRY(cudaMemcpyAsync(&aborted, m->ex.abort, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    if (aborted)
+    {
+      CUDA_TRY(cudaMemsetAsync(m->ex.abort, 0, sizeof(int), m->stream));
+      return setError(OHMB200_E_CUDA, "exchange: a peer's records did not arrive within the wait bound; that step was dropped on this rank");
+    }
   }
   if (const int seen = m->h_counters->overflow_seen)
   {
@@ -3406,6 +3483,38 @@ int ohmb200_kernel_times(ohmb200_map *m, ohmb200_kernel_time *out, int capacity,
     memset(m->kernel_launches, 0, sizeof(m->kernel_launches));
   }
   return n;
+}
+
+int ohmb200_exchange_open(ohmb200_map *m, int rank, int world, size_t max_rays_per_rank, ohmb200_exchange_handle *handle)
+{
+  return exchangeOpen(m, rank, world, max_rays_per_rank, handle);
+}
+
+int ohmb200_exchange_connect(ohmb200_map *m, const ohmb200_exchange_handle *handles, int count)
+{
+  return exchangeConnect(m, handles, count);
+}
+
+size_t ohmb200_exchange_send_device(ohmb200_map *m, const double *d_rays, size_t element_count, const float *d_intensities,
+                                    const double *d_timestamps, unsigned ray_flags)
+{
+  return exchangeSend(m, d_rays, element_count, d_intensities, d_timestamps, ray_flags) == OHMB200_OK ? element_count : 0;
+}
+
+size_t ohmb200_exchange_send(ohmb200_map *m, const double *rays, size_t element_count, const float *intensities,
+                             const double *timestamps, unsigned ray_flags)
+{
+  return exchangeSendHost(m, rays, element_count, intensities, timestamps, ray_flags) == OHMB200_OK ? element_count : 0;
+}
+
+int ohmb200_exchange_integrate(ohmb200_map *m)
+{
+  return exchangeIntegrate(m);
+}
+
+int ohmb200_exchange_close(ohmb200_map *m)
+{
+  return exchangeClose(m);
 }
 
 }  // extern "C"

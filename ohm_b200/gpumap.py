@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import Params, Stats, KernelTime
+from ._lib import Params, Stats, KernelTime, ExchangeHandle
 
 LAYER_OCCUPANCY, LAYER_MEAN, LAYER_TRAVERSAL, LAYER_TOUCH_TIME, LAYER_INCIDENT = 0, 1, 2, 3, 4
 LAYER_COVARIANCE, LAYER_INTENSITY, LAYER_HIT_MISS, LAYER_TSDF, LAYER_SECONDARY = 5, 6, 7, 8, 9
@@ -319,6 +319,51 @@ class GpuMap:
         key = np.ascontiguousarray(key, dtype=np.int16)
         return self.L.ohmb200_region_owner(key.ctypes.data_as(C.POINTER(C.c_int16)), int(world))
 
+    # -- multi-GPU routed exchange (include/ohmb200.h: ohmb200_exchange_*) ---------------------------------------
+    def exchange_open(self, rank, world, max_rays_per_rank):
+        """Allocate this map's inboxes; returns the 128-byte handle the peers need (bytes)."""
+        h = ExchangeHandle()
+        self._check(self.L.ohmb200_exchange_open(self.h, int(rank), int(world), int(max_rays_per_rank), C.byref(h)))
+        return bytes(h.bytes)
+
+    def exchange_connect(self, handles):
+        """`handles`: every rank's handle (bytes), in rank order."""
+        arr = (ExchangeHandle * len(handles))()
+        for i, raw in enumerate(handles):
+            C.memmove(C.byref(arr[i]), bytes(raw), 128)
+        self._check(self.L.ohmb200_exchange_connect(self.h, arr, len(handles)))
+
+    def exchange_send(self, rays, intensities=None, timestamps=None, ray_flags=RF_DEFAULT):
+        """Phase 1 of a step: this rank's own rays (host arrays) are filtered, cut and routed to the region owners."""
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 3)
+        if intensities is not None:
+            intensities = np.ascontiguousarray(intensities, dtype=np.float32)
+        if timestamps is not None:
+            timestamps = np.ascontiguousarray(timestamps, dtype=np.float64)
+        n = self.L.ohmb200_exchange_send(self.h, _ptr(rays), rays.shape[0], _ptr(intensities), _ptr(timestamps),
+                                         int(ray_flags))
+        if n == 0 and rays.shape[0] >= 2:
+            raise OhmB200Error(_lib.last_error())
+        return n  # (an empty send returns 0 as well: a failure there surfaces in exchange_integrate, "no step pending")
+
+    def exchange_send_ptr(self, host_ptr, element_count, intensities_ptr=None, timestamps_ptr=None, ray_flags=RF_DEFAULT):
+        return self.L.ohmb200_exchange_send(self.h, host_ptr, element_count, intensities_ptr, timestamps_ptr, int(ray_flags))
+
+    def exchange_send_device(self, d_rays_ptr, element_count, d_intensities_ptr=None, d_timestamps_ptr=None,
+                             ray_flags=RF_DEFAULT):
+        n = self.L.ohmb200_exchange_send_device(self.h, d_rays_ptr, element_count, d_intensities_ptr, d_timestamps_ptr,
+                                                int(ray_flags))
+        if n == 0 and element_count >= 2:
+            raise OhmB200Error(_lib.last_error())
+        return n
+
+    def exchange_integrate(self):
+        """Phase 2: wait (on the device) for every rank's records of the step, integrate what was routed here."""
+        self._check(self.L.ohmb200_exchange_integrate(self.h))
+
+    def exchange_close(self):
+        self._check(self.L.ohmb200_exchange_close(self.h))
+
     # -- measurement ---------------------------------------------------------------------------------------
     def set_stream(self, cuda_stream):
         self._check(self.L.ohmb200_set_stream(self.h, cuda_stream))
@@ -327,8 +372,8 @@ class GpuMap:
         self._check(self.L.ohmb200_set_profiling(self.h, int(bool(enabled))))
 
     def kernel_times(self, reset=True):
-        arr = (KernelTime * 24)()
-        n = self._check(self.L.ohmb200_kernel_times(self.h, arr, 24, int(reset)))
+        arr = (KernelTime * 40)()
+        n = self._check(self.L.ohmb200_kernel_times(self.h, arr, 40, int(reset)))
         return {arr[i].name.decode(): {"ms": arr[i].ms, "launches": int(arr[i].launches)} for i in range(n)}
 
 
@@ -364,3 +409,20 @@ class GpuTsdfMap(GpuMap):
         if sparsity_compensation_factor is not None:
             kw["tsdf_sparsity"] = sparsity_compensation_factor
         self.set_params(**kw)
+
+
+def open_exchange(maps, max_rays_per_rank):
+    """Connect `maps` (one per rank, in rank order, all in this process) into one routed exchange."""
+    handles = [m.exchange_open(r, len(maps), max_rays_per_rank) for r, m in enumerate(maps)]
+    for m in maps:
+        m.exchange_connect(handles)
+    return handles
+
+
+def exchange_step(maps, batches, ray_flags=RF_DEFAULT):
+    """One step of the exchange driven from a single process: every rank sends, then every rank integrates.
+    `batches[r]` = (rays, intensities, timestamps) of rank r (rays may be empty)."""
+    for m, (rays, intensities, timestamps) in zip(maps, batches):
+        m.exchange_send(rays, intensities, timestamps, ray_flags)
+    for m in maps:
+        m.exchange_integrate()
