@@ -135,6 +135,7 @@ typedef struct ohmb200_stats
   uint64_t region_capacity;  /* region slots allocated */
   uint64_t batches;          /* integrate calls */
   uint64_t kernel_launches;  /* kernels launched by this library */
+  uint64_t sample_voxels;    /* S': distinct sample voxels per batch, summed over batches (NDT byte model) */
 } ohmb200_stats;
 
 typedef struct ohmb200_map ohmb200_map;

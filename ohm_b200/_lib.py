@@ -45,7 +45,7 @@ class Params(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "rays_in", "rays_accepted", "voxel_visits", "sample_updates", "ordered_records", "regions",
-        "region_capacity", "batches", "kernel_launches")]
+        "region_capacity", "batches", "kernel_launches", "sample_voxels")]
 
 
 class ExchangeHandle(C.Structure):

@@ -97,6 +97,7 @@ struct Counters
   // sticky
   int table_full;
   int overflow_seen;  // bit 0: an ordered-record list overflowed (results incomplete); bit 1: the segment list did (batch dropped)
+  unsigned long long sample_voxels;  // S': distinct sample voxels, summed over batches (the NDT byte model's unit)
   uint32_t batch_stamp;  // stamp of the last batch planRegions saw (read on the device: a replayed graph bakes no stamp)
 };
 constexpr int kPerBatchCounterWords = 11;  // record_count .. new_count
@@ -378,6 +379,10 @@ __global__ void __launch_bounds__(128) applySamples(DeviceMap dm, Geom g, MapPar
 {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned samples = 0, ordered = 0;
+  if (t == 0 && !b.counters->segment_overflow)
+  {
+    b.counters->sample_voxels += b.counters->run_count;  // S' of the byte model; the run count is final here
+  }
   if (t < b.counters->run_count && !b.counters->segment_overflow)  // (a batch whose segment list overflowed is dropped whole)
   {
     const uint32_t head = b.run_list[t];
@@ -3329,6 +3334,7 @@ int ohmb200_get_stats(ohmb200_map *m, ohmb200_stats *stats)
   stats->region_capacity = m->dm.capacity;
   stats->batches = m->batches;
   stats->kernel_launches = m->launches;
+  stats->sample_voxels = m->h_counters->sample_voxels;
   return OHMB200_OK;
 }
 

@@ -1929,6 +1929,10 @@ __global__ void __launch_bounds__(128) applySamplesNdt(DeviceMap dm, Geom g, Map
 {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned samples = 0;
+  if (t == 0 && !b.counters->segment_overflow)
+  {
+    b.counters->sample_voxels += b.counters->run_count;
+  }
   if (t < b.counters->run_count && !b.counters->segment_overflow)
   {
     const uint32_t head = b.run_list[t];
