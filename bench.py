@@ -345,9 +345,18 @@ def run_single(args, torch):
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     batch = args.batch if args.batch > 0 else None
 
+    exchange1 = args.pipeline == "exchange"
+    if exchange1:
+        # A/B: the routed-exchange pipeline with world = 1 (every record's owner is this GPU)
+        gm.open_exchange([gpu], max(s[0].shape[0] // 2 for s in sweeps))
+
     def integrate_device(k):
         t = d_sweeps[k if traj else 0]
         n = t.shape[0] // 2
+        if exchange1:
+            gpu.exchange_send_device(t.data_ptr(), 2 * n)
+            gpu.exchange_integrate()
+            return
         if batch is None:
             gpu.integrate_rays_device(t.data_ptr(), 2 * n)
         else:
@@ -427,6 +436,10 @@ def run_single(args, torch):
     def integrate_host(k):
         t = h_sweeps[k if traj else 0]
         n = t.shape[0] // 2
+        if exchange1:
+            gpu.exchange_send_ptr(t.data_ptr(), 2 * n)
+            gpu.exchange_integrate()
+            return
         if batch is None:
             gpu.integrate_rays_ptr(t.data_ptr(), 2 * n)
         else:
@@ -524,7 +537,7 @@ def run_single(args, torch):
             + (f", fed in batches of {batch} rays (ohmapp/OhmAppCpu.h:52)" if batch else ""),
             "rays_per_step": rays_per_step, "voxel_visits_per_step": visits, "sample_updates_per_step": samples,
             "sample_voxels_per_step": sample_voxels, "regions": regions, "resolution_m": cfg["resolution"],
-            "parallelism": "single GPU",
+            "parallelism": "single GPU" + (" (routed-exchange pipeline, world = 1)" if exchange1 else ""),
             "graphs": ("batches are replayed as CUDA graphs (same buffers and size every step)" if not traj and batch is None
                        else "no graph replay: every batch differs in buffer or size"),
             "l2": "512 MiB L2 flush between timed steps (outside the timed spans)" + ("" if traj else "; map cleared too")
@@ -881,6 +894,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="feed each sweep in batches of this many rays (0 = one call)")
     ap.add_argument("--device-gib", type=float, default=0.0, help="device bytes for the region slabs (0 = per config)")
     ap.add_argument("--cpu-reps", type=int, default=8, help="CPU mapper passes / sweeps for cpu_baseline (0 = skip)")
+    ap.add_argument("--pipeline", default="plain", choices=["plain", "exchange"],
+                    help="N = 1 A/B: 'exchange' runs the routed-exchange pipeline with world = 1")
     ap.add_argument("--ndt-steps", type=int, default=8, help="N > 1: timed steps of the config-5 (NDT) arm")
     args = ap.parse_args()
     if args.impl == "reference":

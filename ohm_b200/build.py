@@ -7,7 +7,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libohmb200.so")
 SOURCES = [os.path.join(HERE, "csrc", "ohmb200.cu")]
-DEPS = SOURCES + [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc")) if f.endswith(".cuh")] + [
+DEPS = SOURCES + [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))
+                  if f.endswith((".cuh", ".inl", ".h", ".cu"))] + [
     os.path.join(ROOT, "include", "ohmb200.h")]
 
 # --fmad=false: voxel sequences must match the CPU mapper bit for bit (see ohmb200_device.cuh).

@@ -988,6 +988,7 @@ enum KernelId
   kKExSegments,
   kKExWait,
   kKExBin,
+  kKExBinSamples,
   kKExEmit,
   kKernelCount
 };
@@ -996,7 +997,7 @@ static const char *kKernelNames[kKernelCount] = { "prepSamples",  "radixSort",  
                                                   "prepRays",     "prepSegments",  "planRegions",   "emitSegments",  "walkRegions",
                                                   "linkRecords",  "scatterRecords", "markTsdfNear",  "clearTouchedBits", "replayTsdf",
                                                   "ndtGaussianMisses", "ndtClampGaussians", "integrateOrdered",
-                                                  "exPrepRays", "exRouteSamples", "exPrepSegments", "exWait", "exBin", "exEmit" };
+                                                  "exPrepRays", "exRouteSamples", "exPrepSegments", "exWait", "exBinSegments", "exBinSamples", "exEmit" };
 static_assert(kKernelCount <= OHMB200_KERNEL_SLOTS, "raise OHMB200_KERNEL_SLOTS");
 
 struct ohmb200_map
@@ -1110,6 +1111,8 @@ struct ohmb200_map
   struct Exchange
   {
     bool open = false, connected = false, pending = false;
+    bool local_peers = false;  // some peer map lives in this process: its sends are queued by the same host thread
+    bool forked = false;       // the pending step's sample branch runs on the side stream (join_event recorded)
     int rank = 0, world = 1;
     uint32_t per = 0, seg_cap = 0, step = 0;
     char *arena = nullptr;
@@ -1117,10 +1120,29 @@ struct ohmb200_map
     char *peer_base[kMaxWorld] = {};
     bool peer_mapped[kMaxWorld] = {};  // opened with cudaIpcOpenMemHandle (to be closed)
     uint32_t *out_counts = nullptr;    // [2 * kMaxWorld] segments / samples sent to each owner this step
-    unsigned long long *smp_key = nullptr;
+    unsigned long long *smp_key = nullptr;  // sender-side parking of the own rays' samples (see ExStep)
+    uint32_t *smp_voxel = nullptr, *smp_owner = nullptr;
+    double *smp_last_exit = nullptr;
     int *abort = nullptr;
+    uint32_t *d_step = nullptr;        // == step, counted on the device
     cudaStream_t stream = nullptr;     // the per-ray broadcast (copy engines) runs here, beside the cut
-    cudaEvent_t prepped = nullptr;
+    cudaEvent_t prepped = nullptr, bcast_done = nullptr;
+    // CUDA graphs of whole steps (send + integrate), one per (buffers, size, flags, parity): see launchBatch's graphs
+    struct StepGraph
+    {
+      const void *rays, *intensities, *timestamps;
+      size_t n;
+      unsigned ray_flags;
+      int parity;
+      double time_base;
+      cudaGraphExec_t exec;
+      uint64_t launches;
+    };
+    std::vector<StepGraph> graphs, seen;
+    bool capturing = false, replayed = false;
+    StepGraph current{};
+    uint64_t launches_before = 0;
+    int host_buf = -1;                 // input staging buffer of the pending step (ohmb200_exchange_send), -1: device rays
     size_t n_own = 0;
     unsigned ray_flags = 0;
     bool has_timestamps = false, has_intensities = false;
@@ -1431,10 +1453,11 @@ int ensureScratch(ohmb200_map *m, size_t n)
 }
 
 // Rays that walked no voxel take the exit range of the nearest earlier ray that did (see staleExit).
-int carryLastExit(ohmb200_map *m, size_t n, cudaStream_t s)
+int carryLastExit(ohmb200_map *m, size_t n, cudaStream_t s, double *last_exit = nullptr)
 {
   size_t temp = m->carry_temp_bytes;
-  CUDA_TRY(cub::DeviceScan::InclusiveScan(m->carry_temp, temp, m->batch.last_exit, m->batch.last_exit, CarryValid(), (int)n, s));
+  last_exit = last_exit ? last_exit : m->batch.last_exit;
+  CUDA_TRY(cub::DeviceScan::InclusiveScan(m->carry_temp, temp, last_exit, last_exit, CarryValid(), (int)n, s));
   ++m->launches;
   return OHMB200_OK;
 }

@@ -18,8 +18,9 @@
 //     exSignal        counts + a flag into every peer's mailbox         32 B x peers
 //   owner   (what arrived, from every rank incl. itself)
 //     exWait          spin on the mailbox flags of this step (one warp; bounded, never hangs the GPU)
-//     exBin           one thread per received record: region find-or-insert, per-region segment histogram,
-//                     touched list; sample pairs (voxel id, global ray index) for the sort
+//     exBinSamples    (side stream, as soon as the samples are in: beside everybody's cut) sample pairs (voxel id,
+//                     global ray index) for the sort
+//     exBinSegments   one thread per received record: region find-or-insert, per-region segment histogram, touched list
 //     planRegions / exEmit / radix sort / markRuns, then the single-GPU walk and replay kernels unchanged
 //
 // No rank filters or cuts another rank's rays; nothing is all-gathered through the host.  Inboxes live in ONE device
@@ -60,9 +61,10 @@ static_assert(sizeof(WireSample) == 96, "WireSample must be 96 bytes");
 struct ExMailbox
 {
   uint32_t seg_count, sample_count, ray_count, overflow;
-  uint32_t seg_flag;  // == step when the sender's segment and sample records of that step are in place
+  uint32_t seg_flag;  // == step when the sender's segment records of that step are in place
   uint32_t ray_flag;  // == step when its per-ray broadcast is
-  uint32_t pad[2];
+  uint32_t smp_flag;  // == step when its sample records are (they leave first: the owner sorts them beside the cut)
+  uint32_t pad;
 };
 
 // One rank's arena, one parity.
@@ -83,14 +85,27 @@ struct ExStep
   int rank, world;
   uint32_t per;      // ray slots per rank
   uint32_t seg_cap;  // segment records per (sender, owner) pair
-  uint32_t step;
+  const uint32_t *step;  // the step number, counted on the device (a replayed graph carries no host-side number)
   uint32_t n_own;
   uint32_t *out_seg;  // [world] records this rank has sent to each owner this step
   uint32_t *out_smp;
-  unsigned long long *smp_key;  // [per] region key of each own ray's sample voxel
+  unsigned long long *smp_key;  // [per] region key of each own ray's sample voxel, its voxel index and owner, and the
+  uint32_t *smp_voxel;          //       exit range of its last walked voxel: parked by exPrepRays for exRouteSamples
+  uint32_t *smp_owner;
+  double *smp_last_exit;        // (traversal layer only, else null)
   int *abort;         // set when a wait timed out: the step is dropped
   ExView peer[kMaxWorld];
 };
+
+// One 32-byte store (st.global.v8.b32, sm_100+): a record of the inboxes is written as whole sectors — lanes that
+// drew neighbouring slots then fill whole 128-byte lines with one instruction, which is what a store over NVLink
+// wants (two 16-byte halves per lane were measured at an eighth of the link rate).  `dst` is 32-byte aligned.
+__device__ __forceinline__ void store32(void *dst, const uint4 &a, const uint4 &b)
+{
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
 
 // Position among the lanes of the converged group that target the same `bucket`, after one atomic per group.
 __device__ __forceinline__ uint32_t bucketAggregatedInc(uint32_t *counters, uint32_t bucket)
@@ -186,17 +201,17 @@ __global__ void __launch_bounds__(128) exPrepRays(DeviceMap dm, Geom g, MapParam
         }
       }
     }
-    own.keys_in[i] = voxel;
-    own.vals_in[i] = owner;
+    ex.smp_voxel[i] = voxel;
+    ex.smp_owner[i] = owner;
     ex.smp_key[i] = key;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
     {
       reinterpret_cast<uint4 *>(mine.recs + gid)[k] = reinterpret_cast<const uint4 *>(&rec)[k];
     }
-    if (own.last_exit)
+    if (ex.smp_last_exit)
     {
-      own.last_exit[i] = last;
+      ex.smp_last_exit[i] = last;
     }
   }
   __syncwarp();
@@ -216,12 +231,12 @@ __global__ void __launch_bounds__(128) exRouteSamples(Batch own, ExStep ex)
   {
     return;
   }
-  const uint32_t voxel = own.keys_in[i];
+  const uint32_t voxel = ex.smp_voxel[i];
   if (voxel == kInvalidVoxel)
   {
     return;
   }
-  const uint32_t owner = own.vals_in[i];
+  const uint32_t owner = ex.smp_owner[i];
   const uint32_t at = bucketAggregatedInc(ex.out_smp, owner);
   if (at >= ex.per)
   {
@@ -231,7 +246,7 @@ __global__ void __launch_bounds__(128) exRouteSamples(Batch own, ExStep ex)
   smp.key = ex.smp_key[i];
   smp.voxel = voxel;
   smp.ray = (uint32_t)ex.rank * ex.per + i;
-  smp.last_exit = own.last_exit ? own.last_exit[i] : 0.0;
+  smp.last_exit = ex.smp_last_exit ? ex.smp_last_exit[i] : 0.0;
   smp.timestamp = own.timestamps ? own.timestamps[i] : 0.0;
   smp.intensity = own.intensities ? own.intensities[i] : 0.0f;
   smp.pad0 = 0;
@@ -241,11 +256,12 @@ __global__ void __launch_bounds__(128) exRouteSamples(Batch own, ExStep ex)
   {
     smp.pts[k] = own.rays[(size_t)i * 6 + k];
   }
-  uint4 *dst = reinterpret_cast<uint4 *>(ex.peer[owner].smp_in + (size_t)ex.rank * ex.per + at);
+  char *dst = reinterpret_cast<char *>(ex.peer[owner].smp_in + (size_t)ex.rank * ex.per + at);
+  const uint4 *src = reinterpret_cast<const uint4 *>(&smp);
 #pragma unroll
-  for (int k = 0; k < 6; ++k)
+  for (int k = 0; k < 3; ++k)
   {
-    dst[k] = reinterpret_cast<const uint4 *>(&smp)[k];
+    store32(dst + 32 * k, src[2 * k], src[2 * k + 1]);
   }
 }
 
@@ -274,10 +290,10 @@ __global__ void __launch_bounds__(128) exPrepSegments(Geom g, Batch own, ExStep 
           return;
         }
         const unsigned long long key = packRegion(r[0], r[1], r[2]);
-        uint4 *dst = reinterpret_cast<uint4 *>(ex.peer[owner].seg_in + (size_t)ex.rank * ex.seg_cap + at);
-        dst[0] = make_uint4(gid, (uint32_t)st[0] | ((uint32_t)st[1] << 16), (uint32_t)st[2] | ((uint32_t)n << 16),
-                            (uint32_t)entry[0] | ((uint32_t)entry[1] << 8) | ((uint32_t)entry[2] << 16));
-        dst[1] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), 0xFFFFFFFFu, 0u);
+        store32(ex.peer[owner].seg_in + (size_t)ex.rank * ex.seg_cap + at,
+                make_uint4(gid, (uint32_t)st[0] | ((uint32_t)st[1] << 16), (uint32_t)st[2] | ((uint32_t)n << 16),
+                           (uint32_t)entry[0] | ((uint32_t)entry[1] << 8) | ((uint32_t)entry[2] << 16)),
+                make_uint4((uint32_t)key, (uint32_t)(key >> 32), 0xFFFFFFFFu, 0u));
       });
     }
   }
@@ -293,8 +309,13 @@ __global__ void __launch_bounds__(128) exPrepSegments(Geom g, Batch own, ExStep 
   }
 }
 
-// Tell every owner what this rank has put into its inbox.  stage 0: segment and sample records; stage 1: the per-ray
-// broadcast.  The data was written by earlier work of the same stream(s); the system-scope fence orders it before
+__global__ void exBumpStep(uint32_t *step)
+{
+  *step += 1u;
+}
+
+// Tell every owner what this rank has put into its inbox.  stage 2: sample records (sent first); stage 0: segment
+// records; stage 1: the per-ray broadcast.  The data was written by earlier work of the same stream(s); the system-scope fence orders it before
 // the flag for a reader on another GPU.
 __global__ void exSignal(ExStep ex, int stage)
 {
@@ -308,29 +329,35 @@ __global__ void exSignal(ExStep ex, int stage)
   {
     const uint32_t segs = ex.out_seg[o];
     box->seg_count = min(segs, ex.seg_cap);
-    box->sample_count = min(ex.out_smp[o], ex.per);
     box->ray_count = ex.n_own;
     box->overflow = segs > ex.seg_cap ? 1u : 0u;
     __threadfence_system();
-    *reinterpret_cast<volatile uint32_t *>(&box->seg_flag) = ex.step;
+    *reinterpret_cast<volatile uint32_t *>(&box->seg_flag) = *ex.step;
+  }
+  else if (stage == 2)
+  {
+    box->sample_count = min(ex.out_smp[o], ex.per);
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t *>(&box->smp_flag) = *ex.step;
   }
   else
   {
     __threadfence_system();
-    *reinterpret_cast<volatile uint32_t *>(&box->ray_flag) = ex.step;
+    *reinterpret_cast<volatile uint32_t *>(&box->ray_flag) = *ex.step;
   }
 }
 
 // Wait (one warp, lane = sender) until every sender's flag of this step is in this rank's mailbox.  Bounded: after
 // ~4 s of spinning the step is abandoned (abort flag: exBin / exEmit see empty inboxes, ohmb200_sync reports it) — a
 // missing peer must never hang the GPU.
-__global__ void exWait(ExMailbox *mailbox, int world, uint32_t step, int stage, int *abort)
+__global__ void exWait(ExMailbox *mailbox, int world, const uint32_t *step_counter, int stage, int *abort)
 {
+  const uint32_t step = *step_counter;
   const int s = (int)threadIdx.x;
   bool ok = true;
   if (s < world)
   {
-    const volatile uint32_t *flag = stage == 0 ? &mailbox[s].seg_flag : &mailbox[s].ray_flag;
+    const volatile uint32_t *flag = stage == 0 ? &mailbox[s].seg_flag : (stage == 1 ? &mailbox[s].ray_flag : &mailbox[s].smp_flag);
     const long long t0 = clock64();
     while (*flag != step)
     {
@@ -385,11 +412,12 @@ __device__ __forceinline__ int exSender(const uint32_t *first, int world, uint32
   return s;
 }
 
-// One thread per received record.  Segments: region find-or-insert in THIS rank's table, per-region histogram, touched
-// list (what prepSegments does per ray on the single-GPU path).  Samples: the (voxel id, global ray) pair at index
-// `ray` — the pairs are then in global ray order, which the stable sort keeps inside a voxel — plus the ray itself
-// where the rays were not broadcast.
-__global__ void __launch_bounds__(256) exBin(DeviceMap dm, Geom g, Batch b, ExStep ex, int rays_from_samples)
+// One thread per received segment record: region find-or-insert in THIS rank's table, per-region histogram, touched
+// list (what prepSegments does per ray on the single-GPU path).  The lanes of a warp that hold the same region — the
+// k-th segments of neighbouring rays — probe the table once: the first of them looks the region up (or creates it) and
+// adds the whole group to the histogram.  (One probe and one compare-and-swap per LANE was 110 us on a fresh map: tens
+// of thousands of lanes arrive at an empty slot of a hot region together.)
+__global__ void __launch_bounds__(256) exBinSegments(DeviceMap dm, Batch b, ExStep ex)
 {
   __shared__ ExInbox in;
   if (threadIdx.x == 0)
@@ -416,6 +444,7 @@ __global__ void __launch_bounds__(256) exBin(DeviceMap dm, Geom g, Batch b, ExSt
   const ExView &mine = ex.peer[ex.rank];
   const uint32_t total_segs = in.seg_first[kMaxWorld];
   const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t lane = threadIdx.x & 31u;
   for (uint32_t base = blockIdx.x * blockDim.x; base < total_segs; base += stride)
   {
     const uint32_t j = base + threadIdx.x;
@@ -424,21 +453,35 @@ __global__ void __launch_bounds__(256) exBin(DeviceMap dm, Geom g, Batch b, ExSt
       const int s = exSender(in.seg_first, ex.world, j);
       WireSegment *ws = mine.seg_in + (size_t)s * ex.seg_cap + (j - in.seg_first[s]);
       const unsigned long long key = (unsigned long long)ws->key_lo | ((unsigned long long)ws->key_hi << 32);
-      const int slot = regionSlot(dm, key);
-      ws->slot = (uint32_t)slot;
-      if (slot >= 0)
+      const unsigned peers = __match_any_sync(__activemask(), key);
+      const int leader = __ffs(peers) - 1;
+      int slot = -1;
+      if ((int)lane == leader)
       {
-        const unsigned peers = __match_any_sync(__activemask(), slot);
-        if ((int)(threadIdx.x & 31) == __ffs(peers) - 1)
+        slot = regionSlot(dm, key);
+        if (slot >= 0 && atomicAdd(&b.seg_count[slot], (uint32_t)__popc(peers)) == 0u)
         {
-          if (atomicAdd(&b.seg_count[slot], (uint32_t)__popc(peers)) == 0u)
-          {
-            b.touched_list[atomicAdd(&b.counters->touched_count, 1u)] = (uint32_t)slot;
-          }
+          b.touched_list[atomicAdd(&b.counters->touched_count, 1u)] = (uint32_t)slot;
         }
       }
+      slot = __shfl_sync(peers, slot, leader);
+      ws->slot = (uint32_t)slot;
     }
   }
+}
+
+// One thread per received sample record: the (voxel id, global ray) pair at index `ray` — the pairs are then in global
+// ray order, which the stable sort keeps inside a voxel — plus the ray itself where the rays were not broadcast.
+__global__ void __launch_bounds__(256) exBinSamples(DeviceMap dm, Geom g, Batch b, ExStep ex, int rays_from_samples)
+{
+  __shared__ ExInbox in;
+  if (threadIdx.x == 0)
+  {
+    exLoadInbox(in, ex);
+  }
+  __syncthreads();
+  const ExView &mine = ex.peer[ex.rank];
+  const uint32_t stride = gridDim.x * blockDim.x;
   const uint32_t total_smps = in.smp_first[kMaxWorld];
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < total_smps; j += stride)
   {

@@ -1,6 +1,19 @@
 // ohmb200_exchange_host.inl — host side of the routed multi-GPU exchange (included inside ohmb200.cu's anonymous
 // namespace; kernels and the protocol: ohmb200_exchange.cuh).
 
+// Debug aid (OHMB200_TRACE_CAPTURE): reports the first operation after which a step's recording was invalidated.
+#define EX_CAPCHK(m, what)                                                                                  \
+  do                                                                                                        \
+  {                                                                                                         \
+    static const bool trace__ = getenv("OHMB200_TRACE_CAPTURE") != nullptr;                                 \
+    if (trace__ && (m)->ex.capturing)                                                                       \
+    {                                                                                                       \
+      cudaStreamCaptureStatus st__ = cudaStreamCaptureStatusNone;                                           \
+      cudaStreamIsCapturing((m)->stream, &st__);                                                            \
+      fprintf(stderr, "[capture] %s:%d %s -> %d\n", __FILE__, __LINE__, what, (int)st__);                   \
+    }                                                                                                       \
+  } while (0)
+
 struct ExHandle
 {
   unsigned long long magic;
@@ -91,7 +104,19 @@ int exchangeClose(ohmb200_map *m)
   cudaFree(x.arena);
   cudaFree(x.out_counts);
   cudaFree(x.smp_key);
+  cudaFree(x.smp_voxel);
+  cudaFree(x.smp_owner);
+  cudaFree(x.smp_last_exit);
   cudaFree(x.abort);
+  cudaFree(x.d_step);
+  for (auto &g : x.graphs)
+  {
+    cudaGraphExecDestroy(g.exec);
+  }
+  if (x.bcast_done)
+  {
+    cudaEventDestroy(x.bcast_done);
+  }
   if (x.stream)
   {
     cudaStreamDestroy(x.stream);
@@ -158,8 +183,17 @@ int exchangeOpen(ohmb200_map *m, int rank, int world, size_t max_rays_per_rank, 
   }
   ok = ok && cudaMalloc(&x.out_counts, sizeof(uint32_t) * 2 * kMaxWorld) == cudaSuccess;
   ok = ok && cudaMalloc(&x.smp_key, sizeof(unsigned long long) * x.per) == cudaSuccess;
+  ok = ok && cudaMalloc(&x.smp_voxel, sizeof(uint32_t) * x.per) == cudaSuccess;
+  ok = ok && cudaMalloc(&x.smp_owner, sizeof(uint32_t) * x.per) == cudaSuccess;
+  if (m->dm.traversal)
+  {
+    ok = ok && cudaMalloc(&x.smp_last_exit, sizeof(double) * x.per) == cudaSuccess;
+  }
   ok = ok && cudaMalloc(&x.abort, sizeof(int)) == cudaSuccess;
   ok = ok && cudaMemsetAsync(x.abort, 0, sizeof(int), m->stream) == cudaSuccess;
+  ok = ok && cudaMalloc(&x.d_step, sizeof(uint32_t)) == cudaSuccess;
+  ok = ok && cudaMemsetAsync(x.d_step, 0, sizeof(uint32_t), m->stream) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&x.bcast_done, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&x.stream, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&x.prepped, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaStreamSynchronize(m->stream) == cudaSuccess;
@@ -225,6 +259,7 @@ int exchangeConnect(ohmb200_map *m, const ohmb200_exchange_handle *handles, int 
     }
     if (h.pid == (int32_t)getpid())
     {
+      x.local_peers = true;
       // a peer map of this process: its pointer is ours too; another device needs peer access switched on
       if (h.device != m->device)
       {
@@ -268,11 +303,14 @@ void exFillStep(ohmb200_map *m, ExStep &ex)
   ex.world = x.world;
   ex.per = x.per;
   ex.seg_cap = x.seg_cap;
-  ex.step = x.step;
+  ex.step = x.d_step;
   ex.n_own = (uint32_t)x.n_own;
   ex.out_seg = x.out_counts;
   ex.out_smp = x.out_counts + kMaxWorld;
   ex.smp_key = x.smp_key;
+  ex.smp_voxel = x.smp_voxel;
+  ex.smp_owner = x.smp_owner;
+  ex.smp_last_exit = x.smp_last_exit;
   ex.abort = x.abort;
   for (int r = 0; r < x.world; ++r)
   {
@@ -283,6 +321,54 @@ void exFillStep(ohmb200_map *m, ExStep &ex)
 bool exNdt(const ohmb200_map *m)
 {
   return m->mode == OHMB200_MODE_NDT || m->mode == OHMB200_MODE_NDT_TM;
+}
+
+// The owner's sample branch: wait for every rank's sample records, turn them into (voxel id, ray) pairs, sort, mark the
+// runs — on the side stream (joined before the walk) unless per-kernel profiling serialises everything.
+int exSampleBranch(ohmb200_map *m, const ExStep &ex)
+{
+  ohmb200_map::Exchange &x = m->ex;
+  const ExView &mine = ex.peer[x.rank];
+  const size_t n_total = (size_t)x.world * x.per;
+  cudaStream_t s = m->stream;
+  Batch &b = m->batch;
+  b.rays = mine.rays;
+  b.n = (uint32_t)n_total;
+  b.counters = m->d_counters;
+  const bool fork = !m->profiling;
+  cudaStream_t ss = fork ? m->side_stream : s;
+  if (fork)
+  {
+    CUDA_TRY(cudaEventRecord(m->fork_event, s));
+    CUDA_TRY(cudaStreamWaitEvent(ss, m->fork_event, 0));
+  }
+  CUDA_TRY(cudaMemsetAsync(b.keys_in, 0xFF, sizeof(uint32_t) * n_total, ss));  // rays without a sample here: no voxel
+  CUDA_TRY(cudaMemsetAsync(b.sample_begin, 0, sizeof(uint32_t) * 2 * m->dm.capacity, ss));
+  EX_CAPCHK(m, "branch memsets");
+  {
+    KernelScope scope(m, kKExWait);
+    exWait<<<1, 32, 0, ss>>>(mine.mailbox, x.world, x.d_step, 2, x.abort);
+  }
+  {
+    KernelScope scope(m, kKExBinSamples);
+    exBinSamples<<<(unsigned)m->sm_count * 4u, 256, 0, ss>>>(m->dm, m->geom, b, ex, exNdt(m) ? 0 : 1);
+  }
+  {
+    KernelScope scope(m, kKSort);
+    size_t temp = m->cub_temp_bytes;
+    cub::DeviceRadixSort::SortPairs(m->cub_temp, temp, b.keys_in, b.keys_out, b.vals_in, b.vals_out, (int)n_total, 0, m->sort_bits, ss);
+  }
+  EX_CAPCHK(m, "branch sort");
+  {
+    KernelScope scope(m, kKMark);
+    markRuns<<<(unsigned)((n_total + 127) / 128), 128, 0, ss>>>(m->dm, b, m->geom.vpr);
+  }
+  if (fork)
+  {
+    CUDA_TRY(cudaEventRecord(m->join_event, ss));
+  }
+  x.forked = fork;
+  return OHMB200_OK;
 }
 
 // Phase 1 of a step: this rank's own rays (device memory) -> filter, cut, route.  Returns after queueing.
@@ -337,6 +423,54 @@ int exchangeSend(ohmb200_map *m, const double *d_rays, size_t element_count, con
   x.ray_flags = ray_flags;
   x.has_timestamps = d_timestamps != nullptr;
   x.has_intensities = d_intensities != nullptr;
+  x.replayed = false;
+  x.capturing = false;
+  cudaStream_t s = m->stream;
+  // A step of the same shape as one met before — same ray buffers, count, flags, parity of the inboxes — is replayed as
+  // one CUDA graph (send + integrate: ~45 stream operations); the second time a shape comes it is recorded (relaxed
+  // capture mode: the recording spans two API calls, and what the caller does between them is none of its business).  Not with
+  // peer maps in this process (their calls interleave with ours), per-kernel profiling or a paged-out map.
+  if (m->use_graphs && !m->profiling && m->store.empty() && !x.local_peers)
+  {
+    const ohmb200_map::Exchange::StepGraph key{ d_rays, d_intensities, d_timestamps, n, ray_flags, (int)(x.step & 1u),
+                                                 m->first_ray_time, nullptr, 0 };
+    auto same = [&](const ohmb200_map::Exchange::StepGraph &g) {
+      return g.rays == key.rays && g.intensities == key.intensities && g.timestamps == key.timestamps && g.n == key.n &&
+             g.ray_flags == key.ray_flags && g.parity == key.parity && g.time_base == key.time_base;
+    };
+    for (auto &g : x.graphs)
+    {
+      if (same(g))
+      {
+        CUDA_TRY(cudaGraphLaunch(g.exec, s));
+        m->launches += g.launches;
+        x.replayed = true;
+        x.pending = true;
+        return OHMB200_OK;
+      }
+    }
+    bool met = false;
+    for (auto &g : x.seen)
+    {
+      met = met || same(g);
+    }
+    if (!met)
+    {
+      if (x.seen.size() >= 16)
+      {
+        x.seen.erase(x.seen.begin());
+      }
+      x.seen.push_back(key);
+    }
+    else if (x.graphs.size() < 8 && cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) == cudaSuccess)
+    {
+      x.capturing = true;
+      x.current = key;
+      x.launches_before = m->launches;
+    }
+  }
+  exBumpStep<<<1, 1, 0, s>>>(x.d_step);
+  EX_CAPCHK(m, "bump");
   ExStep ex;
   exFillStep(m, ex);
   Batch own = m->batch;
@@ -347,9 +481,9 @@ int exchangeSend(ohmb200_map *m, const double *d_rays, size_t element_count, con
   own.ray_flags = ray_flags;
   own.time_base = m->first_ray_time;
   own.counters = m->d_counters;
-  cudaStream_t s = m->stream;
   const unsigned blocks = (unsigned)((n + 127) / 128);
   const bool broadcast_rays = exNdt(m);  // every owner evaluates NDT misses of every ray that crosses its regions
+  const size_t n_total = (size_t)x.world * x.per;
   CUDA_TRY(cudaMemsetAsync(&m->d_counters->record_count, 0, sizeof(uint32_t) * kPerBatchCounterWords, s));
   CUDA_TRY(cudaMemsetAsync(x.out_counts, 0, sizeof(uint32_t) * 2 * kMaxWorld, s));
   if (n)
@@ -358,9 +492,9 @@ int exchangeSend(ohmb200_map *m, const double *d_rays, size_t element_count, con
       KernelScope scope(m, kKExPrepRays);
       exPrepRays<<<blocks, 128, 0, s>>>(m->dm, m->geom, m->mp, own, ex, m->mode, broadcast_rays ? 1 : 0);
     }
-    if (own.last_exit)
+    if (x.smp_last_exit)
     {
-      rc = carryLastExit(m, n, s);
+      rc = carryLastExit(m, n, s, x.smp_last_exit);
       if (rc)
       {
         return rc;
@@ -370,9 +504,12 @@ int exchangeSend(ohmb200_map *m, const double *d_rays, size_t element_count, con
       KernelScope scope(m, kKExRoute);
       exRouteSamples<<<blocks, 128, 0, s>>>(own, ex);
     }
+    EX_CAPCHK(m, "prep+carry+route");
   }
-  // The per-ray broadcast: copy engines over NVLink, beside exPrepSegments.
+  exSignal<<<1, 32, 0, s>>>(ex, 2);  // the samples are out
   CUDA_TRY(cudaEventRecord(x.prepped, s));
+
+  // The per-ray broadcast: copy engines over NVLink, beside exPrepSegments.
   CUDA_TRY(cudaStreamWaitEvent(x.stream, x.prepped, 0));
   const ExView &mine = ex.peer[x.rank];
   const size_t first = (size_t)x.rank * x.per;
@@ -402,13 +539,31 @@ int exchangeSend(ohmb200_map *m, const double *d_rays, size_t element_count, con
     }
   }
   exSignal<<<1, 32, 0, x.stream>>>(ex, 1);
+  CUDA_TRY(cudaEventRecord(x.bcast_done, x.stream));
+  EX_CAPCHK(m, "broadcast");
+
+  // The sample branch of the OWNER side starts here, beside everybody's cut — unless a peer map lives in this process:
+  // its send is queued by this same host thread AFTER this call, and a wait kernel queued now could sit in front of it
+  // in a shared hardware queue.  Then ohmb200_exchange_integrate queues the branch (every send has been queued by then).
+  x.forked = false;
+  if (!x.local_peers)
+  {
+    rc = exSampleBranch(m, ex);
+    if (rc)
+    {
+      return rc;
+    }
+    EX_CAPCHK(m, "sample branch");
+  }
+
   if (n)
   {
     KernelScope scope(m, kKExSegments);
     exPrepSegments<<<blocks, 128, 0, s>>>(m->geom, own, ex);
   }
   exSignal<<<1, 32, 0, s>>>(ex, 0);
-  m->launches += 2;
+  m->launches += 3;
+  EX_CAPCHK(m, "segments+signal");
   CUDA_TRY(cudaGetLastError());
   x.pending = true;
   return OHMB200_OK;
@@ -468,9 +623,15 @@ int exchangeSendHost(ohmb200_map *m, const double *rays, size_t element_count, c
   }
   const int rc = exchangeSend(m, m->d_rays[buf], 2 * n, intensities ? m->d_intensities[buf] : nullptr,
                               timestamps ? m->d_timestamps[buf] : nullptr, ray_flags);
-  // the staged rays are read by the send kernels only (the owners work from the arenas)
-  cudaEventRecord(m->in_free[buf], m->stream);
+  // the staged rays are read by the send kernels only; their buffer is released when the step has been queued whole
+  // (ohmb200_exchange_integrate: a step being recorded as a graph must not swallow the event)
+  m->ex.host_buf = (rc == OHMB200_OK) ? buf : -1;
+  if (rc != OHMB200_OK)
+  {
+    cudaEventRecord(m->in_free[buf], m->stream);
+  }
   cudaEventSynchronize(m->in_ready[buf]);
+  EX_CAPCHK(m, "upload wait");
   return rc;
 }
 
@@ -488,6 +649,23 @@ int exchangeIntegrate(ohmb200_map *m)
   }
   cudaSetDevice(m->device);
   x.pending = false;
+  cudaStream_t s = m->stream;
+  auto finish = [&]() {
+    if (x.host_buf >= 0)
+    {
+      cudaEventRecord(m->in_free[x.host_buf], s);
+      x.host_buf = -1;
+    }
+    m->rays_in += x.n_own;
+    ++m->batches;
+    snapshotRegionCount(m);
+  };
+  if (x.replayed)
+  {
+    x.replayed = false;
+    finish();  // the step's graph holds both phases
+    return OHMB200_OK;
+  }
   ExStep ex;
   exFillStep(m, ex);
   const ExView &mine = ex.peer[x.rank];
@@ -505,51 +683,44 @@ int exchangeIntegrate(ohmb200_map *m)
   b.time_base = m->first_ray_time;
   b.counters = m->d_counters;
   b.stage_by_ray = 0;
-  cudaStream_t s = m->stream;
-  const unsigned blocks = (unsigned)((n_total + 127) / 128);
-  const bool ndt = exNdt(m);
   const unsigned bin_grid = (unsigned)m->sm_count * 8u;
 
   CUDA_TRY(cudaMemsetAsync(b.seg_count, 0, sizeof(uint32_t) * m->dm.capacity, s));
   CUDA_TRY(cudaMemsetAsync(b.seg_cursor, 0, sizeof(uint32_t) * m->dm.capacity, s));
-  CUDA_TRY(cudaMemsetAsync(b.sample_begin, 0, sizeof(uint32_t) * 2 * m->dm.capacity, s));
   CUDA_TRY(cudaMemsetAsync(b.record_vid, 0xFF, sizeof(uint32_t) * b.record_capacity, s));
   CUDA_TRY(cudaMemsetAsync(b.run_head, 0xFF, sizeof(int32_t) * n_total, s));
   b.tail_overflow = b.interval_count + n_total;
   CUDA_TRY(cudaMemsetAsync(b.interval_count, 0, sizeof(uint32_t) * (2 * n_total + 1), s));
-  CUDA_TRY(cudaMemsetAsync(b.keys_in, 0xFF, sizeof(uint32_t) * n_total, s));  // rays without a sample here: no voxel
+  if (x.local_peers)
+  {
+    int rc_branch = exSampleBranch(m, ex);
+    if (rc_branch)
+    {
+      return rc_branch;
+    }
+  }
   {
     KernelScope scope(m, kKExWait);
-    exWait<<<1, 32, 0, s>>>(mine.mailbox, x.world, x.step, 0, x.abort);
+    exWait<<<1, 32, 0, s>>>(mine.mailbox, x.world, x.d_step, 0, x.abort);
   }
   {
     KernelScope scope(m, kKExBin);
-    exBin<<<bin_grid, 256, 0, s>>>(m->dm, m->geom, b, ex, ndt ? 0 : 1);
+    exBinSegments<<<bin_grid, 256, 0, s>>>(m->dm, b, ex);
   }
+  const bool fork = x.forked;
   if (!m->store.empty())
   {
-    int rc = pageInNewRegions(m);  // regions this step brought back: restore their chunks before anything updates them
+    // regions this step brought back (the sample branch creates regions too): restore their chunks before anything
+    // updates them
+    if (fork)
+    {
+      CUDA_TRY(cudaStreamWaitEvent(s, m->join_event, 0));
+    }
+    int rc = pageInNewRegions(m);
     if (rc)
     {
       return rc;
     }
-  }
-  const bool fork = !m->profiling;
-  cudaStream_t sample_stream = fork ? m->side_stream : s;
-  if (fork)
-  {
-    CUDA_TRY(cudaEventRecord(m->fork_event, s));
-    CUDA_TRY(cudaStreamWaitEvent(sample_stream, m->fork_event, 0));
-  }
-  {
-    KernelScope scope(m, kKSort);
-    size_t temp = m->cub_temp_bytes;
-    cub::DeviceRadixSort::SortPairs(m->cub_temp, temp, b.keys_in, b.keys_out, b.vals_in, b.vals_out, (int)n_total, 0, m->sort_bits,
-                                    sample_stream);
-  }
-  {
-    KernelScope scope(m, kKMark);
-    markRuns<<<blocks, 128, 0, sample_stream>>>(m->dm, b, m->geom.vpr);
   }
   {
     KernelScope scope(m, kKPlan);
@@ -561,21 +732,45 @@ int exchangeIntegrate(ohmb200_map *m)
   }
   if (fork)
   {
-    CUDA_TRY(cudaEventRecord(m->join_event, sample_stream));
-    CUDA_TRY(cudaStreamWaitEvent(s, m->join_event, 0));
+    CUDA_TRY(cudaStreamWaitEvent(s, m->join_event, 0));  // the sample branch (queued by ohmb200_exchange_send)
   }
   {
     KernelScope scope(m, kKExWait);
-    exWait<<<1, 32, 0, s>>>(mine.mailbox, x.world, x.step, 1, x.abort);  // the walk constants of every rank's rays
+    exWait<<<1, 32, 0, s>>>(mine.mailbox, x.world, x.d_step, 1, x.abort);  // the walk constants of every rank's rays
   }
   int rc = launchWalkAndReplay(m, b, s, n_total, true);
+  CUDA_TRY(cudaStreamWaitEvent(s, x.bcast_done, 0));  // (long done: joins the broadcast stream for a recorded step)
+  if (x.capturing)
+  {
+    x.capturing = false;
+    cudaGraph_t graph = nullptr;
+    const cudaError_t end = cudaStreamEndCapture(s, &graph);
+    cudaGraphExec_t exec = nullptr;
+    if (rc == OHMB200_OK && end == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess)
+    {
+      cudaGraphDestroy(graph);
+      x.current.exec = exec;
+      x.current.launches = m->launches - x.launches_before;
+      x.graphs.push_back(x.current);
+      CUDA_TRY(cudaGraphLaunch(exec, s));
+    }
+    else
+    {
+      if (graph)
+      {
+        cudaGraphDestroy(graph);
+      }
+      cudaGetLastError();
+      m->use_graphs = false;
+      return setError(OHMB200_E_CUDA, "exchange: the step could not be recorded as a CUDA graph (graphs are now off; the step "
+                                      "was NOT integrated: send it again)");
+    }
+  }
   if (rc)
   {
     return rc;
   }
   CUDA_TRY(cudaGetLastError());
-  m->rays_in += x.n_own;
-  ++m->batches;
-  snapshotRegionCount(m);
+  finish();
   return OHMB200_OK;
 }

@@ -174,3 +174,23 @@ def test_exchange_flags_and_filters(gpu):
     maps[0].exchange_close()
     maps[0].integrate_rays(rays[:64])              # and works again afterwards
     maps[0].sync_voxels()
+
+
+def test_exchange_steps_replayed_as_graphs(gpu):
+    """A step of the same shape as one met before is recorded and replayed as one CUDA graph (send + integrate); the
+    step number lives on the device.  Ten identical steps, world = 1: recorded at steps 3 and 4 (one per inbox parity),
+    replayed from then on — the map must still equal the CPU mapper's after every step count."""
+    maps, cpu = make_world(1, 0.25, layers=[gm.LAYER_OCCUPANCY, gm.LAYER_MEAN], per=8192)
+    rays = random_rays(8000, 10.0, seed=9)
+    before = maps[0].stats()["kernel_launches"]
+    for step in range(10):
+        gm.exchange_step(maps, [(rays, None, None)])
+        cpu.integrate_rays(rays)
+    check_union(maps, cpu)
+    st = maps[0].stats()
+    assert st["batches"] == 10 and st["kernel_launches"] - before >= 10 * 10
+    # a different batch after the replays: back to plain launches, same map
+    other = random_rays(5000, 10.0, seed=10)
+    gm.exchange_step(maps, [(other, None, None)])
+    cpu.integrate_rays(other)
+    check_union(maps, cpu)
