@@ -116,7 +116,10 @@ __device__ __forceinline__ uint32_t bucketAggregatedInc(uint32_t *counters, uint
 
 // Filter, walk constants and sample voxel of this rank's own rays.  The RayRec goes to the rank's own arena (the
 // broadcast copies it on); the sample is parked in scratch until exRouteSamples.
-__global__ void __launch_bounds__(128) exPrepRays(DeviceMap dm, Geom g, MapParams mp, Batch own, ExStep ex, int mode, int copy_rays)
+// route_now: the sample record leaves from here (no traversal layer: nothing to wait for); else exRouteSamples sends it
+// once carryLastExit has run.
+__global__ void __launch_bounds__(128) exPrepRays(DeviceMap dm, Geom g, MapParams mp, Batch own, ExStep ex, int mode, int copy_rays,
+                                                  int route_now)
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   bool accepted = false;
@@ -126,6 +129,7 @@ __global__ void __launch_bounds__(128) exPrepRays(DeviceMap dm, Geom g, MapParam
     const uint32_t gid = (uint32_t)ex.rank * ex.per + i;
     double start[3], end[3];
     loadRay(own, i, start, end);
+    const double raw[6] = { start[0], start[1], start[2], end[0], end[1], end[2] };
     if (copy_rays)
     {
       // the consumers read rays by global index (ndtGaussianMisses, the replays): the raw ray, filtered again there
@@ -201,9 +205,33 @@ __global__ void __launch_bounds__(128) exPrepRays(DeviceMap dm, Geom g, MapParam
         }
       }
     }
-    ex.smp_voxel[i] = voxel;
-    ex.smp_owner[i] = owner;
-    ex.smp_key[i] = key;
+    if (route_now)
+    {
+      if (voxel != kInvalidVoxel)
+      {
+        const uint32_t at = bucketAggregatedInc(ex.out_smp, owner);
+        if (at < ex.per)
+        {
+          char *dst = reinterpret_cast<char *>(ex.peer[owner].smp_in + (size_t)ex.rank * ex.per + at);
+          const double ts = own.timestamps ? own.timestamps[i] : 0.0;
+          const float intensity = own.intensities ? own.intensities[i] : 0.0f;
+          store32(dst, make_uint4((uint32_t)key, (uint32_t)(key >> 32), voxel, gid),
+                  make_uint4(0u, 0u, (uint32_t)__double_as_longlong(ts), (uint32_t)(__double_as_longlong(ts) >> 32)));
+          store32(dst + 32, make_uint4(__float_as_uint(intensity), 0u, (uint32_t)__double_as_longlong(raw[0]), (uint32_t)(__double_as_longlong(raw[0]) >> 32)),
+                  make_uint4((uint32_t)__double_as_longlong(raw[1]), (uint32_t)(__double_as_longlong(raw[1]) >> 32),
+                             (uint32_t)__double_as_longlong(raw[2]), (uint32_t)(__double_as_longlong(raw[2]) >> 32)));
+          store32(dst + 64, make_uint4((uint32_t)__double_as_longlong(raw[3]), (uint32_t)(__double_as_longlong(raw[3]) >> 32),
+                                       (uint32_t)__double_as_longlong(raw[4]), (uint32_t)(__double_as_longlong(raw[4]) >> 32)),
+                  make_uint4((uint32_t)__double_as_longlong(raw[5]), (uint32_t)(__double_as_longlong(raw[5]) >> 32), 0u, 0u));
+        }
+      }
+    }
+    else
+    {
+      ex.smp_voxel[i] = voxel;
+      ex.smp_owner[i] = owner;
+      ex.smp_key[i] = key;
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k)
     {

@@ -488,19 +488,18 @@ int exchangeSend(ohmb200_map *m, const double *d_rays, size_t element_count, con
   CUDA_TRY(cudaMemsetAsync(x.out_counts, 0, sizeof(uint32_t) * 2 * kMaxWorld, s));
   if (n)
   {
+    const bool route_now = x.smp_last_exit == nullptr;  // no traversal layer: no exit range to carry first
     {
       KernelScope scope(m, kKExPrepRays);
-      exPrepRays<<<blocks, 128, 0, s>>>(m->dm, m->geom, m->mp, own, ex, m->mode, broadcast_rays ? 1 : 0);
+      exPrepRays<<<blocks, 128, 0, s>>>(m->dm, m->geom, m->mp, own, ex, m->mode, broadcast_rays ? 1 : 0, route_now ? 1 : 0);
     }
-    if (x.smp_last_exit)
+    if (!route_now)
     {
       rc = carryLastExit(m, n, s, x.smp_last_exit);
       if (rc)
       {
         return rc;
       }
-    }
-    {
       KernelScope scope(m, kKExRoute);
       exRouteSamples<<<blocks, 128, 0, s>>>(own, ex);
     }

@@ -19,7 +19,8 @@ namespace ohmb200
 {
 constexpr unsigned kRecValid = 1u << 3, kRecExcludeStart = 1u << 4, kRecExcludeEnd = 1u << 5;
 constexpr uint32_t kMaxSegmentsPerItem = 2048;  // < 32768: tile counters are 15 bit + flag
-constexpr uint32_t kRecordChunk = 256;  // ordered-miss records are reserved per warp in chunks
+constexpr uint32_t kRecordChunk = 64;   // ordered-miss records are reserved per warp in chunks (unused slots of a chunk are
+                                        // skipped by linkRecords: 256 per chunk left it four empty slots per record)
 // Counter tile addressing.  One u16 counter per voxel (15-bit count + flag bit), two per 32-bit word.  The tile is a
 // padded copy of the region, the position of a voxel LINEAR in its coordinates:
 //        position(x, y, z) = x + row * y + slab * z          (counters; row and slab are even)
