@@ -516,7 +516,16 @@ __global__ void __launch_bounds__(256) exBinSamples(DeviceMap dm, Geom g, Batch 
     const int s = exSender(in.smp_first, ex.world, j);
     const WireSample *smp = mine.smp_in + (size_t)s * ex.per + (j - in.smp_first[s]);
     const uint32_t ray = smp->ray;
-    const int slot = regionSlot(dm, smp->key);
+    // the lanes that hold the same region probe the table once (see exBinSegments)
+    const unsigned long long key = smp->key;
+    const unsigned peers = __match_any_sync(__activemask(), key);
+    const int leader = __ffs(peers) - 1;
+    int slot = -1;
+    if ((int)(threadIdx.x & 31u) == leader)
+    {
+      slot = regionSlot(dm, key);
+    }
+    slot = __shfl_sync(peers, slot, leader);
     if (slot >= 0)
     {
       b.keys_in[ray] = (uint32_t)slot * g.vpr + smp->voxel;

@@ -449,10 +449,12 @@ int exchangeSend(ohmb200_map *m, const double *d_rays, size_t element_count, con
         return OHMB200_OK;
       }
     }
+    // (met before: whatever the parity was — the two recordings of a shape then fall into its second and third step)
     bool met = false;
     for (auto &g : x.seen)
     {
-      met = met || same(g);
+      met = met || (g.rays == key.rays && g.intensities == key.intensities && g.timestamps == key.timestamps && g.n == key.n &&
+                    g.ray_flags == key.ray_flags && g.time_base == key.time_base);
     }
     if (!met)
     {

@@ -88,3 +88,25 @@ def test_region_owner_partitions_regions():
             for d in ([1, 0, 0], [0, 1, 0], [0, 0, 1]):
                 n = np.array([2 + d[0], 4 + d[1], d[2]], dtype=np.int16)
                 assert lib.ohmb200_region_owner(n.ctypes.data_as(C.POINTER(C.c_int16)), world) != a
+
+
+def test_reference_side_binding_defines_the_ohmgpu_classes():
+    """Where it was built (needs /root/reference): tests/binding/GpuMapB200.cpp, compiled against the reference's own
+    ohmgpu/GpuMap.h, GpuNdtMap.h, GpuTsdfMap.h and ohm/MapRegionCache.h, defines the classes OhmAppGpu links against and
+    reaches the device only through the C ABI (no compute here: symbols only)."""
+    import pytest
+    path = os.path.join(ROOT, "oracle", "_ref", "libohm_b200_binding.so")
+    if not os.path.exists(path):
+        pytest.skip("the binding is built only where /root/reference exists")
+    out = subprocess.check_output(["nm", "-DC", path]).decode()
+    defined = [line for line in out.splitlines() if " T " in line or " W " in line]
+    for symbol in ("ohm::GpuMap::GpuMap(ohm::OccupancyMap*, bool, unsigned int, unsigned long)", "ohm::GpuMap::integrateRays(",
+                   "ohm::GpuMap::syncVoxels()", "ohm::GpuMap::syncVoxels(std::vector<int", "ohm::GpuMap::setRayFilter(",
+                   "ohm::GpuMap::gpuCache() const", "ohm::GpuNdtMap::GpuNdtMap(", "ohm::GpuNdtMap::setSensorNoise(float)",
+                   "ohm::GpuTsdfMap::GpuTsdfMap(", "ohm::GpuTsdfMap::setTsdfOptions(", "ohm::gpumap::enableGpu(ohm::OccupancyMap&)",
+                   "ohm::gpumap::sync(ohm::OccupancyMap&)", "ohm::gpumap::gpuCache(ohm::OccupancyMap&)",
+                   "ohm::GpuCache::remove(", "ohm::GpuCache::clear()", "ohm::GpuCache::syncLayerTo(", "ohm::GpuCache::findLayerCache("):
+        assert any(symbol in line for line in defined), f"{symbol} is not defined by the binding"
+    undefined = [line.split(" U ")[1] for line in out.splitlines() if " U ohmb200_" in line]
+    assert "ohmb200_integrate" in undefined and "ohmb200_read_regions" in undefined  # it goes through the C ABI
+    assert "cuda" not in subprocess.check_output(["ldd", path]).decode().split("libohmb200")[0].lower()
