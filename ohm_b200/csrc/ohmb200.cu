@@ -1972,12 +1972,14 @@ int makeRoom(ohmb200_map *m, size_t need)
   const size_t count = std::min(live.size(), need - free_slots + capacity / 8u);
   std::vector<uint32_t> victims(live.begin(), live.begin() + count);
   PAGING_TRACE("makeRoom: evicting %zu regions, chunk %zu bytes", count, m->store_chunk_bytes);
+  // (the chunks enter the store only when every layer has arrived: a failure half-way must not leave stale copies of
+  // regions that are still resident)
+  std::vector<std::vector<char>> evicted(count);
   std::vector<std::vector<char> *> chunks(count);
   for (size_t i = 0; i < count; ++i)
   {
-    std::vector<char> &chunk = m->store[keys[victims[i]]];
-    chunk.resize(m->store_chunk_bytes);
-    chunks[i] = &chunk;
+    evicted[i].resize(m->store_chunk_bytes);
+    chunks[i] = &evicted[i];
   }
   for (int l = 0; l < OHMB200_LAYER_COUNT; ++l)
   {
@@ -2001,6 +2003,10 @@ int makeRoom(ohmb200_map *m, size_t need)
   if (rc)
   {
     return rc;
+  }
+  for (size_t i = 0; i < count; ++i)
+  {
+    m->store[keys[victims[i]]] = std::move(evicted[i]);
   }
   CUDA_TRY(cudaMemcpyAsync(m->d_gather_slots, victims.data(), sizeof(uint32_t) * count, cudaMemcpyHostToDevice, m->stream));
   const ClearTable clear_table = makeClearTable(m);
@@ -2336,7 +2342,7 @@ ohmb200_map *ohmb200_create(const ohmb200_params *params, int mode, size_t devic
       cudaGetLastError();
       m->algo = 0;
     }
-    m->walk_ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(kWalkCtasPerSm, (226u * 1024u) / (m->tile_bytes + 6u * 1024u)));
+    m->walk_ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(kWalkCtasPerSm, (226u * 1024u) / (m->tile_bytes + 40u * 1024u)));  // + ~38 KB static: staged segments, queue, ladder
   }
   size_t bytes_per_region = (m->algo == 0) ? sizeof(uint32_t) * m->geom.vpr : 3 * sizeof(uint32_t);  // pending / counters
   if (tsdf)
@@ -2833,7 +2839,10 @@ int ohmb200_read_regions(ohmb200_map *m, int layer, const int16_t *keys_xyz, siz
   cudaSetDevice(m->device);
   if (!m->store.empty())
   {
-    // some regions live in the host store (paging): those are copied from there, the others read one by one
+    // some regions live in the host store (paging): those are copied from there; the resident ones are looked up with
+    // ONE download of the key table and gathered together
+    std::vector<size_t> resident;
+    std::vector<int16_t> resident_keys;
     for (size_t i = 0; i < count; ++i)
     {
       const int16_t *k = keys_xyz + 3 * i;
@@ -2843,13 +2852,28 @@ int ohmb200_read_regions(ohmb200_map *m, int layer, const int16_t *keys_xyz, siz
         memcpy((char *)dst + i * chunk, it->second.data() + m->store_layer_offset[layer], chunk);
         continue;
       }
-      std::vector<uint32_t> slot;
-      int rc1 = findSlots(m, k, 1, slot);
-      rc1 = rc1 ? rc1 : downloadSlots(m, layer, slot.data(), 1, (char *)dst + i * chunk, chunk);
-      if (rc1)
-      {
-        return rc1;
-      }
+      resident.push_back(i);
+      resident_keys.insert(resident_keys.end(), k, k + 3);
+    }
+    if (resident.empty())
+    {
+      return OHMB200_OK;
+    }
+    std::vector<uint32_t> resident_slots;
+    int rc1 = findSlots(m, resident_keys.data(), resident.size(), resident_slots);
+    if (rc1)
+    {
+      return rc1;
+    }
+    std::vector<char> gathered(resident.size() * chunk);
+    rc1 = downloadSlots(m, layer, resident_slots.data(), resident.size(), gathered.data(), chunk);
+    if (rc1)
+    {
+      return rc1;
+    }
+    for (size_t j = 0; j < resident.size(); ++j)
+    {
+      memcpy((char *)dst + resident[j] * chunk, gathered.data() + j * chunk, chunk);
     }
     return OHMB200_OK;
   }

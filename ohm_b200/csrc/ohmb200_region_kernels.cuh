@@ -680,17 +680,77 @@ __device__ __forceinline__ uint32_t reserveRecord(unsigned long long *warp_chunk
   return __shfl_sync(group, at, __ffs(group) - 1) + rank;
 }
 
+// ---- bulk asynchronous copies (TMA unit, cp.async.bulk + mbarrier) -------------------------------------------------
+// The segments of a work item are one contiguous range of 16-byte records (<= 32 KB): ONE cp.async.bulk brings them
+// into shared memory while the CTA is still folding the item before — issued by one thread, completion counted in
+// bytes on an mbarrier the whole CTA waits on at the top of the next item.  queueBuild's two passes over the segments
+// and every queuePop then read shared memory instead of going to L2 / HBM behind a dependent index.
+__device__ __forceinline__ uint32_t smemAddress(const void *p)
+{
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbarInit(unsigned long long *mbar, uint32_t arrivals)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddress(mbar)), "r"(arrivals) : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the async proxy must see the initialised barrier
+}
+
+// One thread: expect `bytes` on the barrier and start the global -> shared bulk copy that delivers them.
+__device__ __forceinline__ void bulkLoad(void *smem_dst, const void *global_src, uint32_t bytes, unsigned long long *mbar)
+{
+  // everything the CTA read from / wrote to smem_dst through the generic proxy is ordered before the copy's writes
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddress(mbar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                 smemAddress(smem_dst)),
+               "l"(global_src), "r"(bytes), "r"(smemAddress(mbar))
+               : "memory");
+}
+
+// Every thread that reads the copied bytes: wait for the barrier's phase `parity` to complete.
+__device__ __forceinline__ void mbarWait(unsigned long long *mbar, uint32_t parity)
+{
+  const uint32_t addr = smemAddress(mbar);
+  uint32_t done = 0;
+  do
+  {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done)
+                 : "r"(addr), "r"(parity)
+                 : "memory");
+  } while (!done);
+}
+
 // The segments of a work item, ordered by decreasing visit count and handed to warps 32 at a time: the lanes of a warp
 // walk segments of (nearly) equal length, long segments start first, and a warp that finishes early takes more.
 struct SegmentQueue
 {
+  uint4 staged[kMaxSegmentsPerItem];  // the item's segments (bulk copy, see above)
+  unsigned long long mbar;            // its completion barrier
   uint16_t order[kMaxSegmentsPerItem];
   uint32_t length_bins[kLengthBins];
   uint32_t next_chunk;
 };
 
-// Every thread of the CTA calls this (it synchronises); the previous item's pops must be behind a barrier already.
-__device__ __forceinline__ void queueBuild(SegmentQueue &q, const Batch &b, const WorkItem &item)
+// One thread, once per kernel.
+__device__ __forceinline__ void queueInit(SegmentQueue &q)
+{
+  mbarInit(&q.mbar, 1u);
+}
+
+// One thread: start bringing the segments of `item` into q.staged.  The previous item's pops are behind a barrier.
+__device__ __forceinline__ void queueStage(SegmentQueue &q, const Batch &b, const WorkItem &item)
+{
+  if (item.slot != 0xFFFFFFFFu)
+  {
+    bulkLoad(q.staged, b.segments + item.begin, (item.end - item.begin) * (uint32_t)sizeof(Segment), &q.mbar);
+  }
+}
+
+// Every thread of the CTA calls this (it synchronises); `stage_parity` = number of items this CTA has staged before
+// this one, mod 2 (the phase of the copy's barrier).
+__device__ __forceinline__ void queueBuild(SegmentQueue &q, const Batch &b, const WorkItem &item, uint32_t stage_parity)
 {
   const uint32_t tid = threadIdx.x;
   if (tid < kLengthBins)
@@ -701,9 +761,10 @@ __device__ __forceinline__ void queueBuild(SegmentQueue &q, const Batch &b, cons
   {
     q.next_chunk = 0;
   }
+  mbarWait(&q.mbar, stage_parity);  // the item's segments are in shared memory
   __syncthreads();
   const uint32_t n_segments = item.end - item.begin;
-  const uint32_t *segment_words = reinterpret_cast<const uint32_t *>(b.segments + item.begin);
+  const uint32_t *segment_words = reinterpret_cast<const uint32_t *>(q.staged);
   for (uint32_t k = tid; k < n_segments; k += blockDim.x)
   {
     const uint32_t visits = segment_words[4 * k + 2] >> 16;
@@ -763,7 +824,7 @@ __device__ __forceinline__ int queuePop(SegmentQueue &q, const Batch &b, const W
   {
     return 2;
   }
-  raw = reinterpret_cast<const uint4 *>(b.segments)[item.begin + q.order[k]];
+  raw = q.staged[q.order[k]];
   return 1;
 }
 
@@ -1245,7 +1306,10 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegions(cons
   if (tid == 0)
   {
     loadWorkItem(b, atomicAdd(&b.counters->work_next, 1u), &items2[0]);
+    queueInit(queue);
+    queueStage(queue, b, items2[0]);
   }
+  uint32_t stage_parity = 1;  // phase of the segment copy's barrier for the item at hand (flipped at the loop top)
 #ifdef OHMB200_PHASE_CLOCKS
   long long ph[7] = { 0, 0, 0, 0, 0, 0, 0 }, tc[7];
 
@@ -1258,6 +1322,7 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegions(cons
   for (;;)
   {
     parity ^= 1u;
+    stage_parity ^= 1u;
     __syncthreads();  // the item is in place; the previous fold is done with the tile
     const WorkItem &item = items2[parity];
     if (item.slot == 0xFFFFFFFFu)
@@ -1302,7 +1367,7 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegions(cons
         atomicOr(&tile[half >> 1], kTileFlag << ((half & 1u) * 16u));
       }
     }
-    queueBuild(queue, b, item);
+    queueBuild(queue, b, item, stage_parity);
     PHASE(2);
     uint32_t next_work = 0;
     if (tid == 0)
@@ -1364,6 +1429,10 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegions(cons
       fold_ticket = 0;
     }
     __syncthreads();
+    if (tid == 0)
+    {
+      queueStage(queue, b, items2[parity ^ 1u]);  // the next item's segments arrive while this one is folded
+    }
     PHASE(4);
 
     // Fold the miss counts into the occupancy slab.  k identical misses commute, so the count is all that matters.
@@ -1562,10 +1631,14 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegionsNdt(c
   if (tid == 0)
   {
     loadWorkItem(b, atomicAdd(&b.counters->work_next, 1u), &items2[0]);
+    queueInit(queue);
+    queueStage(queue, b, items2[0]);
   }
+  uint32_t stage_parity = 1;  // phase of the segment copy's barrier for the item at hand (flipped at the loop top)
   for (;;)
   {
     parity ^= 1u;
+    stage_parity ^= 1u;
     __syncthreads();  // the item is in place; the previous fold is done with the tile
     const WorkItem &item = items2[parity];
     if (item.slot == 0xFFFFFFFFu)
@@ -1620,7 +1693,7 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegionsNdt(c
       const uint32_t half = tileHalf(tl, b.keys_out[s] - vbase);
       atomicOr(&tile[half >> 1], kTileFlag << ((half & 1u) * 16u));
     }
-    queueBuild(queue, b, item);
+    queueBuild(queue, b, item, stage_parity);
     uint32_t next_work = 0;
     if (tid == 0)
     {
@@ -1694,6 +1767,10 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegionsNdt(c
       fold_ticket = 0;
     }
     __syncthreads();
+    if (tid == 0)
+    {
+      queueStage(queue, b, items2[parity ^ 1u]);  // the next item's segments arrive while this one is folded
+    }
 
     // Fold.  Plain voxels: k identical misses (RayMapperNdt applies no exclusion flags).  Gaussian voxels: the
     // adjustments are already in the slab; apply occupancyAdjustDown's clamp.

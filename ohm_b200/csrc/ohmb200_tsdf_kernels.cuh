@@ -265,10 +265,14 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegionsTsdf(
   if (tid == 0)
   {
     loadWorkItem(b, atomicAdd(&b.counters->work_next, 1u), &items2[0]);
+    queueInit(queue);
+    queueStage(queue, b, items2[0]);
   }
+  uint32_t stage_parity = 1;
   for (;;)
   {
     parity ^= 1u;
+    stage_parity ^= 1u;
     __syncthreads();  // the item is in place; the previous fold is done with the tile
     const WorkItem &item = items2[parity];
     if (item.slot == 0xFFFFFFFFu)
@@ -301,7 +305,7 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegionsTsdf(
         }
       }
     }
-    queueBuild(queue, b, item);
+    queueBuild(queue, b, item, stage_parity);
     uint32_t next_work = 0;
     if (tid == 0)
     {
@@ -345,6 +349,10 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegionsTsdf(
       fold_ticket = 0;
     }
     __syncthreads();
+    if (tid == 0)
+    {
+      queueStage(queue, b, items2[parity ^ 1u]);  // the next item's segments arrive while this one is folded
+    }
 
     foldTsdfTile(tile, tl, dm.tsdf + (size_t)vbase, mp, &fold_ticket, item.shared);
   }

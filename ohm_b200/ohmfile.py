@@ -202,7 +202,7 @@ def read_ohm(path):
     for _ in range(layer_count):
         (n,) = r.take("<I")
         name = r.raw(n).decode()
-        _, _, voxel_bytes, member_count = r.take("<IHII")
+        layer_flags, _, voxel_bytes, member_count = r.take("<IHII")
         members = []
         for _ in range(member_count):
             (n,) = r.take("<I")
@@ -214,14 +214,16 @@ def read_ohm(path):
             expect = [(m, k, o) for m, k, o, _ in LAYER_LAYOUT[layer][1]]
             if voxel_bytes != _VOXEL_BYTES[layer] or [(m, k, o) for m, k, o, _ in members] != expect:
                 raise OhmFileError(f"layer {name}: voxel layout differs from the built-in one")
-        file_layers.append((layer, name, voxel_bytes))
+        file_layers.append((layer, name, voxel_bytes, layer_flags))
     voxels = dims[0] * dims[1] * dims[2]
     regions = {}
     for _ in range(region_count):
         key = r.take("<3i")
         r.take("<3dd")
         blocks = {}
-        for layer, name, voxel_bytes in file_layers:
+        for layer, name, voxel_bytes, layer_flags in file_layers:
+            if layer_flags & 1:
+                continue  # MapLayer::kSkipSerialise: no stamp, no block in the file (MapSerialiseV0.4.cpp:60-65)
             r.take("<Q")
             block = r.raw(voxels * voxel_bytes)
             if layer is not None:
@@ -231,8 +233,8 @@ def read_ohm(path):
         regions[tuple(int(k) for k in key)] = blocks
     header = dict(resolution=res, origin=tuple(origin), region_dim=tuple(dims), threshold_value=threshold, hit_value=hit,
                   miss_value=miss, first_ray_time=first_ray_time, stamp=stamp, flags=flags, version=(major, minor, patch),
-                  layers=[l for l, _, _ in file_layers if l is not None], layer_names=[n for _, n, _ in file_layers],
-                  unknown_layers=[n for l, n, _ in file_layers if l is None])
+                  layers=[f[0] for f in file_layers if f[0] is not None], layer_names=[f[1] for f in file_layers],
+                  unknown_layers=[f[1] for f in file_layers if f[0] is None])
     return header, regions, info
 
 
