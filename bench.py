@@ -526,7 +526,7 @@ def run_single(args, torch):
     dom_name = max(per_kernel, key=per_kernel.get) if per_kernel else "walkRegions"
     dom_ms = per_kernel.get(dom_name, 0.0)
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-    traffic, traffic_how = ncu_traffic(dom_name)
+    traffic, traffic_how = ncu_traffic({3: "walkRegionsNdt", 4: "walkRegionsTsdf"}.get(args.config, "walkRegions") if dom_name == "walkRegions" else dom_name)
     cpu = cpu_baseline(args.config, sweeps, args.cpu_reps) if args.cpu_reps > 0 else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,

@@ -2342,6 +2342,15 @@ ohmb200_map *ohmb200_create(const ohmb200_params *params, int mode, size_t devic
       cudaGetLastError();
       m->algo = 0;
     }
+    if (const char *env = getenv("OHMB200_CARVEOUT"))  // percent of the SM's shared memory + L1 to prefer as shared (experiments)
+    {
+      const int pct = atoi(env);
+      cudaFuncSetAttribute(walkRegions<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      cudaFuncSetAttribute(walkRegions<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      cudaFuncSetAttribute(walkRegionsNdt<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      cudaFuncSetAttribute(walkRegionsNdt<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      cudaFuncSetAttribute(walkRegionsTsdf, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }
     m->walk_ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(kWalkCtasPerSm, (226u * 1024u) / (m->tile_bytes + 40u * 1024u)));  // + ~38 KB static: staged segments, queue, ladder
   }
   size_t bytes_per_region = (m->algo == 0) ? sizeof(uint32_t) * m->geom.vpr : 3 * sizeof(uint32_t);  // pending / counters

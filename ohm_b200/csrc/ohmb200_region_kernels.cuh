@@ -1309,7 +1309,6 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegions(cons
     queueInit(queue);
     queueStage(queue, b, items2[0]);
   }
-  uint32_t stage_parity = 1;  // phase of the segment copy's barrier for the item at hand (flipped at the loop top)
 #ifdef OHMB200_PHASE_CLOCKS
   long long ph[7] = { 0, 0, 0, 0, 0, 0, 0 }, tc[7];
 
@@ -1322,7 +1321,6 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegions(cons
   for (;;)
   {
     parity ^= 1u;
-    stage_parity ^= 1u;
     __syncthreads();  // the item is in place; the previous fold is done with the tile
     const WorkItem &item = items2[parity];
     if (item.slot == 0xFFFFFFFFu)
@@ -1367,7 +1365,7 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegions(cons
         atomicOr(&tile[half >> 1], kTileFlag << ((half & 1u) * 16u));
       }
     }
-    queueBuild(queue, b, item, stage_parity);
+    queueBuild(queue, b, item, parity);  // (the copy barrier's phase flips with the item slot)
     PHASE(2);
     uint32_t next_work = 0;
     if (tid == 0)
@@ -1634,11 +1632,9 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegionsNdt(c
     queueInit(queue);
     queueStage(queue, b, items2[0]);
   }
-  uint32_t stage_parity = 1;  // phase of the segment copy's barrier for the item at hand (flipped at the loop top)
   for (;;)
   {
     parity ^= 1u;
-    stage_parity ^= 1u;
     __syncthreads();  // the item is in place; the previous fold is done with the tile
     const WorkItem &item = items2[parity];
     if (item.slot == 0xFFFFFFFFu)
@@ -1693,7 +1689,7 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegionsNdt(c
       const uint32_t half = tileHalf(tl, b.keys_out[s] - vbase);
       atomicOr(&tile[half >> 1], kTileFlag << ((half & 1u) * 16u));
     }
-    queueBuild(queue, b, item, stage_parity);
+    queueBuild(queue, b, item, parity);  // (the copy barrier's phase flips with the item slot)
     uint32_t next_work = 0;
     if (tid == 0)
     {

@@ -18,7 +18,10 @@
 namespace ohmb200
 {
 constexpr unsigned kRecValid = 1u << 3, kRecExcludeStart = 1u << 4, kRecExcludeEnd = 1u << 5;
-constexpr uint32_t kMaxSegmentsPerItem = 2048;  // < 32768: tile counters are 15 bit + flag
+#ifndef OHMB200_ITEM_SEGMENTS
+#define OHMB200_ITEM_SEGMENTS 2048
+#endif
+constexpr uint32_t kMaxSegmentsPerItem = OHMB200_ITEM_SEGMENTS;  // < 32768: tile counters are 15 bit + flag
 constexpr uint32_t kRecordChunk = 64;   // ordered-miss records are reserved per warp in chunks (unused slots of a chunk are
                                         // skipped by linkRecords: 256 per chunk left it four empty slots per record)
 // Counter tile addressing.  One u16 counter per voxel (15-bit count + flag bit), two per 32-bit word.  The tile is a

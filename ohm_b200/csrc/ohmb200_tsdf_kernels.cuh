@@ -268,11 +268,9 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegionsTsdf(
     queueInit(queue);
     queueStage(queue, b, items2[0]);
   }
-  uint32_t stage_parity = 1;
   for (;;)
   {
     parity ^= 1u;
-    stage_parity ^= 1u;
     __syncthreads();  // the item is in place; the previous fold is done with the tile
     const WorkItem &item = items2[parity];
     if (item.slot == 0xFFFFFFFFu)
@@ -305,7 +303,7 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegionsTsdf(
         }
       }
     }
-    queueBuild(queue, b, item, stage_parity);
+    queueBuild(queue, b, item, parity);  // (the copy barrier's phase flips with the item slot)
     uint32_t next_work = 0;
     if (tid == 0)
     {
