@@ -116,8 +116,8 @@ __device__ __forceinline__ uint32_t bucketAggregatedInc(uint32_t *counters, uint
 
 // Filter, walk constants and sample voxel of this rank's own rays.  The RayRec goes to the rank's own arena (the
 // broadcast copies it on); the sample is parked in scratch until exRouteSamples.
-// route_now: the sample record leaves from here (no traversal layer: nothing to wait for); else exRouteSamples sends it
-// once carryLastExit has run.
+// route_now: the sample record leaves from here (no traversal layer: nothing to wait for) — 1: the full 96-byte record,
+// 2: the 16-byte record of an occupancy-only map; 0: exRouteSamples sends it once carryLastExit has run.
 __global__ void __launch_bounds__(128) exPrepRays(DeviceMap dm, Geom g, MapParams mp, Batch own, ExStep ex, int mode, int copy_rays,
                                                   int route_now)
 {
@@ -205,7 +205,20 @@ __global__ void __launch_bounds__(128) exPrepRays(DeviceMap dm, Geom g, MapParam
         }
       }
     }
-    if (route_now)
+    if (route_now == 2)
+    {
+      // an occupancy-only map: the owner replays the hit from (voxel, ray order) alone — a 16-byte record
+      if (voxel != kInvalidVoxel)
+      {
+        const uint32_t at = bucketAggregatedInc(ex.out_smp, owner);
+        if (at < ex.per)
+        {
+          reinterpret_cast<uint4 *>(ex.peer[owner].smp_in)[(size_t)ex.rank * ex.per + at] =
+            make_uint4((uint32_t)key, (uint32_t)(key >> 32), voxel, gid);
+        }
+      }
+    }
+    else if (route_now)
     {
       if (voxel != kInvalidVoxel)
       {
@@ -514,10 +527,24 @@ __global__ void __launch_bounds__(256) exBinSamples(DeviceMap dm, Geom g, Batch 
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < total_smps; j += stride)
   {
     const int s = exSender(in.smp_first, ex.world, j);
-    const WireSample *smp = mine.smp_in + (size_t)s * ex.per + (j - in.smp_first[s]);
-    const uint32_t ray = smp->ray;
+    const size_t at = (size_t)s * ex.per + (j - in.smp_first[s]);
+    const WireSample *smp = mine.smp_in + at;
+    uint32_t ray, voxel;
+    unsigned long long key;
+    if (rays_from_samples == 2)
+    {
+      const uint4 lite = reinterpret_cast<const uint4 *>(mine.smp_in)[at];  // {key, voxel, ray}: occupancy-only map
+      key = (unsigned long long)lite.x | ((unsigned long long)lite.y << 32);
+      voxel = lite.z;
+      ray = lite.w;
+    }
+    else
+    {
+      key = smp->key;
+      voxel = smp->voxel;
+      ray = smp->ray;
+    }
     // the lanes that hold the same region probe the table once (see exBinSegments)
-    const unsigned long long key = smp->key;
     const unsigned peers = __match_any_sync(__activemask(), key);
     const int leader = __ffs(peers) - 1;
     int slot = -1;
@@ -528,10 +555,10 @@ __global__ void __launch_bounds__(256) exBinSamples(DeviceMap dm, Geom g, Batch 
     slot = __shfl_sync(peers, slot, leader);
     if (slot >= 0)
     {
-      b.keys_in[ray] = (uint32_t)slot * g.vpr + smp->voxel;
+      b.keys_in[ray] = (uint32_t)slot * g.vpr + voxel;
       b.vals_in[ray] = ray;
     }
-    if (rays_from_samples)
+    if (rays_from_samples == 1)
     {
 #pragma unroll
       for (int k = 0; k < 6; ++k)
@@ -543,7 +570,7 @@ __global__ void __launch_bounds__(256) exBinSamples(DeviceMap dm, Geom g, Batch 
     }
     if (b.last_exit)
     {
-      b.last_exit[ray] = smp->last_exit;
+      b.last_exit[ray] = smp->last_exit;  // (a map with the traversal layer never takes the 16-byte records)
     }
   }
 }

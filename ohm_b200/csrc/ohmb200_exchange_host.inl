@@ -318,6 +318,13 @@ void exFillStep(ohmb200_map *m, ExStep &ex)
   }
 }
 
+// An occupancy map with no per-sample layer: the owner replays a hit from (voxel, ray order) alone, so the sample
+// records shrink from 96 to 16 bytes (hit value only: no mean, incident normal, touch time or traversal to update).
+bool exLiteSamples(const ohmb200_map *m)
+{
+  return m->mode == OHMB200_MODE_OCCUPANCY && !m->dm.mean && !m->dm.traversal && !m->dm.touch_time && !m->dm.incident;
+}
+
 bool exNdt(const ohmb200_map *m)
 {
   return m->mode == OHMB200_MODE_NDT || m->mode == OHMB200_MODE_NDT_TM;
@@ -351,7 +358,7 @@ int exSampleBranch(ohmb200_map *m, const ExStep &ex)
   }
   {
     KernelScope scope(m, kKExBinSamples);
-    exBinSamples<<<(unsigned)m->sm_count * 4u, 256, 0, ss>>>(m->dm, m->geom, b, ex, exNdt(m) ? 0 : 1);
+    exBinSamples<<<(unsigned)m->sm_count * 4u, 256, 0, ss>>>(m->dm, m->geom, b, ex, exNdt(m) ? 0 : (exLiteSamples(m) ? 2 : 1));
   }
   {
     KernelScope scope(m, kKSort);
@@ -493,7 +500,8 @@ int exchangeSend(ohmb200_map *m, const double *d_rays, size_t element_count, con
     const bool route_now = x.smp_last_exit == nullptr;  // no traversal layer: no exit range to carry first
     {
       KernelScope scope(m, kKExPrepRays);
-      exPrepRays<<<blocks, 128, 0, s>>>(m->dm, m->geom, m->mp, own, ex, m->mode, broadcast_rays ? 1 : 0, route_now ? 1 : 0);
+      exPrepRays<<<blocks, 128, 0, s>>>(m->dm, m->geom, m->mp, own, ex, m->mode, broadcast_rays ? 1 : 0,
+                                        route_now ? (exLiteSamples(m) ? 2 : 1) : 0);
     }
     if (!route_now)
     {
