@@ -647,12 +647,20 @@ def run_sharded(args, torch, dist, rank, local_rank, world, gloo):
     device_step()
     torch.cuda.synchronize()
     st = gpu.stats()
-    mine_counts = [st["rays_accepted"], st["voxel_visits"], st["sample_updates"], st["regions"]]
+    seg_out, smp_out = gpu.exchange_last_counts(world)
+    # NVLink bytes this rank wrote in the step: 32 B per segment record and 16 B per sample record (occupancy-only map) whose
+    # owner is another GPU, + the 64-byte walk constants of every own ray to each of the other GPUs (copy engines)
+    nvlink_bytes = (32 * sum(c for r, c in enumerate(seg_out) if r != rank) + 16 * sum(c for r, c in enumerate(smp_out) if r != rank)
+                    + 64 * n_mine * (world - 1))
+    mine_counts = [st["rays_accepted"], st["voxel_visits"], st["sample_updates"], st["regions"], nvlink_bytes,
+                   sum(seg_out), st["owned_visits"]]
     all_counts = [None] * world
     dist.all_gather_object(all_counts, mine_counts, group=gloo)
     all_ktimes = [None] * world
     dist.all_gather_object(all_ktimes, ktimes, group=gloo)
     accepted, visits, samples, regions = (sum(c[i] for c in all_counts) for i in range(4))
+    nvlink_max = max(c[4] for c in all_counts)
+    segments_total = sum(c[5] for c in all_counts)
     ms_per_step = t_ms / args.steps
     value = n_step / (ms_per_step * 1e-3) / 1e6
 
@@ -797,7 +805,7 @@ def run_sharded(args, torch, dist, rank, local_rank, world, gloo):
     if dom_name == "exWait":  # the wait for the slowest peer is not a kernel of ours to rate
         dom_name = max((k for k in kmax if k != "exWait"), key=kmax.get)
     dom_ms = kmax[dom_name]
-    heaviest = max(c[1] for c in all_counts)
+    heaviest = max(c[6] for c in all_counts)  # the visits the busiest OWNER applied
     achieved = (8 * heaviest + 44 * n_step / world) / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     traffic, traffic_how = ncu_traffic(dom_name)
     ndt_value = ndt_rays / (ndt_ms * 1e-3) / 1e6
@@ -817,10 +825,7 @@ def run_sharded(args, torch, dist, rank, local_rank, world, gloo):
                            "copy engine; mailbox flags + a bounded device-side wait order the step (ohmb200_exchange_*); no "
                            "NCCL on the data path (torch.distributed carries the IPC handles, the barriers and the timing "
                            "reductions)",
-            "nvlink_bytes_per_rank_per_step": {
-                "walk_constants_by_copy_engine": int(64 * n_mine * (world - 1)),
-                "sample_records_upper_bound": int(96 * n_mine),
-                "segment_records": "32 B x the segments of the own sweep whose region another GPU owns (about (N-1)/N of ~1 M)"},
+            "segments_per_step": segments_total,
             "visits_share_of_heaviest_owner": heaviest / (visits / world) if visits else None,
             "l2": "map cleared + 512 MiB L2 flush between timed steps (outside the timed spans)",
             "timing": "CUDA events on the launch stream per step around send + integrate, max over ranks, summed over steps",
@@ -839,6 +844,15 @@ def run_sharded(args, torch, dist, rank, local_rank, world, gloo):
             "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_how,
             "algorithmic_bytes_per_launch": int(8 * heaviest + 44 * n_step / world), "kernel_ms": dom_ms,
             "peak_source": peak_src, "model": cfg["model"] + ", the heaviest owner's visits",
+        },
+        "exchange": {
+            "nvlink_bytes_per_rank_per_step": int(nvlink_max),
+            "what": "bytes the busiest rank writes to its peers in one step: 32 B x segment records + 16 B x sample records whose "
+                    "owner is another GPU (peer stores from the cut kernels) + 64 B walk constants x own rays x (N - 1) peers "
+                    "(copy engines, beside the cut)",
+            "link_floor_ms": nvlink_max / 770e9 * 1e3,
+            "link_peak": "770 GB/s per direction per GPU (measured peer copy on this pool, B200_PROFILING.md; 900 nominal)",
+            "share_of_step_at_link_peak": (nvlink_max / 770e9 * 1e3) / ms_per_step,
         },
         "config5": {
             "workload": f"BASELINE configs[4] shape: GpuNdtMap (NdtMode::kOccupancy), 0.1 m voxels, moving sensor, regions sharded "

@@ -136,6 +136,8 @@ typedef struct ohmb200_stats
   uint64_t batches;          /* integrate calls */
   uint64_t kernel_launches;  /* kernels launched by this library */
   uint64_t sample_voxels;    /* S': distinct sample voxels per batch, summed over batches (NDT byte model) */
+  uint64_t owned_visits;     /* voxel visits applied to THIS map's regions (== voxel_visits unless the exchange routes
+                              * other ranks' segments here: then voxel_visits counts what this rank's own rays cut) */
 } ohmb200_stats;
 
 typedef struct ohmb200_map ohmb200_map;
@@ -302,6 +304,11 @@ OHMB200_API size_t ohmb200_exchange_send_device(ohmb200_map *map, const double *
                                                 unsigned ray_flags);
 OHMB200_API int ohmb200_exchange_integrate(ohmb200_map *map);
 OHMB200_API int ohmb200_exchange_close(ohmb200_map *map);
+/* What this rank put into each owner's inbox in the last step (waits for the queued work): segment records (32 bytes
+ * each) and sample records (96 bytes, 16 on an occupancy-only map), `world` entries each; either pointer may be NULL.
+ * With the per-ray broadcast (64 bytes x own rays x (world - 1) peers; + 60 for NDT maps, + 8 with the traversal
+ * layer) this is the step's NVLink traffic — the number a link-bandwidth roofline of the exchange needs. */
+OHMB200_API int ohmb200_exchange_last_counts(ohmb200_map *map, uint32_t *segments, uint32_t *samples, int capacity);
 
 /* Per-kernel CUDA-event timing on the map's stream (bench.py's roofline numbers).  When enabled every launch is
  * bracketed by events; ohmb200_kernel_times drains {name -> accumulated ms, launches}. */

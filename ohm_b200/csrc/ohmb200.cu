@@ -98,6 +98,7 @@ struct Counters
   int table_full;
   int overflow_seen;  // bit 0: an ordered-record list overflowed (results incomplete); bit 1: the segment list did (batch dropped)
   unsigned long long sample_voxels;  // S': distinct sample voxels, summed over batches (the NDT byte model's unit)
+  unsigned long long owned_visits;   // exchange: voxel visits of the segments routed to THIS rank (voxel_visits counts the sender's)
   uint32_t batch_stamp;  // stamp of the last batch planRegions saw (read on the device: a replayed graph bakes no stamp)
 };
 constexpr int kPerBatchCounterWords = 11;  // record_count .. new_count
@@ -3391,6 +3392,7 @@ int ohmb200_get_stats(ohmb200_map *m, ohmb200_stats *stats)
   stats->batches = m->batches;
   stats->kernel_launches = m->launches;
   stats->sample_voxels = m->h_counters->sample_voxels;
+  stats->owned_visits = m->ex.open ? m->h_counters->owned_visits : m->h_counters->voxel_visits;
   return OHMB200_OK;
 }
 
@@ -3577,6 +3579,30 @@ int ohmb200_exchange_integrate(ohmb200_map *m)
 int ohmb200_exchange_close(ohmb200_map *m)
 {
   return exchangeClose(m);
+}
+
+int ohmb200_exchange_last_counts(ohmb200_map *m, uint32_t *segments, uint32_t *samples, int capacity)
+{
+  if (!m || !m->ex.open || capacity < m->ex.world)
+  {
+    return setError(OHMB200_E_INVALID, "ohmb200_exchange_last_counts: no open exchange, or capacity < world");
+  }
+  cudaSetDevice(m->device);
+  uint32_t counts[2 * kMaxWorld];
+  CUDA_TRY(cudaMemcpyAsync(counts, m->ex.out_counts, sizeof(counts), cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  for (int r = 0; r < m->ex.world; ++r)
+  {
+    if (segments)
+    {
+      segments[r] = counts[r];
+    }
+    if (samples)
+    {
+      samples[r] = counts[kMaxWorld + r];
+    }
+  }
+  return OHMB200_OK;
 }
 
 }  // extern "C"

@@ -486,6 +486,7 @@ __global__ void __launch_bounds__(256) exBinSegments(DeviceMap dm, Batch b, ExSt
   const uint32_t total_segs = in.seg_first[kMaxWorld];
   const uint32_t stride = gridDim.x * blockDim.x;
   const uint32_t lane = threadIdx.x & 31u;
+  unsigned visits = 0;
   for (uint32_t base = blockIdx.x * blockDim.x; base < total_segs; base += stride)
   {
     const uint32_t j = base + threadIdx.x;
@@ -494,6 +495,7 @@ __global__ void __launch_bounds__(256) exBinSegments(DeviceMap dm, Batch b, ExSt
       const int s = exSender(in.seg_first, ex.world, j);
       WireSegment *ws = mine.seg_in + (size_t)s * ex.seg_cap + (j - in.seg_first[s]);
       const unsigned long long key = (unsigned long long)ws->key_lo | ((unsigned long long)ws->key_hi << 32);
+      visits += ws->seg.z >> 16;
       const unsigned peers = __match_any_sync(__activemask(), key);
       const int leader = __ffs(peers) - 1;
       int slot = -1;
@@ -508,6 +510,11 @@ __global__ void __launch_bounds__(256) exBinSegments(DeviceMap dm, Batch b, ExSt
       slot = __shfl_sync(peers, slot, leader);
       ws->slot = (uint32_t)slot;
     }
+  }
+  visits = __reduce_add_sync(0xffffffffu, visits);
+  if (lane == 0 && visits)
+  {
+    atomicAdd(&b.counters->owned_visits, (unsigned long long)visits);
   }
 }
 

@@ -361,6 +361,13 @@ class GpuMap:
         """Phase 2: wait (on the device) for every rank's records of the step, integrate what was routed here."""
         self._check(self.L.ohmb200_exchange_integrate(self.h))
 
+    def exchange_last_counts(self, world):
+        """(segment records, sample records) this rank sent to each owner in the last step."""
+        seg = (C.c_uint32 * world)()
+        smp = (C.c_uint32 * world)()
+        self._check(self.L.ohmb200_exchange_last_counts(self.h, seg, smp, world))
+        return list(seg), list(smp)
+
     def exchange_close(self):
         self._check(self.L.ohmb200_exchange_close(self.h))
 
