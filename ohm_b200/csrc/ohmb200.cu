@@ -1010,6 +1010,8 @@ struct ohmb200_map
   size_t tile_bytes = 0;  // dynamic shared memory of walkRegions
   TileLayout tile;        // layout of the shared-memory counter tile
   int walk_ctas_per_sm = 1;
+  bool slab_walk = false;   // occupancy maps without traversal: walkRegionsSlab (one 1024-thread CTA per SM, slab staged by TMA)
+  size_t slab_walk_bytes = 0;
   uint32_t heavy_run = 16;
   uint32_t seg_factor = 96;     // segments per ray the batch's segment list is sized for (doubled after an overflow)
   uint32_t record_factor = 24;  // ordered-miss records per ray, likewise
@@ -1477,6 +1479,10 @@ int launchWalkAndReplay(ohmb200_map *m, const Batch &b, cudaStream_t s, size_t n
       const auto kernel = m->dm.traversal ? walkRegionsNdt<true> : walkRegionsNdt<false>;
       kernel<<<m->sm_count * m->walk_ctas_per_sm, kWalkThreads, m->tile_bytes, s>>>(m->dm, m->geom, m->mp, b, m->tile);
     }
+    else if (m->slab_walk && !m->dm.traversal)
+    {
+      walkRegionsSlab<<<m->sm_count, kSlabThreads, m->slab_walk_bytes, s>>>(m->dm, m->geom, m->mp, b, m->tile, has_samples ? 1 : 0);
+    }
     else
     {
       const auto kernel = m->dm.traversal ? walkRegions<true> : walkRegions<false>;
@@ -1721,7 +1727,7 @@ int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_i
     }
     {
       KernelScope scope(m, kKPlan);
-      planRegions<<<1, 1024, 0, s>>>(m->dm, b, (uint32_t)(m->sm_count * m->walk_ctas_per_sm));
+      planRegions<<<1, 1024, 0, s>>>(m->dm, b, (uint32_t)(m->sm_count * ((m->slab_walk && !m->dm.traversal) ? 1 : m->walk_ctas_per_sm)));
     }
     {
       KernelScope scope(m, kKEmit);
@@ -2351,6 +2357,22 @@ ohmb200_map *ohmb200_create(const ohmb200_params *params, int mode, size_t devic
       cudaFuncSetAttribute(walkRegionsNdt<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
       cudaFuncSetAttribute(walkRegionsNdt<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
       cudaFuncSetAttribute(walkRegionsTsdf, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }
+    {
+      // the slab-staged walk: tile + the region's whole occupancy slab in one CTA's shared memory
+      const size_t need = m->tile_bytes + sizeof(float) * m->geom.vpr;
+      // OHMB200_WALK=slab selects it (A/B runs).  Measured on config 2: 278 us against the tile kernel's 183 us — with one CTA
+      // per SM no other CTA fills the per-item latencies (segment pops, queue build, barriers), which costs far more than
+      // the shared-memory fold saves; the two-CTA tile kernel stays the default.
+      const char *env = getenv("OHMB200_WALK");
+      const bool want = env && strcmp(env, "slab") == 0;
+      if (want && mode == OHMB200_MODE_OCCUPANCY && m->tile.fast && (m->geom.vpr % 4u) == 0 && need + 8u * 1024u <= 227u * 1024u &&
+          cudaFuncSetAttribute(walkRegionsSlab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need) == cudaSuccess)
+      {
+        m->slab_walk = true;
+        m->slab_walk_bytes = need;
+      }
+      cudaGetLastError();
     }
     m->walk_ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(kWalkCtasPerSm, (226u * 1024u) / (m->tile_bytes + 40u * 1024u)));  // + ~38 KB static: staged segments, queue, ladder
   }

@@ -733,7 +733,7 @@ int exchangeIntegrate(ohmb200_map *m)
   }
   {
     KernelScope scope(m, kKPlan);
-    planRegions<<<1, 1024, 0, s>>>(m->dm, b, (uint32_t)(m->sm_count * m->walk_ctas_per_sm));
+    planRegions<<<1, 1024, 0, s>>>(m->dm, b, (uint32_t)(m->sm_count * ((m->slab_walk && !m->dm.traversal) ? 1 : m->walk_ctas_per_sm)));
   }
   {
     KernelScope scope(m, kKExEmit);

@@ -1450,6 +1450,250 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm) walkRegions(cons
   }
 }
 
+// ---- the slab-staged walk (round 2): occupancy maps without a traversal layer ---------------------------------------
+// One 1024-thread CTA per SM instead of two of 512: the shared memory that frees holds the region's WHOLE occupancy slab
+// (128 KB for a 32^3 region) next to the counter tile.  The slab is brought in by ONE cp.async.bulk (TMA unit) issued at
+// the top of the work item — it lands while the segments are walked, 10 us later — the fold then reads and writes shared
+// memory only (no L2 round trip per group of voxels: the long_scoreboard stalls of the tile kernel's fold), and ONE bulk
+// store writes the slab back while the next item is zeroing its tile.  Work items that share their region with other
+// items (hot regions cut in several) cannot stage it — their folds merge through compare-and-swap on global memory — and
+// keep the tile kernel's shared fold.  Same walk, same counters, same ladder: results are bit-identical (the parity
+// suite passes with it).  MEASURED AND NOT ADOPTED: 278 us against the tile kernel's 183 us on config 2 (profiles/
+// walk_r2_ab.md) — see ohmb200_create.  Kept behind OHMB200_WALK=slab as the record of the experiment.
+constexpr int kSlabThreads = 1024;
+
+struct PlainQueue  // SegmentQueue without the staged segments (the shared memory goes to the slab)
+{
+  uint16_t order[kMaxSegmentsPerItem];
+  uint32_t length_bins[kLengthBins];
+  uint32_t next_chunk;
+};
+
+__device__ __forceinline__ void plainQueueBuild(PlainQueue &q, const Batch &b, const WorkItem &item)
+{
+  const uint32_t tid = threadIdx.x;
+  if (tid < kLengthBins)
+  {
+    q.length_bins[tid] = 0;
+  }
+  if (tid == 0)
+  {
+    q.next_chunk = 0;
+  }
+  __syncthreads();
+  const uint32_t n_segments = item.end - item.begin;
+  const uint32_t *segment_words = reinterpret_cast<const uint32_t *>(b.segments + item.begin);
+  for (uint32_t k = tid; k < n_segments; k += blockDim.x)
+  {
+    const uint32_t visits = segment_words[4 * k + 2] >> 16;
+    atomicAdd(&q.length_bins[kLengthBins - 1u - min(visits, kLengthBins - 1u)], 1u);
+  }
+  __syncthreads();
+  if (tid < 32)
+  {
+    uint32_t c[4], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+      c[k] = q.length_bins[tid * 4 + k];
+      sum += c[k];
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+      incl += (tid >= (uint32_t)d) ? up : 0u;
+    }
+    uint32_t base = incl - sum;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+      q.length_bins[tid * 4 + k] = base;
+      base += c[k];
+    }
+  }
+  __syncthreads();
+  for (uint32_t k = tid; k < n_segments; k += blockDim.x)
+  {
+    const uint32_t visits = segment_words[4 * k + 2] >> 16;
+    q.order[atomicAdd(&q.length_bins[kLengthBins - 1u - min(visits, kLengthBins - 1u)], 1u)] = (uint16_t)k;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ int plainQueuePop(PlainQueue &q, const Batch &b, const WorkItem &item, uint4 &raw)
+{
+  uint32_t k = 0;
+  if ((threadIdx.x & 31u) == 0)
+  {
+    k = atomicAdd(&q.next_chunk, 32u);
+  }
+  k = __shfl_sync(0xffffffffu, k, 0);
+  const uint32_t n_segments = item.end - item.begin;
+  if (k >= n_segments)
+  {
+    return 0;
+  }
+  k += threadIdx.x & 31u;
+  if (k >= n_segments)
+  {
+    return 2;
+  }
+  raw = reinterpret_cast<const uint4 *>(b.segments)[item.begin + q.order[k]];
+  return 1;
+}
+
+// One thread: shared -> global bulk store of `bytes` (a bulk async-group of its own), and the wait for the stores
+// issued so far to have READ their shared-memory source (the buffer may be overwritten) / to have completed.
+__device__ __forceinline__ void bulkStore(void *global_dst, const void *smem_src, uint32_t bytes)
+{
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(global_dst), "r"(smemAddress(smem_src)), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulkStoreWaitRead()
+{
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulkStoreWaitAll()
+{
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kSlabThreads, 1) walkRegionsSlab(const __grid_constant__ DeviceMap dm, const __grid_constant__ Geom g,
+                                                             const __grid_constant__ MapParams mp, const __grid_constant__ Batch b,
+                                                             const __grid_constant__ TileLayout tl, int has_samples)
+{
+  extern __shared__ __align__(128) uint32_t tile[];  // the counter tile, then the region's occupancy slab
+  float *slab = reinterpret_cast<float *>(tile + tl.words);
+  __shared__ WorkItem items2[2];
+  __shared__ unsigned long long record_chunk[kSlabThreads / 32];
+  __shared__ PlainQueue queue;
+  __shared__ MissLadder ladder;
+  __shared__ uint32_t fold_ticket;
+  __shared__ unsigned long long slab_mbar;
+  uint32_t parity = 1;
+  uint32_t slab_phase = 0;  // phase of slab_mbar the next staged slab completes
+  const uint32_t words = tl.words;
+  const uint32_t tile_base = (uint32_t)__cvta_generic_to_shared(tile);
+  const uint32_t tid = threadIdx.x;
+  const uint32_t warp = tid >> 5;
+  const uint32_t slab_bytes = g.vpr * (uint32_t)sizeof(float);
+  if ((tid & 31u) == 0)
+  {
+    record_chunk[warp] = (unsigned long long)kRecordChunk;
+  }
+  if (tid == 32)
+  {
+    buildMissLadder(ladder, mp, b.ray_flags);
+  }
+  if (tid == 0)
+  {
+    mbarInit(&slab_mbar, 1u);
+    loadWorkItem(b, atomicAdd(&b.counters->work_next, 1u), &items2[0]);
+  }
+  for (;;)
+  {
+    parity ^= 1u;
+    __syncthreads();  // the item is in place; the previous fold is done with the tile and the slab
+    const WorkItem &item = items2[parity];
+    if (item.slot == 0xFFFFFFFFu)
+    {
+      if (tid == 0)
+      {
+        bulkStoreWaitAll();  // the last slab has reached global memory
+      }
+      return;
+    }
+    const uint32_t slot = item.slot;
+    const uint32_t vbase = slot * g.vpr;
+    const bool sole = item.shared == 0;
+    if (tid == 0 && sole)
+    {
+      bulkStoreWaitRead();  // the previous item's write-back has read the slab buffer
+      bulkLoad(slab, dm.occupancy + (size_t)vbase, slab_bytes, &slab_mbar);  // lands while the segments are walked
+    }
+    {
+      uint4 *tile4 = reinterpret_cast<uint4 *>(tile);
+      for (uint32_t w = tid; w < (words >> 2); w += blockDim.x)
+      {
+        tile4[w] = make_uint4(0, 0, 0, 0);
+      }
+    }
+    __syncthreads();
+    if (has_samples)
+    {
+      const uint32_t sample_end = b.sample_end[slot];
+      for (uint32_t s = b.sample_begin[slot] + tid; s < sample_end; s += blockDim.x)
+      {
+        const uint32_t half = tileHalf(tl, b.keys_out[s] - vbase);
+        atomicOr(&tile[half >> 1], kTileFlag << ((half & 1u) * 16u));
+      }
+    }
+    plainQueueBuild(queue, b, item);
+    uint32_t next_work = 0;
+    if (tid == 0)
+    {
+      next_work = atomicAdd(&b.counters->work_next, 1u);
+    }
+    for (;;)
+    {
+      uint4 raw;
+      const int got = plainQueuePop(queue, b, item, raw);
+      if (got == 0)
+      {
+        break;
+      }
+      if (got == 1)
+      {
+        SegmentWalk sw;
+        loadSegmentWalk(b, raw, sw);
+        const uint32_t ray = sw.ray;
+        resumeSegmentTile(sw.init, sw.delta, sw.entry, sw.total, sw.flags, sw.st, sw.visits, tl, tile_base, [&](uint32_t offset, uint32_t one) {
+          if (tileAdd(offset, one) & (one << 15))
+          {
+            const uint32_t at = reserveRecord(&record_chunk[warp], &b.counters->record_count);
+            if (at < b.record_capacity)
+            {
+              b.record_vid[at] = vbase + tileVoxel(tl, (offset - tile_base) >> 1);
+              b.record_ray[at] = ray;
+            }
+            else
+            {
+              b.counters->record_overflow = 1;
+              atomicOr(&b.counters->overflow_seen, 1);
+            }
+          }
+        });
+      }
+      __syncwarp();
+    }
+    if (tid == 0)
+    {
+      loadWorkItem(b, next_work, &items2[parity ^ 1u]);
+      fold_ticket = 0;
+    }
+    __syncthreads();
+    if (sole)
+    {
+      mbarWait(&slab_mbar, slab_phase);  // (long since: the copy was issued a whole walk ago)
+      slab_phase ^= 1u;
+      foldLogOddsTile(tile, nullptr, tl, slab, nullptr, mp, b.ray_flags, ladder, &fold_ticket, 0u);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the fold's writes, before the bulk store reads them
+      __syncthreads();
+      if (tid == 0)
+      {
+        bulkStore(dm.occupancy + (size_t)vbase, slab, slab_bytes);
+      }
+    }
+    else
+    {
+      foldLogOddsTile(tile, nullptr, tl, dm.occupancy + (size_t)vbase, nullptr, mp, b.ray_flags, ladder, &fold_ticket, 1u);
+    }
+  }
+}
+
 // Attach every ordered-miss record to the interval between two hits of its voxel: the run of the voxel in the sorted
 // sample pairs (binary search by voxel), then the first hit of the run with a larger ray index (binary search by ray).
 // Only the NUMBER of misses per interval is kept here: interval_count[head + j] for the misses before hit j of the
