@@ -612,24 +612,31 @@ def run_sharded(args, torch, dist, rank, local_rank, world, gloo):
             gpu.exchange_integrate()
 
     def timed(count, profile=False):
-        total = 0.0
+        """`count` steps queued back to back — no host wait between them: each step is fresh map (ohmb200_clear, queued) + L2
+        flush + a DEVICE-side barrier between the ranks (ohmb200_exchange_barrier), then the timed span [send + integrate]
+        between two CUDA events on the launch stream.  The ranks enter every span together (the device barrier) and no
+        rank's span waits for a host: what is timed is device time.  Per step the max over ranks; summed over steps."""
+        barrier()
+        spans = []
+        if profile:
+            gpu.set_profiling(True)
         for _ in range(count):
-            reset_map()
-            barrier()
+            with torch.cuda.stream(stream):
+                gpu.clear()
+                flush.fill_(1)
+                gpu.exchange_barrier()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            if profile:
-                gpu.set_profiling(True)
             a.record(stream)
             device_step()
             b.record(stream)
-            b.synchronize()
-            if profile:
-                gpu.set_profiling(False)
-            barrier()
-            ms = torch.tensor([a.elapsed_time(b)], device="cuda")
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-            total += float(ms.item())
-        return total
+            spans.append((a, b))
+        torch.cuda.synchronize()
+        if profile:
+            gpu.set_profiling(False)
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b) for a, b in spans], device="cuda")
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.sum().item())
 
     timed(args.warmup)
     sampler = ClockSampler(local_rank)
@@ -705,23 +712,27 @@ def run_sharded(args, torch, dist, rank, local_rank, world, gloo):
     ndt.set_stream(stream.cuda_stream)
     own = [sweeps[own_sweep_index(k, rank, world)][0] for k in range(ndt_warm + ndt_steps)]
     d_own = [torch.from_numpy(s).cuda() for s in own]
-    ndt_ms, ndt_rays = 0.0, 0
+    ndt_rays = 0
+    ndt_spans = []
+    barrier()
     for k in range(ndt_warm + ndt_steps):
-        flush.fill_(1)
-        barrier()
+        with torch.cuda.stream(stream):
+            flush.fill_(1)
+            ndt.exchange_barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
         with torch.cuda.stream(stream):
             ndt.exchange_send_device(d_own[k].data_ptr(), d_own[k].shape[0])
             ndt.exchange_integrate()
         b.record(stream)
-        b.synchronize()
-        barrier()
-        ms = torch.tensor([a.elapsed_time(b)], device="cuda")
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ndt_spans.append((a, b))
         if k >= ndt_warm:
-            ndt_ms += float(ms.item())
             ndt_rays += sum(sweeps[k * world + r][0].shape[0] // 2 for r in range(world))
+    torch.cuda.synchronize()
+    barrier()
+    ms = torch.tensor([a.elapsed_time(b) for a, b in ndt_spans[ndt_warm:]], device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ndt_ms = float(ms.sum().item())
     ndt.sync_voxels()
     nst = ndt.stats()
     ndt_counts = [None] * world
@@ -828,7 +839,9 @@ def run_sharded(args, torch, dist, rank, local_rank, world, gloo):
             "segments_per_step": segments_total,
             "visits_share_of_heaviest_owner": heaviest / (visits / world) if visits else None,
             "l2": "map cleared + 512 MiB L2 flush between timed steps (outside the timed spans)",
-            "timing": "CUDA events on the launch stream per step around send + integrate, max over ranks, summed over steps",
+            "timing": "CUDA events on the launch stream per step around send + integrate, max over ranks, summed over steps; the "
+                      "steps are queued back to back with a device-side barrier between the ranks before every span "
+                      "(ohmb200_exchange_barrier): no host wait inside or between the spans",
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_mine.numel() * 8),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,

@@ -304,6 +304,9 @@ OHMB200_API size_t ohmb200_exchange_send_device(ohmb200_map *map, const double *
                                                 unsigned ray_flags);
 OHMB200_API int ohmb200_exchange_integrate(ohmb200_map *map);
 OHMB200_API int ohmb200_exchange_close(ohmb200_map *map);
+/* A barrier between the ranks on the device: each rank's stream passes it when every rank's stream has reached it
+ * (mailbox flags + a bounded spin; no host wait).  Every rank must call it the same number of times, between steps. */
+OHMB200_API int ohmb200_exchange_barrier(ohmb200_map *map);
 /* What this rank put into each owner's inbox in the last step (waits for the queued work): segment records (32 bytes
  * each) and sample records (96 bytes, 16 on an occupancy-only map), `world` entries each; either pointer may be NULL.
  * With the per-ray broadcast (64 bytes x own rays x (world - 1) peers; + 60 for NDT maps, + 8 with the traversal

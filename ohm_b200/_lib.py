@@ -103,6 +103,7 @@ SYMBOLS = [
     ("ohmb200_exchange_send_device", C.c_size_t, [_vp, _vp, C.c_size_t, _vp, _vp, C.c_uint]),
     ("ohmb200_exchange_integrate", C.c_int, [_vp]),
     ("ohmb200_exchange_close", C.c_int, [_vp]),
+    ("ohmb200_exchange_barrier", C.c_int, [_vp]),
     ("ohmb200_exchange_last_counts", C.c_int, [_vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int]),
     ("ohmb200_last_error", C.c_char_p, []),
     ("ohmb200_version", C.c_char_p, []),

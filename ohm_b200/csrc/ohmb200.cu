@@ -1128,6 +1128,7 @@ struct ohmb200_map
     double *smp_last_exit = nullptr;
     int *abort = nullptr;
     uint32_t *d_step = nullptr;        // == step, counted on the device
+    uint32_t *d_barrier = nullptr;     // ohmb200_exchange_barrier calls so far, counted on the device
     cudaStream_t stream = nullptr;     // the per-ray broadcast (copy engines) runs here, beside the cut
     cudaEvent_t prepped = nullptr, bcast_done = nullptr;
     // CUDA graphs of whole steps (send + integrate), one per (buffers, size, flags, parity): see launchBatch's graphs
@@ -1358,7 +1359,11 @@ int ensureScratch(ohmb200_map *m, size_t n)
   rc |= deviceAlloc(b.run_head, cap);
   rc |= deviceAlloc(b.interval_count, 2 * cap + 1);
   b.tail_overflow = b.interval_count + cap;  // re-pointed at interval_count + n by every batch
-  b.record_capacity = (uint32_t)std::min<size_t>(std::max<size_t>(cap * m->record_factor, 1u << 20), 1u << 28);
+  // Ordered-record lists are sized by the rays whose visits this map applies: on an exchange map that is about one
+  // rank's share (twice it, for imbalance), not the whole step's rays — the lists are cleared every batch, and at 8 GPUs a
+  // list sized by all rays was a 113 MB memset per step.
+  const size_t record_rays = m->ex.open ? std::min<size_t>(cap, 2 * (size_t)m->ex.per + 16384) : cap;
+  b.record_capacity = (uint32_t)std::min<size_t>(std::max<size_t>(record_rays * m->record_factor, 1u << 20), 1u << 28);
   rc |= deviceAlloc(b.record_ray, b.record_capacity);
   rc |= deviceAlloc(b.record_next, b.record_capacity);
   if (m->dm.traversal)
@@ -1419,7 +1424,7 @@ int ensureScratch(ohmb200_map *m, size_t n)
       cudaFree(b.gauss_keys);
       rc |= deviceAlloc(b.interval_offset, 2 * cap + 1);
       rc |= deviceAlloc(b.sorted_rays, b.record_capacity);
-      b.gauss_capacity = (uint32_t)std::min<size_t>(std::max<size_t>(cap * 16, 1u << 20), 1u << 28);
+      b.gauss_capacity = (uint32_t)std::min<size_t>(std::max<size_t>(record_rays * (m->record_factor * 2u / 3u), 1u << 20), 1u << 28);
       rc |= deviceAlloc(b.gauss_keys, b.gauss_capacity);
     }
     if (m->mode == OHMB200_MODE_TSDF)
@@ -3373,7 +3378,7 @@ int ohmb200_clear(ohmb200_map *m)
   clearLiveRegions<<<std::min<unsigned>(m->dm.capacity, (unsigned)m->sm_count * 16u), 256, 0, m->stream>>>(m->dm, table);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemsetAsync(m->d_counters, 0, sizeof(Counters), m->stream));
-  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  // (queued, like everything else: what follows on the map's stream sees the empty map; no host wait)
   return OHMB200_OK;
 }
 
@@ -3601,6 +3606,11 @@ int ohmb200_exchange_integrate(ohmb200_map *m)
 int ohmb200_exchange_close(ohmb200_map *m)
 {
   return exchangeClose(m);
+}
+
+int ohmb200_exchange_barrier(ohmb200_map *m)
+{
+  return exchangeBarrier(m);
 }
 
 int ohmb200_exchange_last_counts(ohmb200_map *m, uint32_t *segments, uint32_t *samples, int capacity)

@@ -109,6 +109,7 @@ int exchangeClose(ohmb200_map *m)
   cudaFree(x.smp_last_exit);
   cudaFree(x.abort);
   cudaFree(x.d_step);
+  cudaFree(x.d_barrier);
   for (auto &g : x.graphs)
   {
     cudaGraphExecDestroy(g.exec);
@@ -193,6 +194,8 @@ int exchangeOpen(ohmb200_map *m, int rank, int world, size_t max_rays_per_rank, 
   ok = ok && cudaMemsetAsync(x.abort, 0, sizeof(int), m->stream) == cudaSuccess;
   ok = ok && cudaMalloc(&x.d_step, sizeof(uint32_t)) == cudaSuccess;
   ok = ok && cudaMemsetAsync(x.d_step, 0, sizeof(uint32_t), m->stream) == cudaSuccess;
+  ok = ok && cudaMalloc(&x.d_barrier, sizeof(uint32_t)) == cudaSuccess;
+  ok = ok && cudaMemsetAsync(x.d_barrier, 0, sizeof(uint32_t), m->stream) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&x.bcast_done, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&x.stream, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&x.prepped, cudaEventDisableTiming) == cudaSuccess;
@@ -516,9 +519,10 @@ int exchangeSend(ohmb200_map *m, const double *d_rays, size_t element_count, con
     EX_CAPCHK(m, "prep+carry+route");
   }
   exSignal<<<1, 32, 0, s>>>(ex, 2);  // the samples are out
+  // The per-ray broadcast: copy engines over NVLink, on their own stream, beside the cut.
+  const bool broadcast_first = true;  // (sending an occupancy map's 64-byte records AFTER the cut was measured at 8 GPUs: 0.72 vs 0.68 ms per step)
+  auto broadcast = [&]() -> int {
   CUDA_TRY(cudaEventRecord(x.prepped, s));
-
-  // The per-ray broadcast: copy engines over NVLink, beside exPrepSegments.
   CUDA_TRY(cudaStreamWaitEvent(x.stream, x.prepped, 0));
   const ExView &mine = ex.peer[x.rank];
   const size_t first = (size_t)x.rank * x.per;
@@ -550,6 +554,16 @@ int exchangeSend(ohmb200_map *m, const double *d_rays, size_t element_count, con
   exSignal<<<1, 32, 0, x.stream>>>(ex, 1);
   CUDA_TRY(cudaEventRecord(x.bcast_done, x.stream));
   EX_CAPCHK(m, "broadcast");
+  return OHMB200_OK;
+  };
+  if (broadcast_first)
+  {
+    rc = broadcast();
+    if (rc)
+    {
+      return rc;
+    }
+  }
 
   // The sample branch of the OWNER side starts here, beside everybody's cut — unless a peer map lives in this process:
   // its send is queued by this same host thread AFTER this call, and a wait kernel queued now could sit in front of it
@@ -573,6 +587,14 @@ int exchangeSend(ohmb200_map *m, const double *d_rays, size_t element_count, con
   exSignal<<<1, 32, 0, s>>>(ex, 0);
   m->launches += 3;
   EX_CAPCHK(m, "segments+signal");
+  if (!broadcast_first)
+  {
+    rc = broadcast();
+    if (rc)
+    {
+      return rc;
+    }
+  }
   CUDA_TRY(cudaGetLastError());
   x.pending = true;
   return OHMB200_OK;
@@ -781,5 +803,72 @@ int exchangeIntegrate(ohmb200_map *m)
   }
   CUDA_TRY(cudaGetLastError());
   finish();
+  return OHMB200_OK;
+}
+
+// A barrier between the ranks ON THE DEVICE: every rank's stream passes it only when every rank's stream has reached
+// it (mailbox flag + bounded spin, like a step's handshake).  For callers that want the ranks to enter a step together
+// without a host round trip — bench.py puts it in front of every timed step.
+__global__ void exBarrierSignal(ExStep ex, uint32_t *counter)
+{
+  const int o = (int)threadIdx.x;
+  if (o == 0)
+  {
+    *counter += 1u;
+  }
+  __syncthreads();
+  if (o < ex.world)
+  {
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t *>(&ex.peer[o].mailbox[ex.rank].pad) = *counter;
+  }
+}
+
+__global__ void exBarrierWait(ExMailbox *mailbox, int world, const uint32_t *counter, int *abort)
+{
+  const int s = (int)threadIdx.x;
+  const uint32_t want = *counter;
+  bool ok = true;
+  if (s < world)
+  {
+    const volatile uint32_t *flag = &mailbox[s].pad;
+    const long long t0 = clock64();
+    while ((int32_t)(*flag - want) < 0)
+    {
+      if (clock64() - t0 > 8000000000ll)
+      {
+        ok = false;
+        break;
+      }
+      __nanosleep(100);
+    }
+  }
+  __threadfence_system();
+  if (!ok)
+  {
+    *abort = 1;
+  }
+}
+
+int exchangeBarrier(ohmb200_map *m)
+{
+  if (!m || !m->ex.open || !m->ex.connected || m->ex.pending)
+  {
+    return setError(OHMB200_E_INVALID, "ohmb200_exchange_barrier: needs an open, connected exchange with no step pending");
+  }
+  cudaSetDevice(m->device);
+  ohmb200_map::Exchange &x = m->ex;
+  // the barrier's flags live in parity 0 of the mailboxes (its own word: ExMailbox::pad), whatever the step parity
+  ExStep ex;
+  exFillStep(m, ex);
+  const ExLayout l = exLayout(x.world, x.per, x.seg_cap);
+  for (int r = 0; r < x.world; ++r)
+  {
+    ex.peer[r] = exView(x.peer_base[r], l, x.parity_bytes, 0);
+  }
+  exBarrierSignal<<<1, 32, 0, m->stream>>>(ex, x.d_barrier);
+  exBarrierWait<<<1, 32, 0, m->stream>>>(ex.peer[x.rank].mailbox, x.world, x.d_barrier, x.abort);
+  m->launches += 2;
+  CUDA_TRY(cudaGetLastError());
   return OHMB200_OK;
 }

@@ -361,6 +361,10 @@ class GpuMap:
         """Phase 2: wait (on the device) for every rank's records of the step, integrate what was routed here."""
         self._check(self.L.ohmb200_exchange_integrate(self.h))
 
+    def exchange_barrier(self):
+        """Device-side barrier between the ranks (queued; no host wait)."""
+        self._check(self.L.ohmb200_exchange_barrier(self.h))
+
     def exchange_last_counts(self, world):
         """(segment records, sample records) this rank sent to each owner in the last step."""
         seg = (C.c_uint32 * world)()
