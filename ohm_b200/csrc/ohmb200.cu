@@ -1129,6 +1129,7 @@ struct ohmb200_map
     int *abort = nullptr;
     uint32_t *d_step = nullptr;        // == step, counted on the device
     uint32_t *d_barrier = nullptr;     // ohmb200_exchange_barrier calls so far, counted on the device
+    ExMailbox *mailbox_now = nullptr;  // this rank's mailbox of the step being integrated
     cudaStream_t stream = nullptr;     // the per-ray broadcast (copy engines) runs here, beside the cut
     cudaEvent_t prepped = nullptr, bcast_done = nullptr;
     // CUDA graphs of whole steps (send + integrate), one per (buffers, size, flags, parity): see launchBatch's graphs
@@ -1497,6 +1498,12 @@ int launchWalkAndReplay(ohmb200_map *m, const Batch &b, cudaStream_t s, size_t n
   }
   if (m->mode == OHMB200_MODE_NDT || m->mode == OHMB200_MODE_NDT_TM)
   {
+    if (m->ex.open)
+    {
+      // the rays of the other ranks (read by the Gaussian-miss and replay kernels) follow their walk constants: stage 3
+      KernelScope scope(m, kKExWait);
+      exWait<<<1, 32, 0, s>>>(m->ex.mailbox_now, m->ex.world, m->ex.d_step, 3, m->ex.abort);
+    }
     {
       KernelScope scope(m, kKNdtGauss);
       ndtGaussianMisses<<<m->sm_count * 8, 128, 0, s>>>(m->dm, m->geom, m->mp, b);

@@ -64,8 +64,11 @@ struct ExMailbox
   uint32_t seg_flag;  // == step when the sender's segment records of that step are in place
   uint32_t ray_flag;  // == step when its per-ray broadcast is
   uint32_t smp_flag;  // == step when its sample records are (they leave first: the owner sorts them beside the cut)
-  uint32_t pad;
+  uint32_t pts_flag;  // == step when the rays / timestamps / intensities an NDT map's replays read have followed
+  uint32_t barrier;   // ohmb200_exchange_barrier: the sender's barrier count (parity 0 only)
+  uint32_t pad[3];
 };
+static_assert(sizeof(ExMailbox) == 48, "ExMailbox layout");
 
 // One rank's arena, one parity.
 struct ExView
@@ -356,7 +359,7 @@ __global__ void exBumpStep(uint32_t *step)
 }
 
 // Tell every owner what this rank has put into its inbox.  stage 2: sample records (sent first); stage 0: segment
-// records; stage 1: the per-ray broadcast.  The data was written by earlier work of the same stream(s); the system-scope fence orders it before
+// records; stage 1: the walk constants of the per-ray broadcast; stage 3: its rays / timestamps / intensities (NDT).  The data was written by earlier work of the same stream(s); the system-scope fence orders it before
 // the flag for a reader on another GPU.
 __global__ void exSignal(ExStep ex, int stage)
 {
@@ -381,6 +384,11 @@ __global__ void exSignal(ExStep ex, int stage)
     __threadfence_system();
     *reinterpret_cast<volatile uint32_t *>(&box->smp_flag) = *ex.step;
   }
+  else if (stage == 3)
+  {
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t *>(&box->pts_flag) = *ex.step;
+  }
   else
   {
     __threadfence_system();
@@ -398,7 +406,7 @@ __global__ void exWait(ExMailbox *mailbox, int world, const uint32_t *step_count
   bool ok = true;
   if (s < world)
   {
-    const volatile uint32_t *flag = stage == 0 ? &mailbox[s].seg_flag : (stage == 1 ? &mailbox[s].ray_flag : &mailbox[s].smp_flag);
+    const volatile uint32_t *flag = stage == 0 ? &mailbox[s].seg_flag : (stage == 1 ? &mailbox[s].ray_flag : (stage == 2 ? &mailbox[s].smp_flag : &mailbox[s].pts_flag));
     const long long t0 = clock64();
     while (*flag != step)
     {
