@@ -142,8 +142,8 @@ struct Batch
   uint4 *stage;            // [kStageSegments][stage_stride] segments found by pass A, plane k = k-th segment of each ray
   uint32_t *stage_count;   // [n] segments pass A found for the ray (> kStageSegments: pass B enumerates again)
   uint32_t stage_stride;
-  uint32_t *cross_pos;     // [kStageSegments][stage_stride] per-crossing producer: walk position after the crossing of rank k
-  uint32_t stage_by_ray;   // the staged planes are indexed by ray (per-crossing producer), not by thread (prepSegments)
+  uint32_t *cross_pos;     // (unused: reserved for a per-crossing producer, see crossingOf in ohmb200_regions.cuh)
+  uint32_t stage_by_ray;   // the staged planes are indexed by ray, not by thread (always 0: prepSegments stages by thread)
   WorkItem *items;         // (region, segment range) work list
   uint32_t item_capacity;
   unsigned long long *gauss_keys;          // NDT: (voxel id << 32 | ray) of visits to voxels with an established Gaussian
@@ -1015,7 +1015,6 @@ struct ohmb200_map
   uint32_t heavy_run = 16;
   uint32_t seg_factor = 96;     // segments per ray the batch's segment list is sized for (doubled after an overflow)
   uint32_t record_factor = 24;  // ordered-miss records per ray, likewise
-  int producer = 1;  // 1 = prepSegments (one thread per ray); 2 = one thread per crossing (OHMB200_PRODUCER=2, experimental)
   uint32_t *tsdf_near = nullptr;  // TSDF: per-batch bit per voxel, "visited near a sample in this batch"
   size_t voxel_bit_bytes = 0;     // size of dm.voxel_bits (and of tsdf_near)
   ohmb200_params params{};
@@ -1413,10 +1412,6 @@ int ensureScratch(ohmb200_map *m, size_t n)
     {
       rc |= deviceAlloc(b.stage, (size_t)kStageSegments * cap);
       rc |= deviceAlloc(b.stage_count, cap);
-      if (m->producer == 2)
-      {
-        rc |= deviceAlloc(b.cross_pos, (size_t)kStageSegments * cap);
-      }
     }
     b.item_capacity = m->dm.capacity + b.seg_capacity / 512 + 16;
     rc |= deviceAlloc(b.items, b.item_capacity);
@@ -1713,16 +1708,6 @@ int launchBatch(ohmb200_map *m, const double *d_rays, size_t n, const float *d_i
         markRuns<<<blocks, threads, 0, sample_stream>>>(m->dm, b, m->geom.vpr);
       }
     }
-    if (m->producer == 2 && m->mode != OHMB200_MODE_TSDF && b.cross_pos)
-    {
-      // experimental (OHMB200_PRODUCER=2): one thread per region crossing; markTsdfNear still reads prepSegments' layout
-      KernelScope scope(m, kKPrepSegments);
-      const unsigned producer_blocks = (unsigned)((n + kProducerRays - 1) / kProducerRays);
-      b.stage_by_ray = 1;
-      crossPositions<<<producer_blocks, kProducerRays, 0, s>>>(m->geom, b);
-      finishSlots<<<producer_blocks, kProducerRays, 0, s>>>(m->dm, m->geom, b);
-    }
-    else
     {
       KernelScope scope(m, kKPrepSegments);
       b.stage_by_ray = 0;
@@ -2320,10 +2305,6 @@ ohmb200_map *ohmb200_create(const ohmb200_params *params, int mode, size_t devic
   if (const char *env = getenv("OHMB200_GRAPHS"))
   {
     m->use_graphs = atoi(env) != 0;
-  }
-  if (const char *env = getenv("OHMB200_PRODUCER"))
-  {
-    m->producer = atoi(env) == 2 ? 2 : 1;
   }
   if (const char *env = getenv("OHMB200_HEAVY_RUN"))
   {

@@ -238,234 +238,6 @@ __global__ void __launch_bounds__(128) prepSegments(DeviceMap dm, Geom g, Batch 
   }
 }
 
-// ---- the per-crossing producer (OHMB200_PRODUCER=2) -------------------------------------------------------------
-// EXPERIMENTAL: off by default, written from crossingOf (whose equivalence with enumerateSegments is proven on the host,
-// tests/cpp/segments_host_test.cu) but not yet run or measured on a GPU; prepSegments remains the product path.
-// A CTA takes kProducerRays consecutive rays and spreads their slots — slot 0 of a ray is its start, slot k > 0 one of
-// its region crossings — evenly over its threads (a scan of the slot counts in shared memory, a search per slot), so
-// that a 60-segment ray and a 4-segment ray cost what they weigh.  crossPositions writes the walk position after each
-// crossing at the crossing's RANK; finishSlots computes each slot's segment from its own crossing and the position of
-// the next rank, finds or inserts the region, adds to the region's histogram and stages the record at plane `rank`
-// (empty or foreign segments: region slot ~0, skipped by emitSegments).
-constexpr int kProducerRays = 128;
-
-struct ProducerRays
-{
-  uint32_t first[kProducerRays + 1];  // exclusive scan of the slots per ray
-  uint16_t cross0[kProducerRays];     // crossings of axis 0, of axes 0 and 1: slot k > 0 -> (axis, j)
-  uint16_t cross01[kProducerRays];
-};
-
-// Every thread of the CTA: the slots of ray blockIdx.x * kProducerRays + threadIdx.x; returns the CTA's total.
-__device__ __forceinline__ uint32_t producerSetup(ProducerRays &pr, const Batch &b, const Geom &g)
-{
-  typedef cub::BlockScan<uint32_t, kProducerRays> Scan;
-  __shared__ typename Scan::TempStorage scan_storage;
-  const uint32_t i = blockIdx.x * kProducerRays + threadIdx.x;
-  uint32_t slots = 0, c0 = 0, c1 = 0;
-  if (i < b.n)
-  {
-    RayRec rec;
-    loadRec(rec, b.recs + i);
-    if (rec.flags & kRecValid)
-    {
-      c0 = (uint32_t)crossingsWithin(rec, g, 0, rec.total[0]);
-      c1 = (uint32_t)crossingsWithin(rec, g, 1, rec.total[1]);
-      slots = 1u + c0 + c1 + (uint32_t)crossingsWithin(rec, g, 2, rec.total[2]);
-    }
-  }
-  uint32_t before = 0, total = 0;
-  Scan(scan_storage).ExclusiveSum(slots, before, total);
-  pr.first[threadIdx.x] = before;
-  pr.cross0[threadIdx.x] = (uint16_t)min(c0, 0xffffu);
-  pr.cross01[threadIdx.x] = (uint16_t)min(c0 + c1, 0xffffu);
-  if (threadIdx.x == 0)
-  {
-    pr.first[kProducerRays] = total;
-  }
-  __syncthreads();
-  return total;
-}
-
-// Slot s of the CTA -> (ray of the CTA, slot of the ray).
-__device__ __forceinline__ void producerSlot(const ProducerRays &pr, uint32_t s, uint32_t &ray, uint32_t &k)
-{
-  uint32_t lo = 0, hi = kProducerRays;  // the largest ray with first[ray] <= s
-  while (hi - lo > 1)
-  {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (pr.first[mid] <= s)
-    {
-      lo = mid;
-    }
-    else
-    {
-      hi = mid;
-    }
-  }
-  ray = lo;
-  k = s - pr.first[lo];
-}
-
-// Slot k > 0 of a ray -> its crossing.
-__device__ __forceinline__ bool producerCrossing(const ProducerRays &pr, uint32_t ray, uint32_t k, const RayRec &rec, const Geom &g,
-                                                 Crossing &c)
-{
-  const uint32_t e = k - 1u;
-  const int axis = e < pr.cross0[ray] ? 0 : (e < pr.cross01[ray] ? 1 : 2);
-  const int j = (int)(e - (axis == 0 ? 0u : (axis == 1 ? pr.cross0[ray] : pr.cross01[ray])));
-  return crossingOf(rec, g, axis, j, c);
-}
-
-__global__ void __launch_bounds__(kProducerRays) crossPositions(Geom g, Batch b)
-{
-  __shared__ ProducerRays pr;
-  const uint32_t total = producerSetup(pr, b, g);
-  for (uint32_t s = threadIdx.x; s < total; s += kProducerRays)
-  {
-    uint32_t ray, k;
-    producerSlot(pr, s, ray, k);
-    const uint32_t slots = pr.first[ray + 1] - pr.first[ray];
-    if (k == 0 || slots > kStageSegments)
-    {
-      continue;  // the start of the ray is position 0; rays with more slots than planes take the per-ray path
-    }
-    const uint32_t i = blockIdx.x * kProducerRays + ray;
-    RayRec rec;
-    loadRec(rec, b.recs + i);
-    Crossing c;
-    if (producerCrossing(pr, ray, k, rec, g, c) && (uint32_t)c.rank < kStageSegments)
-    {
-      b.cross_pos[(size_t)c.rank * b.stage_stride + i] = (uint32_t)c.position;
-    }
-  }
-}
-
-__global__ void __launch_bounds__(kProducerRays) finishSlots(DeviceMap dm, Geom g, Batch b)
-{
-  __shared__ ProducerRays pr;
-  const uint32_t total = producerSetup(pr, b, g);
-  {
-    const uint32_t i = blockIdx.x * kProducerRays + threadIdx.x;
-    if (i < b.n)
-    {
-      b.stage_count[i] = pr.first[threadIdx.x + 1] - pr.first[threadIdx.x];
-    }
-  }
-  unsigned visits = 0;
-  // a segment enters its region: histogram (one reduction per group of lanes that entered the same region), touched list
-  auto enter_region = [&](int slot) {
-    const unsigned peers = __match_any_sync(__activemask(), slot);
-    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1)
-    {
-      if (atomicAdd(&b.seg_count[slot], (uint32_t)__popc(peers)) == 0u)
-      {
-        b.touched_list[atomicAdd(&b.counters->touched_count, 1u)] = (uint32_t)slot;
-      }
-    }
-  };
-  for (uint32_t s = threadIdx.x; s < total; s += kProducerRays)
-  {
-    uint32_t ray, k;
-    producerSlot(pr, s, ray, k);
-    const uint32_t slots = pr.first[ray + 1] - pr.first[ray];
-    const uint32_t i = blockIdx.x * kProducerRays + ray;
-    RayRec rec;
-    loadRec(rec, b.recs + i);
-    if (slots > kStageSegments)
-    {
-      // more segments than staging planes (emitSegments enumerates such a ray again): the histogram, per ray
-      if (k == 0)
-      {
-        enumerateSegments(rec, g, [&](const int r[3], const int[3], const int[3], int n) {
-          if (ownsRegion(dm, r))
-          {
-            const int slot = regionSlot(dm, packRegion(r[0], r[1], r[2]));
-            if (slot >= 0)
-            {
-              enter_region(slot);
-              visits += (unsigned)n;
-            }
-          }
-        });
-      }
-      continue;
-    }
-    Crossing c;
-    c.rank = 0;
-    c.position = 0;
-    c.stepped[0] = c.stepped[1] = c.stepped[2] = 0;
-    if (k > 0 && !producerCrossing(pr, ray, k, rec, g, c))
-    {
-      continue;  // (cannot happen: the slots were counted from the same closed form)
-    }
-    const int walk_steps = (int)rec.total[0] + (int)rec.total[1] + (int)rec.total[2];
-    const bool exclude_start = (rec.flags & kRecExcludeStart) != 0, exclude_end = (rec.flags & kRecExcludeEnd) != 0;
-    int st[3] = { c.stepped[0], c.stepped[1], c.stepped[2] };
-    int n;
-    if (walk_steps == 0)
-    {
-      n = exclude_end ? 0 : 1;  // start and end share a voxel: only the end-voxel visit can happen
-    }
-    else
-    {
-      const int end = ((uint32_t)c.rank + 1u < slots) ? (int)b.cross_pos[(size_t)(c.rank + 1) * b.stage_stride + i] - 1 : walk_steps;
-      const int lo = max(c.position, exclude_start ? 1 : 0);
-      const int hi = min(end, exclude_end ? walk_steps - 1 : walk_steps);
-      n = hi - lo + 1;
-      if (n > 0 && lo != c.position)
-      {
-        // the excluded start voxel: the segment begins one step into the ray (the first step: the earliest exit time)
-        double t0[3];
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-        {
-          t0[a] = rec.total[a] ? rec.initial[a] : (double)INFINITY;
-          st[a] = 0;
-        }
-        const int a0 = selectNextAxis(t0);
-        st[0] = a0 == 0;
-        st[1] = a0 == 1;
-        st[2] = a0 == 2;
-      }
-    }
-    uint4 staged = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
-    if (n > 0)
-    {
-      int r[3], entry[3];
-#pragma unroll
-      for (int a = 0; a < 3; ++a)
-      {
-        const int dir = (rec.flags & (1u << a)) ? -1 : 1;
-        const int pos = ((int)rec.local[a] + dir * st[a]) % g.dim[a];
-        entry[a] = pos < 0 ? pos + g.dim[a] : pos;
-        r[a] = (int)(int16_t)((int)rec.region[a] + dir * crossingsWithin(rec, g, a, st[a]));
-      }
-      if (ownsRegion(dm, r))
-      {
-        const int slot = regionSlot(dm, packRegion(r[0], r[1], r[2]));
-        if (slot >= 0)
-        {
-          enter_region(slot);
-          visits += (unsigned)n;
-          staged = make_uint4((uint32_t)slot, (uint32_t)st[0] | ((uint32_t)st[1] << 16), (uint32_t)st[2] | ((uint32_t)n << 16),
-                              (uint32_t)entry[0] | ((uint32_t)entry[1] << 8) | ((uint32_t)entry[2] << 16));
-        }
-      }
-    }
-    if ((uint32_t)c.rank < kStageSegments)
-    {
-      b.stage[(size_t)c.rank * b.stage_stride + i] = staged;
-    }
-  }
-  __syncwarp();
-  const unsigned n_vis = __reduce_add_sync(0xffffffffu, visits);
-  if ((threadIdx.x & 31) == 0 && n_vis)
-  {
-    atomicAdd(&b.counters->voxel_visits, (unsigned long long)n_vis);
-  }
-}
-
 // Single CTA over the touched regions only: segment offsets and the work-item list (largest regions first).
 // The touched list (slot, count, offset) of the first kPlanCache regions is kept in shared memory, so the five
 // size-class passes read no global memory and draw their item indices from a shared-memory counter (a sweep touches
@@ -590,7 +362,7 @@ __global__ void __launch_bounds__(128) emitSegments(DeviceMap dm, Geom g, Batch 
       const uint32_t slot = raw.x;
       if (slot == 0xFFFFFFFFu)
       {
-        continue;  // an empty or foreign segment of the per-crossing producer (prepSegments stages none)
+        continue;  // (an empty plane entry; prepSegments stages none)
       }
       const uint32_t at = b.seg_offset[slot] + slotAggregatedInc(b.seg_cursor, slot);
       if (at < b.seg_capacity)

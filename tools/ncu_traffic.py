@@ -18,8 +18,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
-RUNS = [("walkRegions", ["--config", "2"], "^walkRegions<"), ("walkRegionsNdt", ["--config", "3"], "^walkRegionsNdt"),
-        ("walkRegionsTsdf", ["--config", "4"], "^walkRegionsTsdf")]
+RUNS = [("walkRegions", ["--config", "2"], "^walkRegions$"), ("walkRegionsNdt", ["--config", "3"], "^walkRegionsNdt$"),
+        ("walkRegionsTsdf", ["--config", "4"], "^walkRegionsTsdf$")]
 METRICS = "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum"
 
 
