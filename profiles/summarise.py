@@ -48,8 +48,8 @@ def launches(tag):
     tot = sum(a[1] for a in agg.values())
     out = io.StringIO()
     out.write(f"# ncu launch list, capture {tag}\n\n")
-    out.write("Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py --steps 2 "
-              "--warmup 1 --cpu-reps 0` (1 x B200; cold-cache, serialised: compare SHARES, not absolutes). Microseconds.\n"
+    out.write("Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 260 --csv python bench.py --steps 2 "
+              "--warmup 3 --cpu-reps 0` (1 x B200; cold-cache, serialised: compare SHARES, not absolutes). Microseconds.\n"
               "`fillFloat` is the map clear between steps and the torch fill is the L2 flush; both are outside the "
               "timed spans of bench.py.\n\n| kernel | launches | total us | mean us | share |\n|---|---:|---:|---:|---:|\n")
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -64,8 +64,8 @@ def kernel(tag, name, title, reading=""):
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, r = rows[0], rows[1], rows[2]
     lines = [f"# ncu --set full: {name}, capture {tag} ({title})\n\n",
-             f"Command: `ncu --set full --clock-control none --import-source on -k regex:{name} -s 1 -c 2 python bench.py "
-             f"--steps 2 --warmup 1 --cpu-reps 0` (1 x B200).\n\n| metric | value | unit |\n|---|---:|---|\n"]
+             f"Command: `ncu --set full --clock-control none --import-source on -k regex:{name} -s 5 -c 1 python bench.py "
+             f"--steps 2 --warmup 3 --cpu-reps 0` (1 x B200).\n\n| metric | value | unit |\n|---|---:|---|\n"]
     for k in KEYS:
         if k in hdr:
             i = hdr.index(k)
@@ -78,11 +78,7 @@ def kernel(tag, name, title, reading=""):
     if reading:
         lines.append("\n" + reading + "\n")
     open(os.path.join(ROOT, 'profiles', f'kernel_{tag}.md'), 'w').write(''.join(lines))
-    mult = {'Mbyte': 1e6, 'Gbyte': 1e9, 'Kbyte': 1e3, 'byte': 1}
-    rd = float(r[hdr.index('dram__bytes_read.sum')]) * mult[units[hdr.index('dram__bytes_read.sum')]]
-    wr = float(r[hdr.index('dram__bytes_write.sum')]) * mult[units[hdr.index('dram__bytes_write.sum')]]
-    json.dump({"kernel": name, "capture": f"profiles/kernel_{tag}.md", "dram_bytes_per_launch": int(rd + wr)},
-              open(os.path.join(ROOT, 'profiles', 'traffic.json'), 'w'))
+    # (profiles/traffic.json is written by tools/ncu_traffic.py, keyed by the hash of the CUDA sources)
     return ''.join(lines)
 
 
