@@ -1232,6 +1232,16 @@ void dropBatchGraphs(ohmb200_map *m)
   }
   m->graphs.clear();
   m->seen.clear();
+  // the recorded exchange steps bake the same things in (parameters, scratch pointers, the partition)
+  if (!m->ex.capturing)
+  {
+    for (auto &g : m->ex.graphs)
+    {
+      cudaGraphExecDestroy(g.exec);
+    }
+    m->ex.graphs.clear();
+    m->ex.seen.clear();
+  }
 }
 
 void refreshParams(ohmb200_map *m)

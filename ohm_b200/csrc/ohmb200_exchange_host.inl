@@ -481,6 +481,27 @@ int exchangeSend(ohmb200_map *m, const double *d_rays, size_t element_count, con
       x.launches_before = m->launches;
     }
   }
+  // A failure while the step is being recorded must not leave the stream in capture mode.
+  struct CaptureGuard
+  {
+    ohmb200_map *m;
+    bool armed = true;
+    ~CaptureGuard()
+    {
+      if (armed && m->ex.capturing)
+      {
+        cudaGraph_t graph = nullptr;
+        cudaStreamEndCapture(m->stream, &graph);
+        if (graph)
+        {
+          cudaGraphDestroy(graph);
+        }
+        cudaGetLastError();
+        m->ex.capturing = false;
+        m->use_graphs = false;
+      }
+    }
+  } capture_guard{ m };
   exBumpStep<<<1, 1, 0, s>>>(x.d_step);
   EX_CAPCHK(m, "bump");
   ExStep ex;
@@ -604,6 +625,7 @@ int exchangeSend(ohmb200_map *m, const double *d_rays, size_t element_count, con
   }
   CUDA_TRY(cudaGetLastError());
   x.pending = true;
+  capture_guard.armed = false;
   return OHMB200_OK;
 }
 

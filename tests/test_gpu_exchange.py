@@ -189,6 +189,13 @@ def test_exchange_steps_replayed_as_graphs(gpu):
     check_union(maps, cpu)
     st = maps[0].stats()
     assert st["batches"] == 10 and st["kernel_launches"] - before >= 10 * 10
+    # parameters changed between steps: the recorded steps bake the old ones in and must be dropped, not replayed
+    maps[0].set_params(hit_value=1.25, miss_value=-0.5)
+    cpu.set_params(hit_value=1.25, miss_value=-0.5)
+    for step in range(4):
+        gm.exchange_step(maps, [(rays, None, None)])
+        cpu.integrate_rays(rays)
+    check_union(maps, cpu)
     # a different batch after the replays: back to plain launches, same map
     other = random_rays(5000, 10.0, seed=10)
     gm.exchange_step(maps, [(other, None, None)])
