@@ -110,3 +110,19 @@ def test_reference_side_binding_defines_the_ohmgpu_classes():
     undefined = [line.split(" U ")[1] for line in out.splitlines() if " U ohmb200_" in line]
     assert "ohmb200_integrate" in undefined and "ohmb200_read_regions" in undefined  # it goes through the C ABI
     assert "cuda" not in subprocess.check_output(["ldd", path]).decode().split("libohmb200")[0].lower()
+
+
+def test_exchange_entry_points_reject_bad_arguments_without_a_gpu():
+    """The exchange ABI: argument checks come before any CUDA call (no compute here), the handle is 128 opaque bytes."""
+    lib = _lib.load()
+    assert C.sizeof(_lib.ExchangeHandle) == 128
+    handle = _lib.ExchangeHandle()
+    assert lib.ohmb200_exchange_open(None, 0, 2, 1024, C.byref(handle)) == -1
+    assert lib.ohmb200_exchange_connect(None, C.byref(handle), 1) == -1
+    assert lib.ohmb200_exchange_send(None, None, 0, None, None, 0) == 0
+    assert lib.ohmb200_exchange_send_device(None, None, 0, None, None, 0) == 0
+    assert lib.ohmb200_exchange_integrate(None) == -1
+    assert lib.ohmb200_exchange_barrier(None) == -1
+    assert lib.ohmb200_exchange_last_counts(None, None, None, 0) == -1
+    assert lib.ohmb200_exchange_close(None) == -1
+    assert b"null" in lib.ohmb200_last_error() or b"exchange" in lib.ohmb200_last_error()
